@@ -1,0 +1,147 @@
+"""TEST INFRASTRUCTURE ONLY — loads the *unmodified* reference hot path in-process.
+
+Works only where ``/root/reference`` exists (the build container).  It is used to
+ (1) pin ``oracle/ref_math.py`` (tests/test_oracle_vs_reference.py, skipped elsewhere) and
+ (2) generate the committed golden fixtures (oracle/make_golden.py).
+
+The reference's ``cross_f_box_wrapper`` transitively imports two modules whose real
+versions need detectron2 / natsort / sentence_transformers (absent here and unused by the
+live math).  They are pre-seeded in ``sys.modules`` with minimal stand-ins:
+
+  * ``modeling.commons``                       (real: modeling/commons.py:33,44)
+  * ``modeling.narration_embeds.narr_pooling_layers`` (real: narr_pooling_layers.py:23-33)
+
+No reference source is copied; the reference classes run as they are.
+"""
+from __future__ import annotations
+
+import copy
+import os
+import sys
+import types
+
+import torch
+from torch import nn
+
+REFERENCE_ROOT = os.environ.get("XF_REFERENCE_ROOT", "/root/reference")
+FUSION_YAML = "modeling/cross_fusion/ego_fusion/cross_fusion_config_sym_ego_res50.yml"
+
+
+def reference_available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, FUSION_YAML))
+
+
+def _seed_stub_modules() -> None:
+    if "modeling.commons" not in sys.modules:
+        commons = types.ModuleType("modeling.commons")
+
+        class NaoABC(nn.Module):  # stand-in for modeling/commons.py:44
+            pass
+
+        commons.NaoABC = NaoABC
+        commons.freeze_all_but_bn = lambda m: None  # modeling/commons.py:33
+        sys.modules["modeling.commons"] = commons
+    name = "modeling.narration_embeds.narr_pooling_layers"
+    if name not in sys.modules:
+        npl = types.ModuleType(name)
+        npl.get_narr_pooling_layer = lambda typ: (lambda narr_args, out_mode: nn.Identity())
+        sys.modules[name] = npl
+
+
+def import_reference_wrapper():
+    """Returns the reference ``CrossFusionBoxWrapper`` class (cross_f_box_wrapper.py:41)."""
+    if not reference_available():
+        raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    _seed_stub_modules()
+    from modeling.cross_fusion.ego_fusion.cross_f_box_wrapper import CrossFusionBoxWrapper
+
+    return CrossFusionBoxWrapper
+
+
+def load_fusion_yaml() -> dict:
+    import yaml
+
+    with open(os.path.join(REFERENCE_ROOT, FUSION_YAML)) as f:
+        return yaml.safe_load(f)
+
+
+class FakeRCNN(nn.Module):
+    """The five things ``CrossFusionBoxWrapper`` needs from ``rcnn_model``.
+
+    ``forward_features`` hands back pre-made feature maps; FPN / RPN / RoI are identity so
+    the fused feature maps are exposed directly.
+    """
+
+    def __init__(self, shapes, channels, noun_classes=129, verb_classes=82):
+        super().__init__()
+        self._shapes = list(shapes)
+        self._channels = list(channels)
+        self.noun_classes = noun_classes
+        self.verb_classes = verb_classes
+        self.features = None
+
+    def get_dsampled_shapes(self):
+        return self._shapes
+
+    def get_features_out_channels(self):
+        return self._channels
+
+    def forward_features(self, images, targets=None):
+        return {"features": dict(self.features)}
+
+    def apply_fpn(self, d):
+        return d
+
+    def apply_rpn_roi_on_features(self, d):
+        return d
+
+    def call_model_epoch_triggers(self, epoch):
+        pass
+
+
+class PassThroughPooling(nn.Module):
+    """Emulates SBertLayer's return contract (narr_pooling_layers.py:199-202)."""
+
+    def forward(self, lang, pad_mask=False):
+        emb, mask = lang
+        return emb, None, (mask if pad_mask else None)
+
+
+def build_fusion_cfg(token_dim, n_levels=4, num_layers=None, num_heads=4, patch=None,
+                     dropout=0.0, base_cfg=None) -> dict:
+    """Fusion config as ``run_experiment.update_config`` would hand it over
+    (run_experiment.py:75-77,100), with dropout probabilities overridable."""
+    cfg = copy.deepcopy(base_cfg) if base_cfg is not None else load_fusion_yaml()
+    patch = list(patch) if patch is not None else cfg["patch_h"][:n_levels]
+    cfg["patch_h"] = list(patch)
+    cfg["patch_w"] = list(patch)
+    cfg["fpn_features"] = list(range(n_levels))
+    cfg["replace_fpn_features"] = True
+    cfg["args"]["input_f_size"] = token_dim
+    cfg["args"]["num_heads"] = num_heads
+    cfg["args"]["num_layers"] = list(num_layers) if num_layers is not None else [4] * n_levels
+    cfg["args"]["patch_dropout"] = dropout if dropout == 0.0 else cfg["args"]["patch_dropout"]
+    cfg["args"]["token_dropout"] = dropout if dropout == 0.0 else cfg["args"]["token_dropout"]
+    cfg["backproj_dropout"] = dropout if dropout == 0.0 else cfg["backproj_dropout"]
+    return cfg
+
+
+def build_reference_module(cfg, shapes, channels, lm=False, seed=0,
+                           noun_classes=129, verb_classes=82):
+    """Constructs the reference wrapper under ``torch.manual_seed(seed)``."""
+    Wrapper = import_reference_wrapper()
+    torch.manual_seed(seed)
+    rcnn = FakeRCNN(shapes, channels, noun_classes, verb_classes)
+    m = Wrapper(rcnn, copy.deepcopy(cfg), {"text_pooling": "x", "train_ep": -1},
+                criterion={"lm": 1 if lm else 0})
+    m.narr_pooling_layer = PassThroughPooling()
+    return m
+
+
+def run_reference(m, features: dict, lang: torch.Tensor, att_mask: torch.Tensor):
+    """Forward of the unmodified reference.  Returns (fused feature dict, lm dict or None)."""
+    m.rcnn_model.features = features
+    out = m({"image": None, "language_f": (lang, att_mask)})
+    return out["features"], out.get("lm")

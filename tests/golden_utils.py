@@ -1,0 +1,44 @@
+"""Helpers shared by the oracle / GPU parity tests: load a golden npz (made by
+oracle/make_golden.py from the unmodified reference) into torch tensors."""
+import os
+
+import numpy as np
+import torch
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = ["fusion4_d32", "c5_d64_lm", "c4_d40_oddhead"]
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    g = {"params": {}, "pgrads": {}, "features": {}, "cot": {}, "out": {}, "gfeat": {}, "lm": {}}
+    for k in z.files:
+        v = z[k]
+        if k.startswith("param."):
+            g["params"][k[6:]] = torch.from_numpy(v.copy())
+        elif k.startswith("pgrad."):
+            g["pgrads"][k[6:]] = torch.from_numpy(v.copy())
+        elif k.startswith("in.features."):
+            g["features"][k[12:]] = torch.from_numpy(v.copy())
+        elif k.startswith("in.cotangent."):
+            g["cot"][k[13:]] = torch.from_numpy(v.copy())
+        elif k.startswith("out.features."):
+            g["out"][k[13:]] = torch.from_numpy(v.copy())
+        elif k.startswith("grad.features."):
+            g["gfeat"][k[14:]] = torch.from_numpy(v.copy())
+        elif k.startswith("out.lm."):
+            g["lm"][k[7:]] = torch.from_numpy(v.copy())
+    g["lang"] = torch.from_numpy(z["in.language_f"].copy())
+    g["att_mask"] = torch.from_numpy(z["in.att_mask"].copy())
+    g["glang"] = torch.from_numpy(z["grad.language_f"].copy())
+    g["patch"] = [int(x) for x in z["meta.patch"]]
+    g["layers"] = [int(x) for x in z["meta.layers"]]
+    g["heads"] = int(z["meta.heads"])
+    g["lm_on"] = bool(int(z["meta.lm"]))
+    return g
+
+
+def rel_fro(a, b):
+    a = a.detach().double()
+    b = b.detach().double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))

@@ -1,0 +1,64 @@
+"""CPU: the oracle restatement (oracle/ref_math.py) against golden vectors frozen from the
+unmodified reference module (oracle/make_golden.py).  fp32 tolerance: 1e-5 relative
+(north_star: "about 1e-5 relative in fp32")."""
+import pytest
+import torch
+
+from oracle import ref_math
+from tests.golden_utils import CASES, load_golden, rel_fro
+
+FP32_REL = 1e-5
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_forward_backward_matches_golden(name):
+    g = load_golden(name)
+    sd = {k: v.clone().requires_grad_(True) for k, v in g["params"].items()}
+    feats = {k: v.clone().requires_grad_(True) for k, v in g["features"].items()}
+    lang = g["lang"].clone().requires_grad_(True)
+    out, lm = ref_math.cross_fusion_forward(feats, lang, g["att_mask"], sd, g["patch"], g["heads"],
+                                            g["layers"], lm=g["lm_on"])
+    for k in out:
+        assert out[k].shape == g["out"][k].shape
+        assert rel_fro(out[k], g["out"][k]) < FP32_REL, k
+    loss = sum((out[k] * g["cot"][k]).sum() for k in out)
+    if g["lm_on"]:
+        assert rel_fro(lm["noun_logits"], g["lm"]["noun_logits"]) < FP32_REL
+        assert rel_fro(lm["verb_logits"], g["lm"]["verb_logits"]) < FP32_REL
+        loss = loss + lm["noun_logits"].sum() * 0.5 + (lm["verb_logits"] ** 2).sum() * 0.25
+    loss.backward()
+    for k in feats:
+        assert rel_fro(feats[k].grad, g["gfeat"][k]) < 5 * FP32_REL, k
+    assert rel_fro(lang.grad, g["glang"]) < 5 * FP32_REL
+    checked = 0
+    for k, gr in g["pgrads"].items():
+        assert sd[k].grad is not None, k
+        assert rel_fro(sd[k].grad, gr) < 5 * FP32_REL, k
+        checked += 1
+    assert checked > 10
+    # heatmap_token is registered but unused (cross_f_box_layers.py:43): no grad in the reference
+    for k in g["params"]:
+        if k.endswith("heatmap_token"):
+            assert k not in g["pgrads"]
+
+
+def test_sin1d_table_matches_reference_formula():
+    t = ref_math.sin1d_table(16, 8)
+    assert t.shape == (16, 8)
+    assert torch.allclose(t[0, 0::2], torch.zeros(4))
+    assert torch.allclose(t[0, 1::2], torch.ones(4))
+    assert abs(float(t[3, 0]) - 0.14112000806) < 1e-6  # sin(3)
+
+
+def test_patchify_fold_roundtrip():
+    x = torch.randn(2, 6, 8, 12)
+    for p in (1, 2, 4):
+        y = ref_math.patchify(x, p)
+        assert y.shape == (2, (8 // p) * (12 // p), 6 * p * p)
+        assert torch.equal(ref_math.fold(y, 6, p, 8 // p, 12 // p), x)
+
+
+def test_flop_formula_matches_survey():
+    shapes = [(192, 256), (96, 128), (48, 64), (24, 32)]
+    f = ref_math.algorithmic_flops_fwd(shapes, [256, 512, 1024, 2048], [4, 4, 2, 1], 896, 64, [4] * 4)
+    assert abs(f / 1e9 - 544.7) < 0.5
