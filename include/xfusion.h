@@ -1,0 +1,149 @@
+/* xfusion.h — C ABI of libxfusion_sm100a.so: hand-written sm_100a (B200) kernels for the
+ * TransFusion cross_fusion hot path (reference: modeling/cross_fusion/ego_fusion/
+ * cross_f_box_wrapper.py:165-230, cross_f_box_layers.py:69-108, torch18_adapters.py:108-113,
+ * 544-608, 789-798, modeling/cross_fusion/utils.py:35-46,114-119,209-218).
+ *
+ * The reference has no FFI (100 % Python over ATen); each entry point below replaces the
+ * ATen library calls the cited reference lines dispatch.  Conventions:
+ *   - the caller owns every buffer (device pointers + explicit shapes/strides); nothing is
+ *     allocated, nothing is synchronised: all work is enqueued on the passed stream;
+ *   - return 0 = ok, < 0 = invalid argument / unsupported shape (see xf_last_error()),
+ *     > 0 = cudaError_t;
+ *   - bf16 tensors are row-major with an explicit leading dimension in ELEMENTS;
+ *   - no torch types cross this boundary.
+ */
+#ifndef XFUSION_H_
+#define XFUSION_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* xf_stream_t; /* cudaStream_t */
+
+#define XF_ABI_VERSION 1
+
+int xf_version(void);
+const char* xf_last_error(void);
+/* number of kernel launches issued through this library since load (bench.py: gpu_launches) */
+int64_t xf_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * GEMM  D[M,N] (+)= A(M x K) * B(N x K)^T  on tcgen05 tensor cores (bf16 in, fp32 accumulate
+ * in TMEM, TMA-fed, 128 x tile_n x 64 tiles, persistent CTAs), with a fused epilogue.
+ * Replaces: nn.Conv2d patch-embed as im2col GEMM (cross_f_box_wrapper.py:268-274,183),
+ * F.linear in-proj (torch18_adapters.py:685), out_proj (:608), linear1/linear2 (:111),
+ * RegroupPatchesLayerBox.linear (utils.py:116) and their autograd backward (dgrad, wgrad).
+ *
+ * Operand storage (bf16, row-major):
+ *   a_mn_major = 0: A stored [M, K] (K contiguous)      = 1: A stored [K, M] (M contiguous)
+ *   b_mn_major = 0: B stored [N, K] (K contiguous)      = 1: B stored [K, N] (N contiguous)
+ * so  forward  y = x W^T      : a = x [M,K],  b = W [N,K]           (0,0)
+ *     wgrad    dW = dy^T x    : a = dy [tokens, N_out] (1), b = x [tokens, K_in] (1)
+ *     dgrad    dx = dy W      : a = dy [M,N_out] (0), b = W [N_out, K_in] stored [K,N] (1)
+ *
+ * Epilogue order per element (m, n):  v = acc (+ bias[n]) (+ pos_table[m % rows_in, n])
+ *   -> [drop_first: dropout] -> act / dact -> [!drop_first: dropout] -> (+ residual[m_out, n])
+ *   -> store / atomic-add to out[m_out, n],  m_out = (m / rows_in) * rows_out + m % rows_in + row_off
+ *   (rows_in = 0: m_out = m).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct XfGemm {
+  const void* a; int64_t a_ld;
+  const void* b; int64_t b_ld;
+  int32_t a_mn_major, b_mn_major;
+  int64_t M, N, K;
+  int32_t tile_n;      /* 0 = auto; else multiple of 32 in [32, 256] */
+  int32_t split_k;     /* <= 1: none; > 1 requires out_dtype = 1 and accumulate = 1 */
+  const float* bias;        /* [N] fp32 or NULL */
+  const float* pos_table;   /* [>= rows_in, N] fp32, row = m % rows_in, or NULL (utils.py:209-214) */
+  int64_t rows_in, rows_out, row_off;
+  int32_t act;              /* 0 none, 1 GELU erf (F.gelu) */
+  void* preact_out;         /* bf16, indexed like out: value before act (saved for backward), or NULL */
+  const void* dact_in;      /* bf16, indexed like out: v *= gelu'(dact_in[m,n]) (GELU backward), or NULL */
+  const void* residual;     /* bf16 [m_out, n], leading dim ldr, or NULL */
+  int64_t ldr;
+  void* out; int64_t ldc;
+  int32_t out_dtype;        /* 0 bf16, 1 fp32 */
+  int32_t accumulate;       /* 0 store, 1 fp32 atomic add into out */
+  float drop_p;             /* 0 = no dropout */
+  uint32_t drop_seed, drop_stream;
+  int32_t drop_first;
+  int32_t max_ctas;         /* 0 = one per SM */
+} XfGemm;
+
+int xf_gemm(const XfGemm* g, xf_stream_t stream);
+
+
+/* ------------------------------------------------------------------------------------------
+ * Layout passes (HBM-bound, shared-memory staged so both sides are coalesced).
+ * Token matrix T[(b,i,j), (c,u,v)] <-> feature map F[b,c,i*p+u,j*p+v].
+ * xf_patchify replaces the im2col of nn.Conv2d(k=stride=p) (cross_f_box_wrapper.py:268-274) and
+ * patchify_image(.,1,1) (utils.py:35-39); xf_fold replaces regroup_patches / F.fold
+ * (utils.py:42-46).  Each is the other's backward.  feat_dtype: 0 bf16, 1 fp32.
+ * ------------------------------------------------------------------------------------------ */
+int xf_patchify(const void* feat, int feat_dtype, void* tok_bf16, int64_t tok_ld, int B, int C, int H, int W, int p,
+                xf_stream_t stream);
+int xf_fold(const void* tok_bf16, int64_t tok_ld, void* feat, int feat_dtype, int accumulate, int B, int C, int H, int W,
+            int p, xf_stream_t stream);
+
+/* z[b, n+j, :] = bf16(lang[b,j,:] + kind[:])   (cross_f_box_layers.py:76,86) and its backward
+ * (dlang += dz rows, may be NULL; dkind += column sums). */
+int xf_lang_rows_fwd(const float* lang, const float* kind, void* z_bf16, int B, int L, int D, int n, int S, xf_stream_t stream);
+int xf_lang_rows_bwd(const void* dz_bf16, float* dlang, float* dkind, int B, int L, int D, int n, int S, xf_stream_t stream);
+
+/* LayerNorm(D, eps, affine) — norm1 / norm2 (torch18_adapters.py:110,113) and final_norm_layer
+ * (cross_f_box_layers.py:104-107).  Logical row r maps to x row / y row through the same block
+ * remap as the GEMM epilogue ((r / rows_in) * rows_out + r % rows_in + row_off; rows_in = 0: r),
+ * so the final LN reads only the visual rows of the [B,S,D] sequence.  Optional dropout on y
+ * (RegroupPatchesLayerBox.back_dropout, utils.py:115). */
+typedef struct XfLayerNorm {
+  const void* x; int64_t ldx;
+  void* y; int64_t ldy;
+  const float* gamma; const float* beta;
+  float* mean; float* rstd;          /* [rows] saved for backward, or NULL */
+  int32_t rows, D;
+  int32_t in_rows_in, in_rows_out, in_row_off;
+  int32_t out_rows_in, out_rows_out, out_row_off;
+  float eps;
+  float drop_p; uint32_t drop_seed, drop_stream;
+} XfLayerNorm;
+int xf_layernorm_fwd(const XfLayerNorm* a, xf_stream_t stream);
+
+/* LayerNorm backward: dx, dgamma += , dbeta += , optional dbias += colsum(dx2 or dx) and an optional
+ * dropout-masked copy dx2 of dx (gradient entering the linear whose output was dropped out). */
+typedef struct XfLayerNormBwd {
+  const void* dy; int64_t lddy;
+  const void* x; int64_t ldx;
+  const float* gamma; const float* mean; const float* rstd;
+  void* dx; int64_t lddx;
+  void* dx2;
+  float* dgamma; float* dbeta; float* dbias;
+  int32_t rows, D;
+  int32_t in_rows_in, in_rows_out, in_row_off;
+  int32_t out_rows_in, out_rows_out, out_row_off;
+  float dy_drop_p; uint32_t dy_drop_seed, dy_drop_stream;
+  float dx2_drop_p; uint32_t dx2_drop_seed, dx2_drop_stream;
+} XfLayerNormBwd;
+int xf_layernorm_bwd(const XfLayerNormBwd* a, xf_stream_t stream);
+
+/* out[n] += sum_m x[m,n]  (bias gradients of in_proj / linear1) */
+int xf_colsum(const void* x_bf16, int64_t ld, int rows, int cols, float* out, xf_stream_t stream);
+
+/* fp32 -> bf16 weight cast with optional block padding of rows (rin -> rout) / columns (cin -> cout):
+ * head_dim 178 -> 192 for the Ego4Dv1 shape; xf_unpad_add is the inverse for weight gradients. */
+int xf_cast_pad(const float* src, int64_t lds, void* dst_bf16, int64_t ldd, int rows, int cols, int rin, int rout, int cin,
+                int cout, xf_stream_t stream);
+int xf_unpad_add(const float* src_padded, int64_t lds, float* dst, int64_t ldd, int rows, int cols, int rin, int rout, int cin,
+                 int cout, xf_stream_t stream);
+
+/* delta[row, h] = sum_e O[row, h*dp+e] * dO[row, h*dp+e]  (attention backward pre-pass) */
+int xf_attn_delta(const void* o_bf16, const void* do_bf16, int64_t ld, int rows, int heads, int dp, float* delta,
+                  xf_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XFUSION_H_ */

@@ -1,0 +1,604 @@
+// HBM-bound kernels of the cross_fusion path: patchify / fold layout passes, language-row
+// scatter, LayerNorm forward / backward, column sums (bias grads), casts with head padding.
+// All are vectorised (128-bit where the layout allows), coalesced on both the read and the write
+// side (shared-memory staging for the layout permutations), and sized as multiples of the SM count.
+#include <string.h>
+
+#include "../../include/xfusion.h"
+#include "host_common.cuh"
+#include "ptx.cuh"
+
+namespace xf {
+
+// ------------------------------------------------------------------------------------------
+// patchify / fold.  Token matrix T[(b,i,j), (c,u,v)]  <->  feature map F[b,c,i*p+u,j*p+v]
+// (reference: nn.Conv2d(k=stride=p) im2col, cross_f_box_wrapper.py:268-274 + utils.py:35-39;
+//  inverse: utils.py:42-46 regroup_patches / F.fold).
+// A CTA moves a tile of 32 tokens (along j) x 128 columns through shared memory so that the
+// NCHW side is accessed in runs along w and the token side in runs along k.
+// ------------------------------------------------------------------------------------------
+constexpr int PF_TJ = 32;
+constexpr int PF_TK = 128;
+
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16(v); }
+
+template <typename FT, bool FOLD, bool ACC>
+__global__ void __launch_bounds__(256)
+patchify_fold_kernel(FT* __restrict__ feat, __nv_bfloat16* __restrict__ tok, int B, int Cc, int H, int W, int p,
+                     long long tok_ld) {
+  __shared__ float tile[PF_TJ][PF_TK + 1];
+  const int gh = H / p, gw = W / p;
+  const int K = Cc * p * p;
+  const int jt = (gw + PF_TJ - 1) / PF_TJ;
+  int bid = blockIdx.x;
+  const int j0 = (bid % jt) * PF_TJ; bid /= jt;
+  const int i = bid % gh; bid /= gh;
+  const int b = bid;
+  const int k0 = blockIdx.y * PF_TK;
+  const int pp = p * p;
+  const int c0 = k0 / pp;          // PF_TK is a multiple of p*p for p in {1,2,4,8}
+  const int nc = PF_TK / pp;       // channels in this tile
+  const int wrun = PF_TJ * p;      // contiguous elements along w per (c,u)
+  const long long row0 = (static_cast<long long>(b) * gh + i) * gw + j0;
+  const int total = PF_TJ * PF_TK;
+
+  if (!FOLD) {
+    for (int t = threadIdx.x; t < total; t += blockDim.x) {
+      const int wl = t % wrun;
+      const int cu = t / wrun;
+      const int u = cu % p, cl = cu / p;
+      const int jl = wl / p, v = wl - jl * p;
+      const int c = c0 + cl, j = j0 + jl;
+      float x = 0.f;
+      if (c < Cc && j < gw) x = to_f32<FT>(feat[((static_cast<long long>(b) * Cc + c) * H + i * p + u) * W + j * p + v]);
+      tile[jl][cl * pp + u * p + v] = x;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < total; t += blockDim.x) {
+      const int kl = t % PF_TK, jl = t / PF_TK;
+      if (j0 + jl < gw && k0 + kl < K) tok[(row0 + jl) * tok_ld + k0 + kl] = __float2bfloat16(tile[jl][kl]);
+    }
+  } else {
+    for (int t = threadIdx.x; t < total; t += blockDim.x) {
+      const int kl = t % PF_TK, jl = t / PF_TK;
+      float x = 0.f;
+      if (j0 + jl < gw && k0 + kl < K) x = __bfloat162float(tok[(row0 + jl) * tok_ld + k0 + kl]);
+      tile[jl][kl] = x;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < total; t += blockDim.x) {
+      const int wl = t % wrun;
+      const int cu = t / wrun;
+      const int u = cu % p, cl = cu / p;
+      const int jl = wl / p, v = wl - jl * p;
+      const int c = c0 + cl, j = j0 + jl;
+      if (c < Cc && j < gw) {
+        FT* dst = feat + ((static_cast<long long>(b) * Cc + c) * H + i * p + u) * W + j * p + v;
+        const float x = tile[jl][cl * pp + u * p + v];
+        if (ACC) *dst = from_f32<FT>(to_f32<FT>(*dst) + x);
+        else *dst = from_f32<FT>(x);
+      }
+    }
+  }
+  (void)nc;
+}
+
+// ------------------------------------------------------------------------------------------
+// language rows: z[b, n + j, :] = bf16(lang[b,j,:] + kind[:])   (cross_f_box_layers.py:76,86)
+// backward:      dlang[b,j,:] += dz[b, n+j, :] ;  dkind[:] += sum_{b,j} dz[b,n+j,:]
+// ------------------------------------------------------------------------------------------
+__global__ void lang_rows_fwd_kernel(const float* __restrict__ lang, const float* __restrict__ kind,
+                                     __nv_bfloat16* __restrict__ z, int B, int L, int D, int n, int S) {
+  const long long total = static_cast<long long>(B) * L * (D / 2);
+  for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < total;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int e2 = t % (D / 2);
+    const long long r = t / (D / 2);
+    const int j = r % L, b = r / L;
+    const float2 x = *reinterpret_cast<const float2*>(lang + r * D + 2 * e2);
+    const float2 k = *reinterpret_cast<const float2*>(kind + 2 * e2);
+    *reinterpret_cast<uint32_t*>(z + (static_cast<long long>(b) * S + n + j) * D + 2 * e2) = pack_bf16(x.x + k.x, x.y + k.y);
+  }
+}
+
+__global__ void lang_rows_bwd_kernel(const __nv_bfloat16* __restrict__ dz, float* __restrict__ dlang,
+                                     float* __restrict__ dkind, int B, int L, int D, int n, int S) {
+  // one thread per column pair; loops over all (b, j) rows (B*L is small)
+  const int e2 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e2 >= D / 2) return;
+  float s0 = 0.f, s1 = 0.f;
+  for (int r = blockIdx.y; r < B * L; r += gridDim.y) {
+    const int j = r % L, b = r / L;
+    const uint32_t q = *reinterpret_cast<const uint32_t*>(dz + (static_cast<long long>(b) * S + n + j) * D + 2 * e2);
+    const float g0 = bf16_lo(q), g1 = bf16_hi(q);
+    if (dlang) {
+      float* d = dlang + static_cast<long long>(r) * D + 2 * e2;
+      d[0] += g0; d[1] += g1;
+    }
+    s0 += g0; s1 += g1;
+  }
+  atomicAdd(dkind + 2 * e2, s0);
+  atomicAdd(dkind + 2 * e2 + 1, s1);
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm over the last dim (eps 1e-5, affine), one warp per row, row cached in registers.
+//   y[orow] = (x[irow] - mean) * rstd * gamma + beta ;  irow / orow support the same block remap
+//   as the GEMM epilogue so the final LN reads only the visual rows of z (cross_f_box_layers.py:
+//   104-107) and writes a compact [B*n, D] matrix.
+// ------------------------------------------------------------------------------------------
+constexpr int LN_MAXV = 8;  // up to 8 x (32 lanes x 8 elements) = 2048 columns
+
+struct LnParams {
+  const __nv_bfloat16* x; long long ldx;
+  __nv_bfloat16* y; long long ldy;
+  const float* gamma; const float* beta;
+  float* mean; float* rstd;   // [rows], indexed by logical row
+  int rows, D;
+  int in_rows_in, in_rows_out, in_row_off;     // logical row r -> x row
+  int out_rows_in, out_rows_out, out_row_off;  // logical row r -> y row
+  float eps;
+  // dropout on the output (backproj_dropout, utils.py:115)
+  float drop_p; uint32_t drop_seed, drop_stream, drop_thresh; float drop_scale;
+};
+
+__device__ __forceinline__ long long remap_row(int r, int rin, int rout, int off) {
+  if (rin <= 0) return r;
+  const int g = r / rin;
+  return static_cast<long long>(g) * rout + (r - g * rin) + off;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const LnParams p) {
+  const int warps_per_cta = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nvec = p.D >> 3;
+  for (int r = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); r < p.rows; r += gridDim.x * warps_per_cta) {
+    const __nv_bfloat16* xr = p.x + remap_row(r, p.in_rows_in, p.in_rows_out, p.in_row_off) * p.ldx;
+    uint4 q[LN_MAXV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int vidx = lane + 32 * i;
+      if (vidx < nvec) {
+        q[i] = __ldg(reinterpret_cast<const uint4*>(xr) + vidx);
+        s += bf16_lo(q[i].x) + bf16_hi(q[i].x) + bf16_lo(q[i].y) + bf16_hi(q[i].y) + bf16_lo(q[i].z) + bf16_hi(q[i].z) +
+             bf16_lo(q[i].w) + bf16_hi(q[i].w);
+      }
+    }
+    const float mean = warp_sum(s) / p.D;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int vidx = lane + 32 * i;
+      if (vidx < nvec) {
+        const uint32_t w[4] = {q[i].x, q[i].y, q[i].z, q[i].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float a = bf16_lo(w[k]) - mean, b = bf16_hi(w[k]) - mean;
+          ss += a * a + b * b;
+        }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(ss) / p.D + p.eps);
+    if (lane == 0 && p.mean) { p.mean[r] = mean; p.rstd[r] = rstd; }
+    const long long orow = remap_row(r, p.out_rows_in, p.out_rows_out, p.out_row_off);
+    __nv_bfloat16* yr = p.y + orow * p.ldy;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int vidx = lane + 32 * i;
+      if (vidx < nvec) {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma) + 2 * vidx);
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gamma) + 2 * vidx + 1);
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta) + 2 * vidx);
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.beta) + 2 * vidx + 1);
+        float o[8];
+        o[0] = (bf16_lo(q[i].x) - mean) * rstd * g0.x + b0.x;
+        o[1] = (bf16_hi(q[i].x) - mean) * rstd * g0.y + b0.y;
+        o[2] = (bf16_lo(q[i].y) - mean) * rstd * g0.z + b0.z;
+        o[3] = (bf16_hi(q[i].y) - mean) * rstd * g0.w + b0.w;
+        o[4] = (bf16_lo(q[i].z) - mean) * rstd * g1.x + b1.x;
+        o[5] = (bf16_hi(q[i].z) - mean) * rstd * g1.y + b1.y;
+        o[6] = (bf16_lo(q[i].w) - mean) * rstd * g1.z + b1.z;
+        o[7] = (bf16_hi(q[i].w) - mean) * rstd * g1.w + b1.w;
+        if (p.drop_p > 0.f) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            o[k] = dropout_keep(p.drop_seed, p.drop_stream, static_cast<uint64_t>(orow * p.ldy + vidx * 8 + k), p.drop_thresh)
+                       ? o[k] * p.drop_scale : 0.f;
+        }
+        *(reinterpret_cast<uint4*>(yr) + vidx) =
+            make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+      }
+    }
+  }
+}
+
+// LayerNorm backward.  dx = rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy * gamma.
+// Also: dgamma += sum dy*xhat, dbeta += sum dy (fp32 atomics, one per column per CTA) and, optionally,
+// colsum(dx) (= bias grad of the linear that produced the pre-LN sum) and a second output
+// dx2 = dropout-masked copy of dx (gradient flowing into that linear when dropout1/2 are on).
+struct LnBwdParams {
+  const __nv_bfloat16* dy; long long lddy;     // indexed by "out" remap of the forward
+  const __nv_bfloat16* x; long long ldx;       // forward input (pre-LN), "in" remap
+  const float* gamma; const float* mean; const float* rstd;
+  __nv_bfloat16* dx; long long lddx;           // "in" remap
+  __nv_bfloat16* dx2;                          // optional, same indexing as dx
+  float* dgamma; float* dbeta; float* dbias;   // [D] fp32, atomically accumulated; dbias optional
+  int rows, D;
+  int in_rows_in, in_rows_out, in_row_off;
+  int out_rows_in, out_rows_out, out_row_off;
+  // dropout applied to the forward LN output (mask on dy) and/or to the branch that fed the LN input (dx2)
+  float dy_drop_p; uint32_t dy_seed, dy_stream, dy_thresh; float dy_scale;
+  float dx2_drop_p; uint32_t dx2_seed, dx2_stream, dx2_thresh; float dx2_scale;
+};
+
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const LnBwdParams p) {
+  extern __shared__ float red[];  // [3][warps][D] would be large; instead reduce with atomics per CTA via smem [3][D]
+  const int warps_per_cta = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nvec = p.D >> 3;
+  float* s_dg = red;
+  float* s_db = red + p.D;
+  float* s_dbias = red + 2 * p.D;
+  for (int i = threadIdx.x; i < 3 * p.D; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+
+  float acc_dg[LN_MAXV][8], acc_db[LN_MAXV][8], acc_dbias[LN_MAXV][8];
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc_dg[i][k] = acc_db[i][k] = acc_dbias[i][k] = 0.f;
+
+  for (int r = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); r < p.rows; r += gridDim.x * warps_per_cta) {
+    const long long irow = remap_row(r, p.in_rows_in, p.in_rows_out, p.in_row_off);
+    const long long orow = remap_row(r, p.out_rows_in, p.out_rows_out, p.out_row_off);
+    const __nv_bfloat16* xr = p.x + irow * p.ldx;
+    const __nv_bfloat16* dyr = p.dy + orow * p.lddy;
+    const float mean = p.mean[r], rstd = p.rstd[r];
+    float xh[LN_MAXV][8], g[LN_MAXV][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int vidx = lane + 32 * i;
+      if (vidx < nvec) {
+        const uint4 qx = __ldg(reinterpret_cast<const uint4*>(xr) + vidx);
+        const uint4 qd = __ldg(reinterpret_cast<const uint4*>(dyr) + vidx);
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma) + 2 * vidx);
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gamma) + 2 * vidx + 1);
+        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const uint32_t wx[4] = {qx.x, qx.y, qx.z, qx.w};
+        const uint32_t wd[4] = {qd.x, qd.y, qd.z, qd.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float d0 = bf16_lo(wd[k]), d1 = bf16_hi(wd[k]);
+          if (p.dy_drop_p > 0.f) {
+            d0 = dropout_keep(p.dy_seed, p.dy_stream, static_cast<uint64_t>(orow * p.lddy + vidx * 8 + 2 * k), p.dy_thresh) ? d0 * p.dy_scale : 0.f;
+            d1 = dropout_keep(p.dy_seed, p.dy_stream, static_cast<uint64_t>(orow * p.lddy + vidx * 8 + 2 * k + 1), p.dy_thresh) ? d1 * p.dy_scale : 0.f;
+          }
+          const float x0 = (bf16_lo(wx[k]) - mean) * rstd, x1 = (bf16_hi(wx[k]) - mean) * rstd;
+          xh[i][2 * k] = x0; xh[i][2 * k + 1] = x1;
+          g[i][2 * k] = d0 * gm[2 * k]; g[i][2 * k + 1] = d1 * gm[2 * k + 1];
+          acc_dg[i][2 * k] += d0 * x0; acc_dg[i][2 * k + 1] += d1 * x1;
+          acc_db[i][2 * k] += d0; acc_db[i][2 * k + 1] += d1;
+          s1 += g[i][2 * k] + g[i][2 * k + 1];
+          s2 += g[i][2 * k] * x0 + g[i][2 * k + 1] * x1;
+        }
+      }
+    }
+    s1 = warp_sum(s1) / p.D;
+    s2 = warp_sum(s2) / p.D;
+    __nv_bfloat16* dxr = p.dx + irow * p.lddx;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+      const int vidx = lane + 32 * i;
+      if (vidx < nvec) {
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          o[k] = rstd * (g[i][k] - s1 - xh[i][k] * s2);
+          // bias grad of the producing linear sees the (dropout-masked) gradient
+        }
+        *(reinterpret_cast<uint4*>(dxr) + vidx) =
+            make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+        if (p.dx2) {
+          float o2[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            o2[k] = o[k];
+            if (p.dx2_drop_p > 0.f)
+              o2[k] = dropout_keep(p.dx2_seed, p.dx2_stream, static_cast<uint64_t>(irow * p.lddx + vidx * 8 + k), p.dx2_thresh) ? o[k] * p.dx2_scale : 0.f;
+            acc_dbias[i][k] += o2[k];
+          }
+          *(reinterpret_cast<uint4*>(p.dx2 + irow * p.lddx) + vidx) =
+              make_uint4(pack_bf16(o2[0], o2[1]), pack_bf16(o2[2], o2[3]), pack_bf16(o2[4], o2[5]), pack_bf16(o2[6], o2[7]));
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc_dbias[i][k] += o[k];
+        }
+      }
+    }
+  }
+  // CTA-level reduction in shared memory, then one global atomic per column per CTA
+#pragma unroll
+  for (int i = 0; i < LN_MAXV; ++i) {
+    const int vidx = lane + 32 * i;
+    if (vidx < nvec) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        atomicAdd(&s_dg[vidx * 8 + k], acc_dg[i][k]);
+        atomicAdd(&s_db[vidx * 8 + k], acc_db[i][k]);
+        if (p.dbias) atomicAdd(&s_dbias[vidx * 8 + k], acc_dbias[i][k]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < p.D; i += blockDim.x) {
+    atomicAdd(p.dgamma + i, s_dg[i]);
+    atomicAdd(p.dbeta + i, s_db[i]);
+    if (p.dbias) atomicAdd(p.dbias + i, s_dbias[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// column sums: out[n] += sum_m x[m, n]  (bias gradients of in_proj and linear1)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+colsum_kernel(const __nv_bfloat16* __restrict__ x, long long ld, int rows, int cols, int rows_per_cta, float* __restrict__ out) {
+  const int vc = blockIdx.x * blockDim.x + threadIdx.x;  // 8-column vector index
+  if (vc * 8 >= cols) return;
+  const int r0 = blockIdx.y * rows_per_cta;
+  const int r1 = min(rows, r0 + rows_per_cta);
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int r = r0; r < r1; ++r) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(x + static_cast<long long>(r) * ld) + vc);
+    s[0] += bf16_lo(q.x); s[1] += bf16_hi(q.x); s[2] += bf16_lo(q.y); s[3] += bf16_hi(q.y);
+    s[4] += bf16_lo(q.z); s[5] += bf16_hi(q.z); s[6] += bf16_lo(q.w); s[7] += bf16_hi(q.w);
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if (vc * 8 + k < cols) atomicAdd(out + vc * 8 + k, s[k]);
+}
+
+// ------------------------------------------------------------------------------------------
+// cast fp32 [rows, cols] -> bf16 with optional row / column block padding
+// (src block of `rin` rows -> dst block of `rout` rows; same for columns), and the inverse
+// (fp32 padded -> fp32 compact, accumulate) used to un-pad weight gradients.
+// ------------------------------------------------------------------------------------------
+__global__ void cast_pad_kernel(const float* __restrict__ src, long long lds, __nv_bfloat16* __restrict__ dst, long long ldd,
+                                int rows, int cols, int rin, int rout, int cin, int cout) {
+  const long long total = static_cast<long long>(rows) * cols;
+  for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < total;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = t % cols;
+    const int r = t / cols;
+    const long long dr = rin > 0 ? static_cast<long long>(r / rin) * rout + r % rin : r;
+    const long long dc = cin > 0 ? static_cast<long long>(c / cin) * cout + c % cin : c;
+    dst[dr * ldd + dc] = __float2bfloat16(src[static_cast<long long>(r) * lds + c]);
+  }
+}
+
+__global__ void unpad_add_kernel(const float* __restrict__ src, long long lds, float* __restrict__ dst, long long ldd,
+                                 int rows, int cols, int rin, int rout, int cin, int cout) {
+  // dst is compact [rows, cols]; src is padded
+  const long long total = static_cast<long long>(rows) * cols;
+  for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < total;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = t % cols;
+    const int r = t / cols;
+    const long long sr = rin > 0 ? static_cast<long long>(r / rin) * rout + r % rin : r;
+    const long long sc = cin > 0 ? static_cast<long long>(c / cin) * cout + c % cin : c;
+    dst[static_cast<long long>(r) * ldd + c] += src[sr * lds + sc];
+  }
+}
+
+// delta[row, h] = sum_e O[row, h*dp + e] * dO[row, h*dp + e]   (attention backward pre-pass)
+__global__ void __launch_bounds__(256)
+attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o, long long ld, int rows,
+                  int heads, int dp, float* __restrict__ delta) {
+  const int warps_per_cta = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long total = static_cast<long long>(rows) * heads;
+  for (long long w = blockIdx.x * static_cast<long long>(warps_per_cta) + (threadIdx.x >> 5); w < total;
+       w += static_cast<long long>(gridDim.x) * warps_per_cta) {
+    const int h = w % heads;
+    const long long r = w / heads;
+    const __nv_bfloat16* po = o + r * ld + h * dp;
+    const __nv_bfloat16* pd = d_o + r * ld + h * dp;
+    float s = 0.f;
+    for (int e = lane * 2; e < dp; e += 64) {
+      const uint32_t a = *reinterpret_cast<const uint32_t*>(po + e);
+      const uint32_t b = *reinterpret_cast<const uint32_t*>(pd + e);
+      s += bf16_lo(a) * bf16_lo(b) + bf16_hi(a) * bf16_hi(b);
+    }
+    s = warp_sum(s);
+    if (lane == 0) delta[w] = s;
+  }
+}
+
+static inline int grid_for(long long work_items, int per_cta, int waves = 8) {
+  long long ctas = (work_items + per_cta - 1) / per_cta;
+  long long cap = static_cast<long long>(sm_count()) * waves;
+  if (ctas > cap) ctas = cap;
+  if (ctas < 1) ctas = 1;
+  return static_cast<int>(ctas);
+}
+
+}  // namespace xf
+
+using namespace xf;
+
+extern "C" int xf_patchify(const void* feat, int feat_dtype, void* tok, int64_t tok_ld, int B, int C, int H, int W, int p,
+                           xf_stream_t s) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(s);
+  if (!feat || !tok) return fail(-1, "xf_patchify: null pointer");
+  if (p <= 0 || PF_TK % (p * p) != 0 || H % p || W % p) return fail(-2, "xf_patchify: unsupported patch %d for %dx%d", p, H, W);
+  const int gh = H / p, gw = W / p, K = C * p * p;
+  dim3 grid(B * gh * ((gw + PF_TJ - 1) / PF_TJ), (K + PF_TK - 1) / PF_TK);
+  if (feat_dtype == 1)
+    patchify_fold_kernel<float, false, false><<<grid, 256, 0, stream>>>(const_cast<float*>(reinterpret_cast<const float*>(feat)),
+                                                                        reinterpret_cast<__nv_bfloat16*>(tok), B, C, H, W, p, tok_ld);
+  else if (feat_dtype == 0)
+    patchify_fold_kernel<__nv_bfloat16, false, false><<<grid, 256, 0, stream>>>(
+        const_cast<__nv_bfloat16*>(reinterpret_cast<const __nv_bfloat16*>(feat)), reinterpret_cast<__nv_bfloat16*>(tok), B, C, H, W, p, tok_ld);
+  else return fail(-3, "xf_patchify: bad dtype");
+  g_launches.fetch_add(1);
+  XF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int xf_fold(const void* tok, int64_t tok_ld, void* feat, int feat_dtype, int accumulate, int B, int C, int H, int W,
+                       int p, xf_stream_t s) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(s);
+  if (!feat || !tok) return fail(-1, "xf_fold: null pointer");
+  if (p <= 0 || PF_TK % (p * p) != 0 || H % p || W % p) return fail(-2, "xf_fold: unsupported patch %d for %dx%d", p, H, W);
+  const int gh = H / p, gw = W / p, K = C * p * p;
+  dim3 grid(B * gh * ((gw + PF_TJ - 1) / PF_TJ), (K + PF_TK - 1) / PF_TK);
+  __nv_bfloat16* t = const_cast<__nv_bfloat16*>(reinterpret_cast<const __nv_bfloat16*>(tok));
+  if (feat_dtype == 1) {
+    if (accumulate) patchify_fold_kernel<float, true, true><<<grid, 256, 0, stream>>>(reinterpret_cast<float*>(feat), t, B, C, H, W, p, tok_ld);
+    else patchify_fold_kernel<float, true, false><<<grid, 256, 0, stream>>>(reinterpret_cast<float*>(feat), t, B, C, H, W, p, tok_ld);
+  } else if (feat_dtype == 0) {
+    if (accumulate) patchify_fold_kernel<__nv_bfloat16, true, true><<<grid, 256, 0, stream>>>(reinterpret_cast<__nv_bfloat16*>(feat), t, B, C, H, W, p, tok_ld);
+    else patchify_fold_kernel<__nv_bfloat16, true, false><<<grid, 256, 0, stream>>>(reinterpret_cast<__nv_bfloat16*>(feat), t, B, C, H, W, p, tok_ld);
+  } else return fail(-3, "xf_fold: bad dtype");
+  g_launches.fetch_add(1);
+  XF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int xf_lang_rows_fwd(const float* lang, const float* kind, void* z, int B, int L, int D, int n, int S, xf_stream_t s) {
+  if (!lang || !kind || !z) return fail(-1, "xf_lang_rows_fwd: null pointer");
+  if (D % 2) return fail(-2, "xf_lang_rows_fwd: D must be even");
+  if (B * L == 0) return 0;
+  lang_rows_fwd_kernel<<<grid_for(static_cast<long long>(B) * L * D / 2, 256), 256, 0, reinterpret_cast<cudaStream_t>(s)>>>(
+      lang, kind, reinterpret_cast<__nv_bfloat16*>(z), B, L, D, n, S);
+  g_launches.fetch_add(1);
+  XF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int xf_lang_rows_bwd(const void* dz, float* dlang, float* dkind, int B, int L, int D, int n, int S, xf_stream_t s) {
+  if (!dz || !dkind) return fail(-1, "xf_lang_rows_bwd: null pointer");
+  if (D % 2) return fail(-2, "xf_lang_rows_bwd: D must be even");
+  if (B * L == 0) return 0;
+  // gridDim.y = 1 when dlang is written (each (row, col) must be owned by exactly one thread)
+  dim3 grid((D / 2 + 127) / 128, 1);
+  lang_rows_bwd_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(s)>>>(reinterpret_cast<const __nv_bfloat16*>(dz), dlang, dkind, B, L, D, n, S);
+  g_launches.fetch_add(1);
+  XF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int xf_layernorm_fwd(const XfLayerNorm* a, xf_stream_t s) {
+  if (!a || !a->x || !a->y || !a->gamma || !a->beta) return fail(-1, "xf_layernorm_fwd: null pointer");
+  if (a->D % 8 || a->D > LN_MAXV * 256) return fail(-2, "xf_layernorm_fwd: D=%d must be a multiple of 8 and <= %d", a->D, LN_MAXV * 256);
+  if ((a->ldx % 8) || (a->ldy % 8)) return fail(-3, "xf_layernorm_fwd: leading dims must be multiples of 8");
+  if (a->rows == 0) return 0;
+  LnParams p;
+  memset(&p, 0, sizeof(p));
+  p.x = reinterpret_cast<const __nv_bfloat16*>(a->x); p.ldx = a->ldx;
+  p.y = reinterpret_cast<__nv_bfloat16*>(a->y); p.ldy = a->ldy;
+  p.gamma = a->gamma; p.beta = a->beta; p.mean = a->mean; p.rstd = a->rstd;
+  p.rows = a->rows; p.D = a->D;
+  p.in_rows_in = a->in_rows_in; p.in_rows_out = a->in_rows_out; p.in_row_off = a->in_row_off;
+  p.out_rows_in = a->out_rows_in; p.out_rows_out = a->out_rows_out; p.out_row_off = a->out_row_off;
+  p.eps = a->eps;
+  p.drop_p = a->drop_p; p.drop_seed = a->drop_seed; p.drop_stream = a->drop_stream;
+  p.drop_thresh = static_cast<uint32_t>(static_cast<double>(a->drop_p) * 4294967296.0);
+  p.drop_scale = a->drop_p > 0.f ? 1.f / (1.f - a->drop_p) : 1.f;
+  layernorm_fwd_kernel<<<grid_for(a->rows, 8), 256, 0, reinterpret_cast<cudaStream_t>(s)>>>(p);
+  g_launches.fetch_add(1);
+  XF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int xf_layernorm_bwd(const XfLayerNormBwd* a, xf_stream_t s) {
+  if (!a || !a->dy || !a->x || !a->gamma || !a->mean || !a->rstd || !a->dx || !a->dgamma || !a->dbeta)
+    return fail(-1, "xf_layernorm_bwd: null pointer");
+  if (a->D % 8 || a->D > LN_MAXV * 256) return fail(-2, "xf_layernorm_bwd: D=%d must be a multiple of 8 and <= %d", a->D, LN_MAXV * 256);
+  if ((a->ldx % 8) || (a->lddy % 8) || (a->lddx % 8)) return fail(-3, "xf_layernorm_bwd: leading dims must be multiples of 8");
+  if (a->rows == 0) return 0;
+  LnBwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.dy = reinterpret_cast<const __nv_bfloat16*>(a->dy); p.lddy = a->lddy;
+  p.x = reinterpret_cast<const __nv_bfloat16*>(a->x); p.ldx = a->ldx;
+  p.gamma = a->gamma; p.mean = a->mean; p.rstd = a->rstd;
+  p.dx = reinterpret_cast<__nv_bfloat16*>(a->dx); p.lddx = a->lddx;
+  p.dx2 = reinterpret_cast<__nv_bfloat16*>(a->dx2);
+  p.dgamma = a->dgamma; p.dbeta = a->dbeta; p.dbias = a->dbias;
+  p.rows = a->rows; p.D = a->D;
+  p.in_rows_in = a->in_rows_in; p.in_rows_out = a->in_rows_out; p.in_row_off = a->in_row_off;
+  p.out_rows_in = a->out_rows_in; p.out_rows_out = a->out_rows_out; p.out_row_off = a->out_row_off;
+  p.dy_drop_p = a->dy_drop_p; p.dy_seed = a->dy_drop_seed; p.dy_stream = a->dy_drop_stream;
+  p.dy_thresh = static_cast<uint32_t>(static_cast<double>(a->dy_drop_p) * 4294967296.0);
+  p.dy_scale = a->dy_drop_p > 0.f ? 1.f / (1.f - a->dy_drop_p) : 1.f;
+  p.dx2_drop_p = a->dx2_drop_p; p.dx2_seed = a->dx2_drop_seed; p.dx2_stream = a->dx2_drop_stream;
+  p.dx2_thresh = static_cast<uint32_t>(static_cast<double>(a->dx2_drop_p) * 4294967296.0);
+  p.dx2_scale = a->dx2_drop_p > 0.f ? 1.f / (1.f - a->dx2_drop_p) : 1.f;
+  const int ctas = grid_for(a->rows, 8 * 16, 2);  // >= 16 rows per warp so the per-CTA column atomics amortise
+  layernorm_bwd_kernel<<<ctas, 256, 3 * a->D * sizeof(float), reinterpret_cast<cudaStream_t>(s)>>>(p);
+  g_launches.fetch_add(1);
+  XF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int xf_colsum(const void* x, int64_t ld, int rows, int cols, float* out, xf_stream_t s) {
+  if (!x || !out) return fail(-1, "xf_colsum: null pointer");
+  if (cols % 8 || ld % 8) return fail(-2, "xf_colsum: cols and ld must be multiples of 8");
+  if (rows == 0) return 0;
+  const int vcols = cols / 8;
+  const int gx = (vcols + 255) / 256;
+  int gy = (2 * sm_count() + gx - 1) / gx;
+  if (gy > rows) gy = rows;
+  const int rows_per_cta = (rows + gy - 1) / gy;
+  gy = (rows + rows_per_cta - 1) / rows_per_cta;
+  colsum_kernel<<<dim3(gx, gy), 256, 0, reinterpret_cast<cudaStream_t>(s)>>>(reinterpret_cast<const __nv_bfloat16*>(x), ld, rows, cols,
+                                                                            rows_per_cta, out);
+  g_launches.fetch_add(1);
+  XF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int xf_cast_pad(const float* src, int64_t lds, void* dst, int64_t ldd, int rows, int cols, int rin, int rout, int cin,
+                           int cout, xf_stream_t s) {
+  if (!src || !dst) return fail(-1, "xf_cast_pad: null pointer");
+  if (rows == 0 || cols == 0) return 0;
+  cast_pad_kernel<<<grid_for(static_cast<long long>(rows) * cols, 256 * 4), 256, 0, reinterpret_cast<cudaStream_t>(s)>>>(
+      src, lds, reinterpret_cast<__nv_bfloat16*>(dst), ldd, rows, cols, rin, rout, cin, cout);
+  g_launches.fetch_add(1);
+  XF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int xf_unpad_add(const float* src, int64_t lds, float* dst, int64_t ldd, int rows, int cols, int rin, int rout, int cin,
+                            int cout, xf_stream_t s) {
+  if (!src || !dst) return fail(-1, "xf_unpad_add: null pointer");
+  if (rows == 0 || cols == 0) return 0;
+  unpad_add_kernel<<<grid_for(static_cast<long long>(rows) * cols, 256 * 4), 256, 0, reinterpret_cast<cudaStream_t>(s)>>>(
+      src, lds, dst, ldd, rows, cols, rin, rout, cin, cout);
+  g_launches.fetch_add(1);
+  XF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int xf_attn_delta(const void* o, const void* d_o, int64_t ld, int rows, int heads, int dp, float* delta, xf_stream_t s) {
+  if (!o || !d_o || !delta) return fail(-1, "xf_attn_delta: null pointer");
+  if (dp % 2) return fail(-2, "xf_attn_delta: dp must be even");
+  if (rows == 0) return 0;
+  attn_delta_kernel<<<grid_for(static_cast<long long>(rows) * heads, 8), 256, 0, reinterpret_cast<cudaStream_t>(s)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(o), reinterpret_cast<const __nv_bfloat16*>(d_o), ld, rows, heads, dp, delta);
+  g_launches.fetch_add(1);
+  XF_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,439 @@
+// xf_gemm: persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   D[M,N] (+)= A(M x K) * B(N x K)^T,  bf16 operands, fp32 accumulation in TMEM.
+//
+// CTA = 192 threads: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2..5 =
+// epilogue (one TMEM lane quadrant each).  Tile = 128 x tile_n x 64; operands are staged by TMA
+// into a ring of SWIZZLE_128B shared-memory stages; tcgen05.mma (M=128, N=tile_n, K=16) reads them
+// through shared-memory descriptors in either K-major or MN-major form, so forward (x W^T), dgrad
+// (dy W) and wgrad (dy^T x) all run on the same kernel without materialised transposes.  The
+// accumulator is double-buffered in TMEM (2 x tile_n columns) so the epilogue of tile i overlaps the
+// MMAs of tile i+1.  Work items (m-tile, n-tile, k-split) are distributed round-robin over a
+// persistent grid of one CTA per SM.
+//
+// Shared-memory stage layout (all atoms 1024-byte aligned):
+//   A: K-major  -> one TMA box {64 k, 128 rows}            = 128 rows x 128 B
+//      MN-major -> two TMA boxes {64 m, 64 k}, 8 KB apart  = chunk c holds m in [64c, 64c+64)
+//   B: K-major  -> one TMA box {64 k, tile_n rows}
+//      MN-major -> ceil(tile_n/64) TMA boxes {64 n, 64 k}, 8 KB apart
+#include "../../include/xfusion.h"
+#include "host_common.cuh"
+#include "ptx.cuh"
+#include <string.h>
+
+namespace xf {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
+constexpr int GEMM_SMEM_BUDGET = 200 * 1024;         // stage ring budget
+
+struct GemmParams {
+  int M, N, K;
+  int tile_n;
+  int a_mn, b_mn;
+  int num_m_tiles, num_n_tiles, split_k, kb_per_split, total_kb;
+  int stages, b_bytes, stage_bytes;
+  // epilogue
+  const float* bias;
+  const float* pos_table;
+  int rows_in, rows_out, row_off;
+  int act;
+  __nv_bfloat16* preact_out;
+  const __nv_bfloat16* dact_in;
+  const __nv_bfloat16* residual;
+  long long ldr;
+  void* out;
+  long long ldc;
+  int out_f32, accumulate, vec_ok;
+  float drop_p;
+  uint32_t drop_seed, drop_stream, drop_thresh;
+  float drop_scale;
+  int drop_first;
+};
+
+__device__ __forceinline__ void decode_item(const GemmParams& p, int item, int& mt, int& nt, int& kb0, int& nkb) {
+  nt = item % p.num_n_tiles;
+  int r = item / p.num_n_tiles;
+  int ks = r % p.split_k;
+  mt = r / p.split_k;
+  kb0 = ks * p.kb_per_split;
+  int kb1 = min(p.total_kb, kb0 + p.kb_per_split);
+  nkb = max(0, kb1 - kb0);
+}
+
+// One 32-column chunk of one accumulator row.
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int m, int n0, uint32_t (&acc)[32]) {
+  if (m >= p.M) return;
+  int m_out = m, m_in = m;
+  if (p.rows_in > 0) {
+    int g = m / p.rows_in;
+    m_in = m - g * p.rows_in;
+    m_out = g * p.rows_out + m_in + p.row_off;
+  }
+  const bool full = (n0 + 32 <= p.N);
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(acc[i]);
+
+  if (p.bias) {
+    if (full) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + i));
+        v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (n0 + i < p.N) v[i] += __ldg(p.bias + n0 + i);
+    }
+  }
+  if (p.pos_table) {
+    const float* pt = p.pos_table + static_cast<long long>(m_in) * p.N + n0;
+    if (full && p.vec_ok) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        float4 b = __ldg(reinterpret_cast<const float4*>(pt + i));
+        v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (n0 + i < p.N) v[i] += __ldg(pt + i);
+    }
+  }
+  const long long orow = static_cast<long long>(m_out) * p.ldc + n0;
+  if (p.drop_p > 0.f && p.drop_first) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      v[i] = dropout_keep(p.drop_seed, p.drop_stream, static_cast<uint64_t>(orow + i), p.drop_thresh) ? v[i] * p.drop_scale : 0.f;
+  }
+  if (p.act == 1) {
+    if (p.preact_out) {
+      __nv_bfloat16* po = p.preact_out + orow;
+      if (full && p.vec_ok) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint4 q = make_uint4(pack_bf16(v[i], v[i + 1]), pack_bf16(v[i + 2], v[i + 3]), pack_bf16(v[i + 4], v[i + 5]),
+                               pack_bf16(v[i + 6], v[i + 7]));
+          *reinterpret_cast<uint4*>(po + i) = q;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (n0 + i < p.N) po[i] = __float2bfloat16(v[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+  }
+  if (p.dact_in) {
+    const __nv_bfloat16* di = p.dact_in + orow;
+    if (full && p.vec_ok) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        uint4 q = __ldg(reinterpret_cast<const uint4*>(di + i));
+        v[i] *= gelu_erf_grad(bf16_lo(q.x)); v[i + 1] *= gelu_erf_grad(bf16_hi(q.x));
+        v[i + 2] *= gelu_erf_grad(bf16_lo(q.y)); v[i + 3] *= gelu_erf_grad(bf16_hi(q.y));
+        v[i + 4] *= gelu_erf_grad(bf16_lo(q.z)); v[i + 5] *= gelu_erf_grad(bf16_hi(q.z));
+        v[i + 6] *= gelu_erf_grad(bf16_lo(q.w)); v[i + 7] *= gelu_erf_grad(bf16_hi(q.w));
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (n0 + i < p.N) v[i] *= gelu_erf_grad(__bfloat162float(di[i]));
+    }
+  }
+  if (p.drop_p > 0.f && !p.drop_first) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      v[i] = dropout_keep(p.drop_seed, p.drop_stream, static_cast<uint64_t>(orow + i), p.drop_thresh) ? v[i] * p.drop_scale : 0.f;
+  }
+  if (p.residual) {
+    const __nv_bfloat16* rs = p.residual + static_cast<long long>(m_out) * p.ldr + n0;
+    if (full && p.vec_ok) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        uint4 q = __ldg(reinterpret_cast<const uint4*>(rs + i));
+        v[i] += bf16_lo(q.x); v[i + 1] += bf16_hi(q.x); v[i + 2] += bf16_lo(q.y); v[i + 3] += bf16_hi(q.y);
+        v[i + 4] += bf16_lo(q.z); v[i + 5] += bf16_hi(q.z); v[i + 6] += bf16_lo(q.w); v[i + 7] += bf16_hi(q.w);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (n0 + i < p.N) v[i] += __bfloat162float(rs[i]);
+    }
+  }
+  if (p.out_f32) {
+    float* o = reinterpret_cast<float*>(p.out) + orow;
+    if (p.accumulate) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (n0 + i < p.N) atomicAdd(o + i, v[i]);
+    } else if (full && p.vec_ok) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (n0 + i < p.N) o[i] = v[i];
+    }
+  } else {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + orow;
+    if (full && p.vec_ok) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        uint4 q = make_uint4(pack_bf16(v[i], v[i + 1]), pack_bf16(v[i + 2], v[i + 3]), pack_bf16(v[i + 4], v[i + 5]),
+                             pack_bf16(v[i + 6], v[i + 7]));
+        *reinterpret_cast<uint4*>(o + i) = q;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (n0 + i < p.N) o[i] = __float2bfloat16(v[i]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // control block: barriers + TMEM base pointer; stage ring starts at the next 1024-byte boundary
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);  // [0..7] full, [8..15] empty, [16,17] tmem_full, [18,19] tmem_empty
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + 256);
+  uint8_t* ring = smem + 1024;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (8 + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (16 + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (18 + s); };
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_ptr_smem), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int num_items = p.num_m_tiles * p.num_n_tiles * p.split_k;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        int mt, nt, kb0, nkb;
+        decode_item(p, item, mt, nt, kb0, nkb);
+        const int m0 = mt * GEMM_BM, n0 = nt * p.tile_n;
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int k0 = (kb0 + kb) * GEMM_BK;
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_u32(ring + stage * p.stage_bytes);
+          const uint32_t sb = sa + GEMM_A_BYTES;
+          mbar_expect_tx(full_bar(stage), GEMM_A_BYTES + p.b_bytes);
+          if (!p.a_mn) {
+            tma_load_2d(sa, &tmap_a, full_bar(stage), k0, m0);
+          } else {
+            tma_load_2d(sa, &tmap_a, full_bar(stage), m0, k0);
+            tma_load_2d(sa + 8192, &tmap_a, full_bar(stage), m0 + 64, k0);
+          }
+          if (!p.b_mn) {
+            tma_load_2d(sb, &tmap_b, full_bar(stage), k0, n0);
+          } else {
+            for (int c = 0; c * 64 < p.tile_n; ++c) tma_load_2d(sb + c * 8192, &tmap_b, full_bar(stage), n0 + c * 64, k0);
+          }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(p.tile_n, p.a_mn, p.b_mn);
+      const uint32_t a_lbo = p.a_mn ? 8192u : 16u, b_lbo = p.b_mn ? 8192u : 16u;
+      const uint32_t a_kstep = p.a_mn ? 2048u : 32u, b_kstep = p.b_mn ? 2048u : 32u;
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        int mt, nt, kb0, nkb;
+        decode_item(p, item, mt, nt, kb0, nkb);
+        if (nkb == 0) continue;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * p.tile_n;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(ring + stage * p.stage_bytes);
+          const uint32_t sb = sa + GEMM_A_BYTES;
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            const uint64_t da = make_smem_desc(sa + k * a_kstep, a_lbo, 1024);
+            const uint64_t db = make_smem_desc(sb + k * b_kstep, b_lbo, 1024);
+            umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
+          }
+          umma_commit(empty_bar(stage));
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull_bar(acc));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      int mt, nt, kb0, nkb;
+      decode_item(p, item, mt, nt, kb0, nkb);
+      if (nkb == 0) continue;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int m = mt * GEMM_BM + quad * 32 + lane;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * p.tile_n;
+      for (int c = 0; c < p.tile_n; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(t_row + c, r);
+        tmem_ld_wait();
+        if (c + 32 >= p.tile_n) {
+          // whole accumulator is in registers: hand the TMEM stage back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+        }
+        const int n0 = nt * p.tile_n + c;
+        if (n0 < p.N) epilogue_chunk(p, m, n0, r);
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+static int pick_tile_n(long long N) {
+  // largest tile in {256,224,192,160,128} that divides N; else minimise padded columns
+  const int cands[] = {256, 224, 192, 160, 128};
+  for (int c : cands)
+    if (N % c == 0) return c;
+  if (N <= 256) return static_cast<int>(((N + 31) / 32) * 32);
+  int best = 256;
+  long long best_pad = -1;
+  for (int c : cands) {
+    long long pad = ((N + c - 1) / c) * c - N;
+    if (best_pad < 0 || pad < best_pad) { best = c; best_pad = pad; }
+  }
+  return best;
+}
+
+}  // namespace xf
+
+extern "C" int xf_gemm(const XfGemm* g, xf_stream_t stream_) {
+  using namespace xf;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!g || !g->a || !g->b || !g->out) return fail(-1, "xf_gemm: null pointer");
+  if (g->M <= 0 || g->N <= 0 || g->K <= 0) return fail(-2, "xf_gemm: bad shape M=%lld N=%lld K=%lld", (long long)g->M, (long long)g->N, (long long)g->K);
+  int tile_n = g->tile_n > 0 ? g->tile_n : pick_tile_n(g->N);
+  if (tile_n % 32 != 0 || tile_n < 32 || tile_n > 256) return fail(-3, "xf_gemm: tile_n %d not a multiple of 32 in [32,256]", tile_n);
+  int split_k = g->split_k > 1 ? g->split_k : 1;
+  if (split_k > 1 && !(g->out_dtype == 1 && g->accumulate == 1)) return fail(-4, "xf_gemm: split_k needs fp32 atomic accumulation");
+  if (g->accumulate && g->out_dtype != 1) return fail(-5, "xf_gemm: accumulate needs fp32 output");
+  if (g->drop_p < 0.f || g->drop_p >= 1.f) return fail(-6, "xf_gemm: drop_p out of range");
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = (int)g->M; p.N = (int)g->N; p.K = (int)g->K;
+  p.tile_n = tile_n;
+  p.a_mn = g->a_mn_major ? 1 : 0;
+  p.b_mn = g->b_mn_major ? 1 : 0;
+  p.num_m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
+  p.num_n_tiles = (p.N + tile_n - 1) / tile_n;
+  p.total_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+  if (split_k > p.total_kb) split_k = p.total_kb;
+  p.kb_per_split = (p.total_kb + split_k - 1) / split_k;
+  split_k = (p.total_kb + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
+  p.split_k = split_k;
+  p.b_bytes = p.b_mn ? ((tile_n + 63) / 64) * 8192 : tile_n * 128;
+  p.stage_bytes = GEMM_A_BYTES + ((p.b_bytes + 1023) / 1024) * 1024;
+  p.stages = GEMM_SMEM_BUDGET / p.stage_bytes;
+  if (p.stages > 8) p.stages = 8;
+  p.bias = g->bias;
+  p.pos_table = g->pos_table;
+  p.rows_in = (int)g->rows_in; p.rows_out = (int)g->rows_out; p.row_off = (int)g->row_off;
+  p.act = g->act;
+  p.preact_out = reinterpret_cast<__nv_bfloat16*>(g->preact_out);
+  p.dact_in = reinterpret_cast<const __nv_bfloat16*>(g->dact_in);
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(g->residual);
+  p.ldr = g->ldr;
+  p.out = g->out;
+  p.ldc = g->ldc;
+  p.out_f32 = g->out_dtype == 1;
+  p.accumulate = g->accumulate;
+  const int esz = p.out_f32 ? 4 : 2;
+  p.vec_ok = ((reinterpret_cast<uintptr_t>(g->out) & 15) == 0) && ((g->ldc * esz) % 16 == 0) && (p.N % 4 == 0) &&
+             (!g->residual || (((reinterpret_cast<uintptr_t>(g->residual) & 15) == 0) && ((g->ldr * 2) % 16 == 0))) &&
+             (!g->preact_out || (((reinterpret_cast<uintptr_t>(g->preact_out) & 15) == 0) && ((g->ldc * 2) % 16 == 0))) &&
+             (!g->dact_in || (((reinterpret_cast<uintptr_t>(g->dact_in) & 15) == 0) && ((g->ldc * 2) % 16 == 0))) &&
+             (!g->pos_table || ((reinterpret_cast<uintptr_t>(g->pos_table) & 15) == 0)) &&
+             (!g->bias || ((reinterpret_cast<uintptr_t>(g->bias) & 15) == 0));
+  p.drop_p = g->drop_p;
+  p.drop_seed = g->drop_seed;
+  p.drop_stream = g->drop_stream;
+  p.drop_first = g->drop_first;
+  p.drop_thresh = static_cast<uint32_t>(static_cast<double>(g->drop_p) * 4294967296.0);
+  p.drop_scale = g->drop_p > 0.f ? 1.0f / (1.0f - g->drop_p) : 1.0f;
+
+  CUtensorMap ta, tb;
+  int rc;
+  if (!p.a_mn) rc = make_tmap_2d_bf16(&ta, g->a, p.M, p.K, g->a_ld, 64, 128);
+  else         rc = make_tmap_2d_bf16(&ta, g->a, p.K, p.M, g->a_ld, 64, 64);
+  if (rc) return rc;
+  if (!p.b_mn) rc = make_tmap_2d_bf16(&tb, g->b, p.N, p.K, g->b_ld, 64, tile_n);
+  else         rc = make_tmap_2d_bf16(&tb, g->b, p.K, p.N, g->b_ld, 64, 64);
+  if (rc) return rc;
+
+  const int smem_bytes = 1024 /*align slack*/ + 1024 /*control*/ + p.stages * p.stage_bytes;
+  static bool attr_set = false;
+  if (!attr_set) {
+    XF_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const int items = p.num_m_tiles * p.num_n_tiles * p.split_k;
+  int ctas = g->max_ctas > 0 ? g->max_ctas : sm_count();
+  if (ctas > items) ctas = items;
+  gemm_bf16_tcgen05_kernel<<<ctas, GEMM_THREADS, smem_bytes, stream>>>(ta, tb, p);
+  g_launches.fetch_add(1);
+  XF_CUDA(cudaGetLastError());
+  return 0;
+}

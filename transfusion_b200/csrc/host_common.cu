@@ -1,0 +1,63 @@
+#include "host_common.cuh"
+
+#include <mutex>
+
+#include "../../include/xfusion.h"
+
+namespace xf {
+
+thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, []() {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+  });
+  return fn;
+}
+
+int make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld,
+                      uint32_t box_cols, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return fail(-10, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return fail(-11, "TMA base pointer not 16-byte aligned");
+  if ((ld * 2) % 16 != 0) return fail(-12, "TMA row pitch %llu B not a multiple of 16", (unsigned long long)(ld * 2));
+  if (box_cols * 2 > 128 || box_rows > 256) return fail(-13, "bad TMA box %u x %u", box_cols, box_rows);
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstr[1] = {ld * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(-14, "cuTensorMapEncodeTiled failed: %d (rows=%llu cols=%llu ld=%llu)", (int)r,
+                                     (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld);
+  return 0;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 148;
+    n = p.multiProcessorCount;
+  }
+  return n;
+}
+
+}  // namespace xf
+
+extern "C" {
+int xf_version(void) { return XF_ABI_VERSION; }
+const char* xf_last_error(void) { return xf::g_err; }
+int64_t xf_launch_count(void) { return xf::g_launches.load(); }
+}

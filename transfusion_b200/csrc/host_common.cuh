@@ -1,0 +1,48 @@
+// Host-side helpers shared by the C-ABI entry points: error string, launch counter,
+// lazily resolved cuTensorMapEncodeTiled (no link-time dependency on libcuda, so the library
+// loads on a CPU-only box), TMA descriptor construction.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+
+namespace xf {
+
+extern thread_local char g_err[512];
+extern std::atomic<int64_t> g_launches;
+
+inline int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+inline int cuda_fail(cudaError_t e, const char* what) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+  return static_cast<int>(e);
+}
+
+#define XF_CUDA(call)                                   \
+  do {                                                  \
+    cudaError_t _e = (call);                            \
+    if (_e != cudaSuccess) return xf::cuda_fail(_e, #call); \
+  } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_tiled();
+
+// 2-D bf16 row-major tensor [rows, cols] with leading dimension ld (elements); box = box_cols x box_rows,
+// SWIZZLE_128B (box_cols * 2 bytes must be <= 128), out-of-bounds elements read as zero.
+int make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld,
+                      uint32_t box_cols, uint32_t box_rows);
+
+int sm_count();
+
+}  // namespace xf
