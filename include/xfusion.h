@@ -143,6 +143,29 @@ int xf_unpad_add(const float* src_padded, int64_t lds, float* dst, int64_t ldd, 
 int xf_attn_delta(const void* o_bf16, const void* do_bf16, int64_t ld, int rows, int heads, int dp, float* delta,
                   xf_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Fused multi-head attention (flash-style: no S x S tensor in HBM), tcgen05 + TMA + TMEM.
+ * Replaces torch18_adapters.py:544-555 (head split), :578-597 (key_padding_mask -> -inf),
+ * :789-798 (_scaled_dot_product_attention) and :607 (head merge); general Sq != Sk, so the
+ * QKVEncoder cross-attention (cross_qkv_layers.py:70-77) is the same call.
+ * q/k/v/out: bf16, token-major [B*S, ld], head hd in columns [hd*dp, hd*dp+dp) (dp = head dim
+ * padded to a multiple of 16; pad columns must be zero).  For a fused in-proj output
+ * [B*S, 3*H*dp] pass k = q + H*dp, v = q + 2*H*dp with ldq = ldk = ldv = 3*H*dp.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct XfAttnFwd {
+  const void* q; int64_t ldq;
+  const void* k; int64_t ldk;
+  const void* v; int64_t ldv;
+  void* out; int64_t ldo;
+  float* lse;                        /* [B,H,Sq] fp32, log2-domain logsumexp of the scaled scores (for backward), or NULL */
+  const uint8_t* key_padding_mask;   /* [B,Sk] nonzero = ignore (True of src_key_padding_mask), or NULL */
+  int32_t kpm_start;                 /* keys < kpm_start are never masked (visual tokens): lets tiles skip the mask */
+  int32_t B, H, Sq, Sk, dp;
+  float scale;                       /* 1/sqrt(head_dim) */
+  float drop_p; uint32_t drop_seed, drop_stream;   /* dropout on the attention probabilities */
+} XfAttnFwd;
+int xf_attn_fwd(const XfAttnFwd* a, xf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

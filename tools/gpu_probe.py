@@ -45,7 +45,164 @@ def gemm_case(M, N, K, a_mn, b_mn, tile_n=0, split_k=1, f32=False, bias=False, s
             print("   blockmax(32x32):\n", (blk > 0.05 * ref.abs().max()).int().cpu().numpy(), flush=True)
 
 
+def report(tag, e, tol):
+    print(("PASS " if e < tol else "FAIL ") + tag + f" rel={e:.3e}", flush=True)
+
+
+def attn_ref(q, k, v, H, d, kpm):
+    B, Sq, _ = q.shape
+    Sk = k.shape[1]
+    qh = q.float().reshape(B, Sq, H, d).transpose(1, 2)
+    kh = k.float().reshape(B, Sk, H, d).transpose(1, 2)
+    vh = v.float().reshape(B, Sk, H, d).transpose(1, 2)
+    s = qh @ kh.transpose(-1, -2) / (d ** 0.5)
+    if kpm is not None:
+        s = s.masked_fill(kpm[:, None, None, :].bool(), float("-inf"))
+    lse2 = torch.logsumexp(s, dim=-1) * 1.4426950408889634
+    o = torch.softmax(s, dim=-1) @ vh
+    return o.transpose(1, 2).reshape(B, Sq, H * d), lse2
+
+
+def attn_case(B, H, Sq, Sk, d, mask=False, fused=True, seed=0):
+    torch.manual_seed(seed)
+    dev = "cuda"
+    dp = (d + 15) // 16 * 16
+    D = H * d
+    if fused and Sq == Sk:
+        qkv = torch.zeros(B * Sq, 3 * H * dp, device=dev, dtype=torch.bfloat16)
+        src = torch.randn(B, Sq, 3, H, d, device=dev).bfloat16()
+        qkv.view(B, Sq, 3, H, dp)[..., :d] = src
+        q2, k2, v2 = qkv[:, :H * dp], qkv[:, H * dp:2 * H * dp], qkv[:, 2 * H * dp:]
+        q, k, v = (src[:, :, i].reshape(B, Sq, D) for i in range(3))
+    else:
+        qs = torch.randn(B, Sq, H, d, device=dev).bfloat16()
+        ks = torch.randn(B, Sk, H, d, device=dev).bfloat16()
+        vs = torch.randn(B, Sk, H, d, device=dev).bfloat16()
+        q2 = torch.zeros(B * Sq, H * dp, device=dev, dtype=torch.bfloat16); q2.view(B, Sq, H, dp)[..., :d] = qs
+        k2 = torch.zeros(B * Sk, H * dp, device=dev, dtype=torch.bfloat16); k2.view(B, Sk, H, dp)[..., :d] = ks
+        v2 = torch.zeros(B * Sk, H * dp, device=dev, dtype=torch.bfloat16); v2.view(B, Sk, H, dp)[..., :d] = vs
+        q, k, v = qs.reshape(B, Sq, D), ks.reshape(B, Sk, D), vs.reshape(B, Sk, D)
+    kpm = None
+    if mask:
+        kpm = torch.zeros(B, Sk, dtype=torch.uint8, device=dev)
+        for b in range(B):
+            kpm[b, Sk - 1 - 7 * b - 3:] = 1
+    out = torch.zeros(B * Sq, H * dp, device=dev, dtype=torch.bfloat16)
+    lse = torch.zeros(B, H, Sq, device=dev)
+    ops.attn_fwd(q2, k2, v2, out, lse, B=B, H=H, Sq=Sq, Sk=Sk, dp=dp, scale=1.0 / d ** 0.5,
+                 key_padding_mask=kpm, kpm_start=max(0, Sk - 64))
+    torch.cuda.synchronize()
+    ref, lse_ref = attn_ref(q, k, v, H, d, kpm)
+    got = out.view(B, Sq, H, dp)[..., :d].reshape(B, Sq, D).float()
+    tag = f"attn_fwd B={B} H={H} Sq={Sq} Sk={Sk} d={d} mask={int(mask)} fused={int(fused)}"
+    report(tag + " out", rel(got, ref), 1e-2)
+    report(tag + " lse", float((lse - lse_ref).abs().max() / lse_ref.abs().max()), 1e-3)
+    if dp != d:
+        padmax = float(out.view(B, Sq, H, dp)[..., d:].abs().max())
+        print("   pad-cols max:", padmax, flush=True)
+
+
+def ln_case(rows, D, seed=0):
+    torch.manual_seed(seed)
+    dev = "cuda"
+    x = torch.randn(rows, D, device=dev).bfloat16()
+    g = torch.randn(D, device=dev); b = torch.randn(D, device=dev)
+    y = torch.empty_like(x); mean = torch.empty(rows, device=dev); rstd = torch.empty(rows, device=dev)
+    ops.layernorm_fwd(x, y, g, b, mean, rstd, rows, D)
+    xr = x.float().requires_grad_(True)
+    yr = torch.nn.functional.layer_norm(xr, (D,), g, b, 1e-5)
+    report(f"ln_fwd rows={rows} D={D}", rel(y.float(), yr), 6e-3)
+    dy = torch.randn(rows, D, device=dev).bfloat16()
+    gr = g.clone().requires_grad_(True); br = b.clone().requires_grad_(True)
+    yr2 = torch.nn.functional.layer_norm(xr, (D,), gr, br, 1e-5)
+    yr2.backward(dy.float())
+    dx = torch.empty_like(x); dg = torch.zeros(D, device=dev); db = torch.zeros(D, device=dev); dbias = torch.zeros(D, device=dev)
+    ops.layernorm_bwd(dy, x, g, mean, rstd, dx, dg, db, rows, D, dbias=dbias)
+    torch.cuda.synchronize()
+    report(f"ln_bwd dx rows={rows} D={D}", rel(dx.float(), xr.grad), 8e-3)
+    report(f"ln_bwd dgamma", rel(dg, gr.grad), 1e-3)
+    report(f"ln_bwd dbeta", rel(db, br.grad), 1e-3)
+    report(f"ln_bwd dbias", rel(dbias, dx.float().sum(0)), 1e-3)
+    # remapped: read only first n of every S rows, write compact
+    B, S, n = 3, rows // 3, rows // 3 - 5
+    yc = torch.empty(B * n, D, device=dev, dtype=torch.bfloat16)
+    ops.layernorm_fwd(x, yc, g, b, None, None, B * n, D, in_map=(n, S, 0))
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.layer_norm(x.float().view(B, S, D)[:, :n], (D,), g, b, 1e-5).reshape(B * n, D)
+    report(f"ln_fwd remap", rel(yc.float(), ref), 6e-3)
+
+
+def layout_case(B, Cc, H, W, p, dtype=torch.float32):
+    import sys as _s
+    torch.manual_seed(0)
+    dev = "cuda"
+    f = torch.randn(B, Cc, H, W, device=dev).to(dtype)
+    gh, gw = H // p, W // p
+    tok = torch.empty(B * gh * gw, Cc * p * p, device=dev, dtype=torch.bfloat16)
+    ops.patchify(f, p, tok)
+    ref = f.float().reshape(B, Cc, gh, p, gw, p).permute(0, 2, 4, 1, 3, 5).reshape(B * gh * gw, Cc * p * p).bfloat16()
+    torch.cuda.synchronize()
+    ok = torch.equal(tok, ref)
+    print(("PASS " if ok else "FAIL ") + f"patchify B={B} C={Cc} {H}x{W} p={p} {dtype}", flush=True)
+    out = torch.zeros(B, Cc, H, W, device=dev, dtype=dtype)
+    ops.fold(tok, out, p)
+    torch.cuda.synchronize()
+    ok = torch.equal(out.float(), f.bfloat16().float())
+    print(("PASS " if ok else "FAIL ") + f"fold B={B} C={Cc} {H}x{W} p={p} {dtype}", flush=True)
+
+
+def misc_case():
+    torch.manual_seed(0)
+    dev = "cuda"
+    x = torch.randn(1000, 2688, device=dev).bfloat16()
+    out = torch.zeros(2688, device=dev)
+    ops.colsum(x, out, 1000, 2688)
+    report("colsum", rel(out, x.float().sum(0)), 1e-4)
+    B, L, D, n = 3, 7, 64, 10
+    S = n + L
+    lang = torch.randn(B, L, D, device=dev); kind = torch.randn(D, device=dev)
+    z = torch.zeros(B, S, D, device=dev, dtype=torch.bfloat16)
+    ops.lang_rows_fwd(lang, kind, z, n)
+    report("lang_rows_fwd", rel(z[:, n:].float(), (lang + kind).bfloat16().float()), 1e-6)
+    dz = torch.randn(B, S, D, device=dev).bfloat16()
+    dlang = torch.zeros(B, L, D, device=dev); dkind = torch.zeros(D, device=dev)
+    ops.lang_rows_bwd(dz, dlang, dkind, B, L, n)
+    report("lang_rows_bwd dlang", rel(dlang, dz[:, n:].float()), 1e-6)
+    report("lang_rows_bwd dkind", rel(dkind, dz[:, n:].float().sum((0, 1))), 1e-5)
+    # cast_pad: rows 3 blocks of 10 -> 16
+    w = torch.randn(30, 24, device=dev)
+    wp = torch.zeros(48, 24, device=dev, dtype=torch.bfloat16)
+    ops.cast_pad(w, wp, 30, 24, rin=10, rout=16)
+    ok = torch.equal(wp.view(3, 16, 24)[:, :10].reshape(30, 24), w.bfloat16()) and float(wp.view(3, 16, 24)[:, 10:].abs().max()) == 0
+    print(("PASS " if ok else "FAIL ") + "cast_pad rows", flush=True)
+    wp2 = torch.zeros(30, 3 * 16, device=dev, dtype=torch.bfloat16)
+    w2 = torch.randn(30, 30, device=dev)
+    ops.cast_pad(w2, wp2, 30, 30, cin=10, cout=16)
+    ok = torch.equal(wp2.view(30, 3, 16)[:, :, :10].reshape(30, 30), w2.bfloat16())
+    print(("PASS " if ok else "FAIL ") + "cast_pad cols", flush=True)
+    gsrc = torch.randn(30, 48, device=dev); gdst = torch.ones(30, 30, device=dev)
+    ops.unpad_add(gsrc, gdst, 30, 30, cin=10, cout=16)
+    ok = torch.allclose(gdst, 1 + gsrc.view(30, 3, 16)[:, :, :10].reshape(30, 30))
+    print(("PASS " if ok else "FAIL ") + "unpad_add cols", flush=True)
+    o = torch.randn(50, 4 * 32, device=dev).bfloat16(); do = torch.randn(50, 4 * 32, device=dev).bfloat16()
+    delta = torch.zeros(50, 4, device=dev)
+    ops.attn_delta(o, do, delta, 50, 4, 32)
+    report("attn_delta", rel(delta, (o.float() * do.float()).view(50, 4, 32).sum(-1)), 1e-5)
+
+
 CASES = {
+    "attn_small": lambda: attn_case(1, 1, 128, 64, 64),
+    "attn_2tiles": lambda: attn_case(1, 1, 128, 128, 64),
+    "attn_multi": lambda: attn_case(2, 4, 300, 300, 64, mask=True),
+    "attn_d224": lambda: attn_case(2, 4, 832, 832, 224, mask=True),
+    "attn_d178": lambda: attn_case(2, 4, 500, 500, 178, mask=True),
+    "attn_cross": lambda: attn_case(2, 2, 200, 333, 32, mask=True, fused=False),
+    "attn_d16": lambda: attn_case(2, 4, 70, 70, 16, mask=True),
+    "attn_big": lambda: attn_case(2, 4, 3136, 3136, 224, mask=True),
+    "ln": lambda: (ln_case(999, 896), ln_case(300, 712), ln_case(129, 64)),
+    "layout": lambda: (layout_case(2, 256, 16, 24, 4), layout_case(2, 512, 8, 12, 4, torch.bfloat16),
+                       layout_case(2, 64, 12, 20, 2), layout_case(3, 2048, 24, 32, 1), layout_case(2, 8, 16, 24, 4)),
+    "misc": misc_case,
     "gemm_kk_small": lambda: gemm_case(128, 128, 64, False, False, tile_n=128),
     "gemm_kk_k256": lambda: gemm_case(128, 128, 256, False, False, tile_n=128),
     "gemm_kk_multi": lambda: gemm_case(1024, 896, 896, False, False, bias=True),

@@ -34,6 +34,51 @@ class XfGemm(C.Structure):
     ]
 
 
+class XfLayerNorm(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("ldx", C.c_int64),
+        ("y", C.c_void_p), ("ldy", C.c_int64),
+        ("gamma", C.c_void_p), ("beta", C.c_void_p),
+        ("mean", C.c_void_p), ("rstd", C.c_void_p),
+        ("rows", C.c_int32), ("D", C.c_int32),
+        ("in_rows_in", C.c_int32), ("in_rows_out", C.c_int32), ("in_row_off", C.c_int32),
+        ("out_rows_in", C.c_int32), ("out_rows_out", C.c_int32), ("out_row_off", C.c_int32),
+        ("eps", C.c_float),
+        ("drop_p", C.c_float), ("drop_seed", C.c_uint32), ("drop_stream", C.c_uint32),
+    ]
+
+
+class XfLayerNormBwd(C.Structure):
+    _fields_ = [
+        ("dy", C.c_void_p), ("lddy", C.c_int64),
+        ("x", C.c_void_p), ("ldx", C.c_int64),
+        ("gamma", C.c_void_p), ("mean", C.c_void_p), ("rstd", C.c_void_p),
+        ("dx", C.c_void_p), ("lddx", C.c_int64),
+        ("dx2", C.c_void_p),
+        ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("dbias", C.c_void_p),
+        ("rows", C.c_int32), ("D", C.c_int32),
+        ("in_rows_in", C.c_int32), ("in_rows_out", C.c_int32), ("in_row_off", C.c_int32),
+        ("out_rows_in", C.c_int32), ("out_rows_out", C.c_int32), ("out_row_off", C.c_int32),
+        ("dy_drop_p", C.c_float), ("dy_drop_seed", C.c_uint32), ("dy_drop_stream", C.c_uint32),
+        ("dx2_drop_p", C.c_float), ("dx2_drop_seed", C.c_uint32), ("dx2_drop_stream", C.c_uint32),
+    ]
+
+
+class XfAttnFwd(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("ldq", C.c_int64),
+        ("k", C.c_void_p), ("ldk", C.c_int64),
+        ("v", C.c_void_p), ("ldv", C.c_int64),
+        ("out", C.c_void_p), ("ldo", C.c_int64),
+        ("lse", C.c_void_p),
+        ("key_padding_mask", C.c_void_p),
+        ("kpm_start", C.c_int32),
+        ("B", C.c_int32), ("H", C.c_int32), ("Sq", C.c_int32), ("Sk", C.c_int32), ("dp", C.c_int32),
+        ("scale", C.c_float),
+        ("drop_p", C.c_float), ("drop_seed", C.c_uint32), ("drop_stream", C.c_uint32),
+    ]
+
+
 def lib():
     """Loads the shared library once.  Raises if it has not been built
     (``python -m transfusion_b200.build`` / ``__graft_entry__.build()``)."""
@@ -59,6 +104,9 @@ def lib():
 # every symbol include/xfusion.h declares (checked by tests/test_cabi.py)
 EXPORTS = [
     "xf_version", "xf_last_error", "xf_launch_count", "xf_gemm",
+    "xf_patchify", "xf_fold", "xf_lang_rows_fwd", "xf_lang_rows_bwd",
+    "xf_layernorm_fwd", "xf_layernorm_bwd", "xf_colsum", "xf_cast_pad", "xf_unpad_add",
+    "xf_attn_delta", "xf_attn_fwd",
 ]
 
 

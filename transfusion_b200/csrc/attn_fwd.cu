@@ -1,0 +1,362 @@
+// xf_attn_fwd: fused multi-head attention forward for sm_100a (flash-style, no S x S tensor).
+//
+// Replaces torch18_adapters.py:544-555 (head split), :578-597 (key-padding mask -> -inf), :789-798
+// (_scaled_dot_product_attention: q/sqrt(d), bmm, softmax, dropout, bmm) and :607 (head merge).
+// General Lq != Lk (the QKVEncoder-style cross-attention of cross_qkv_layers.py:70-77 is the same op).
+//
+// One CTA per (batch, head, 128-query tile); 192 threads:
+//   warp 0    TMA producer: Q tile once, then K_j / V_j tiles (64 keys) into 2-stage rings
+//   warp 1    MMA issuer  : S_j = Q K_j^T  (tcgen05, M=128, N=64,  K=dp)  -> TMEM S[j&1]
+//                           O  += P_j V_j  (tcgen05, M=128, N=dp,  K=64)  -> TMEM O
+//   warps 2-5 softmax     : one thread per query row (TMEM lane): tcgen05.ld the S row, key-padding /
+//                           tail mask, running max / sum in registers (log2 domain, lazy rescale of
+//                           O in TMEM only when the max grows by > 2^8), dropout on P, P -> bf16 ->
+//                           SWIZZLE_128B shared memory as the A operand of the PV MMA; final
+//                           O / l -> bf16 -> global (heads merged), LSE saved for backward.
+// S is double-buffered in TMEM so QK^T of tile j+1 overlaps the softmax of tile j.
+//
+// Shared memory (1024-byte aligned atoms, SWIZZLE_128B, 64-column chunks written by TMA):
+//   Q : nchunk x [128 rows x 128 B]      K-major A operand of S
+//   K : 2 x nchunk x [64 rows x 128 B]   K-major B operand of S
+//   V : 2 x nchunk x [64 rows x 128 B]   MN-major B operand of PV (N = head dim contiguous)
+//   P : [128 rows x 128 B]               K-major A operand of PV (written by the softmax warps)
+#include <string.h>
+
+#include "../../include/xfusion.h"
+#include "host_common.cuh"
+#include "ptx.cuh"
+
+namespace xf {
+
+constexpr int AF_BM = 128;
+constexpr int AF_BN = 64;
+constexpr int AF_THREADS = 192;
+constexpr float AF_RESCALE_THRESHOLD = 8.0f;  // log2 units
+
+struct AttnFwdParams {
+  int B, H, Sq, Sk, dp, nchunk, q_tiles;
+  float sl2;  // log2(e) / sqrt(head_dim)
+  const uint8_t* kpm;  // [B, Sk], 1 = ignore key; may be null
+  int kpm_start;       // keys < kpm_start are never masked
+  __nv_bfloat16* out;
+  long long ldo;
+  float* lse;  // [B, H, Sq], log2 domain: m + log2(l)
+  float drop_p, drop_scale;
+  uint32_t drop_seed, drop_stream, drop_thresh;
+};
+
+__global__ void __launch_bounds__(AF_THREADS, 1)
+attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                        const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ AttnFwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + 256);
+  const uint32_t q_bytes = p.nchunk * 16384u, kv_bytes = p.nchunk * 8192u;
+  uint8_t* sQ = smem + 1024;
+  uint8_t* sK = sQ + q_bytes;
+  uint8_t* sV = sK + 2 * kv_bytes;
+  uint8_t* sP = sV + 2 * kv_bytes;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = smem_u32(bars);
+  // barrier indices
+  const uint32_t Q_FULL = bar0;
+  auto K_FULL = [&](int s) { return bar0 + 8u * (1 + s); };
+  auto K_EMPTY = [&](int s) { return bar0 + 8u * (3 + s); };
+  auto V_FULL = [&](int s) { return bar0 + 8u * (5 + s); };
+  auto V_EMPTY = [&](int s) { return bar0 + 8u * (7 + s); };
+  auto S_FULL = [&](int s) { return bar0 + 8u * (9 + s); };
+  auto S_EMPTY = [&](int s) { return bar0 + 8u * (11 + s); };
+  const uint32_t P_FULL = bar0 + 8u * 13;
+  const uint32_t O_READY = bar0 + 8u * 14;
+
+  int bid = blockIdx.x;
+  const int qt = bid % p.q_tiles; bid /= p.q_tiles;
+  const int hd = bid % p.H;
+  const int b = bid / p.H;
+  const int q0 = qt * AF_BM;
+  const int nkv = (p.Sk + AF_BN - 1) / AF_BN;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_k);
+    tma_prefetch_desc(&tmap_v);
+    mbar_init(Q_FULL, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(K_FULL(s), 1); mbar_init(K_EMPTY(s), 1);
+      mbar_init(V_FULL(s), 1); mbar_init(V_EMPTY(s), 1);
+      mbar_init(S_FULL(s), 1); mbar_init(S_EMPTY(s), 4);
+    }
+    mbar_init(P_FULL, 4);
+    mbar_init(O_READY, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_ptr_smem), 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t tmem_S = tmem_base;         // 2 x 64 columns
+  const uint32_t tmem_O = tmem_base + 128;   // dp columns
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int col0 = hd * p.dp;
+      mbar_expect_tx(Q_FULL, q_bytes);
+      for (int c = 0; c < p.nchunk; ++c) tma_load_3d(smem_u32(sQ + c * 16384), &tmap_q, Q_FULL, col0 + 64 * c, q0, b);
+      for (int j = 0; j < nkv; ++j) {
+        const int st = j & 1;
+        const uint32_t par = ((j >> 1) & 1) ^ 1;
+        mbar_wait(K_EMPTY(st), par);
+        mbar_expect_tx(K_FULL(st), kv_bytes);
+        for (int c = 0; c < p.nchunk; ++c)
+          tma_load_3d(smem_u32(sK + st * kv_bytes + c * 8192), &tmap_k, K_FULL(st), col0 + 64 * c, j * AF_BN, b);
+        mbar_wait(V_EMPTY(st), par);
+        mbar_expect_tx(V_FULL(st), kv_bytes);
+        for (int c = 0; c < p.nchunk; ++c)
+          tma_load_3d(smem_u32(sV + st * kv_bytes + c * 8192), &tmap_v, V_FULL(st), col0 + 64 * c, j * AF_BN, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_bf16(AF_BN, 0, 0);
+      const uint32_t idesc_o = make_idesc_bf16(p.dp, 0, 1);
+      const int ksteps = p.dp / 16;
+      auto issue_s = [&](int j) {
+        const int st = j & 1, sb = j & 1;
+        mbar_wait(K_FULL(st), (j >> 1) & 1);
+        mbar_wait(S_EMPTY(sb), ((j >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK + st * kv_bytes);
+        for (int k = 0; k < ksteps; ++k) {
+          const uint64_t da = make_smem_desc(qa + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
+          const uint64_t db = make_smem_desc(ka + (k >> 2) * 8192 + (k & 3) * 32, 16, 1024);
+          umma_bf16(tmem_S + sb * AF_BN, da, db, idesc_s, k != 0);
+        }
+        umma_commit(S_FULL(sb));
+        umma_commit(K_EMPTY(st));
+      };
+      mbar_wait(Q_FULL, 0);
+      issue_s(0);
+      for (int j = 0; j < nkv; ++j) {
+        if (j + 1 < nkv) issue_s(j + 1);
+        const int st = j & 1;
+        mbar_wait(P_FULL, j & 1);
+        mbar_wait(V_FULL(st), (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t pa = smem_u32(sP), va = smem_u32(sV + st * kv_bytes);
+#pragma unroll
+        for (int k = 0; k < AF_BN / 16; ++k) {
+          const uint64_t da = make_smem_desc(pa + k * 32, 16, 1024);
+          const uint64_t db = make_smem_desc(va + k * 2048, 8192, 1024);
+          umma_bf16(tmem_O, da, db, idesc_o, (j | k) != 0);
+        }
+        umma_commit(V_EMPTY(st));
+        umma_commit(O_READY);
+      }
+    }
+  } else {
+    // ===================== softmax / correction / epilogue =====================
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;     // row within the tile == TMEM lane
+    const int q = q0 + r;
+    const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
+    float m_used = 0.f, l = 0.f;
+    const uint64_t drop_row = (static_cast<uint64_t>(b * p.H + hd) * p.Sq + q) * static_cast<uint64_t>(p.Sk);
+    uint8_t* prow = sP + r * 128;
+
+    for (int j = 0; j < nkv; ++j) {
+      const int sb = j & 1;
+      const int k0 = j * AF_BN;
+      mbar_wait(S_FULL(sb), (j >> 1) & 1);
+      tc_fence_after();
+      uint32_t sr0[32], sr1[32];
+      tmem_ld32(tmem_S + lane_sel + sb * AF_BN, sr0);
+      tmem_ld32(tmem_S + lane_sel + sb * AF_BN + 32, sr1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(S_EMPTY(sb));
+
+      // mask bits: bit c set -> key k0+c is ignored (beyond Sk or key-padding)
+      uint32_t mb0 = 0, mb1 = 0;
+      const int kvalid = p.Sk - k0;
+      if (kvalid < 64) {
+        if (kvalid <= 32) { mb1 = 0xffffffffu; mb0 = kvalid >= 32 ? 0u : (0xffffffffu << kvalid); }
+        else mb1 = 0xffffffffu << (kvalid - 32);
+      }
+      if (p.kpm && k0 + AF_BN > p.kpm_start) {
+        const uint8_t* mrow = p.kpm + static_cast<long long>(b) * p.Sk + k0;
+        const bool a0 = (lane < kvalid) && mrow[lane] != 0;
+        const bool a1 = (lane + 32 < kvalid) && mrow[lane + 32] != 0;
+        mb0 |= __ballot_sync(0xffffffffu, a0);
+        mb1 |= __ballot_sync(0xffffffffu, a1);
+      }
+      float x[64];
+      float mt = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        x[c] = ((mb0 >> c) & 1u) ? -INFINITY : __uint_as_float(sr0[c]) * p.sl2;
+        x[32 + c] = ((mb1 >> c) & 1u) ? -INFINITY : __uint_as_float(sr1[c]) * p.sl2;
+        mt = fmaxf(mt, fmaxf(x[c], x[32 + c]));
+      }
+      bool need = false;
+      float alpha = 1.f;
+      if (j == 0) {
+        m_used = (mt == -INFINITY) ? 0.f : mt;
+      } else {
+        need = mt > m_used + AF_RESCALE_THRESHOLD;
+      }
+      const bool any_need = __any_sync(0xffffffffu, need);
+      if (any_need) {
+        const float m_new = fmaxf(m_used, mt);
+        alpha = fast_exp2(m_used - m_new);
+        l *= alpha;
+        m_used = m_new;
+      }
+      float psum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) {
+        x[c] = fast_exp2(x[c] - m_used);
+        psum += x[c];
+      }
+      l += psum;
+      if (p.drop_p > 0.f) {
+#pragma unroll
+        for (int c = 0; c < 64; ++c)
+          x[c] = dropout_keep(p.drop_seed, p.drop_stream, drop_row + static_cast<uint64_t>(k0 + c), p.drop_thresh) ? x[c] * p.drop_scale : 0.f;
+      }
+      if (j > 0) {
+        mbar_wait(O_READY, (j - 1) & 1);  // PV_{j-1} retired: P buffer free, O stable
+        tc_fence_after();
+        if (any_need) {
+          int c = 0;
+          for (; c + 32 <= p.dp; c += 32) {
+            uint32_t o[32];
+            tmem_ld32(tmem_O + lane_sel + c, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st32(tmem_O + lane_sel + c, o);
+          }
+          if (c < p.dp) {
+            uint32_t o[16];
+            tmem_ld16(tmem_O + lane_sel + c, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st16(tmem_O + lane_sel + c, o);
+          }
+          tmem_st_wait();
+        }
+      }
+      // P row -> shared memory, K-major SWIZZLE_128B: 16-byte segment s of row r lands at s ^ (r & 7)
+#pragma unroll
+      for (int sgm = 0; sgm < 8; ++sgm) {
+        const uint4 v = make_uint4(pack_bf16(x[8 * sgm], x[8 * sgm + 1]), pack_bf16(x[8 * sgm + 2], x[8 * sgm + 3]),
+                                   pack_bf16(x[8 * sgm + 4], x[8 * sgm + 5]), pack_bf16(x[8 * sgm + 6], x[8 * sgm + 7]));
+        *reinterpret_cast<uint4*>(prow + ((sgm ^ (r & 7)) << 4)) = v;
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(P_FULL);
+    }
+
+    // ---- epilogue: O / l -> bf16, heads merged; LSE (log2 domain)
+    mbar_wait(O_READY, (nkv - 1) & 1);
+    tc_fence_after();
+    const float inv = l > 0.f ? 1.f / l : 0.f;
+    const bool row_ok = q < p.Sq;
+    __nv_bfloat16* orow = p.out + (static_cast<long long>(b) * p.Sq + q) * p.ldo + hd * p.dp;
+    int c = 0;
+    for (; c + 32 <= p.dp; c += 32) {
+      uint32_t o[32];
+      tmem_ld32(tmem_O + lane_sel + c, o);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          const uint4 v = make_uint4(pack_bf16(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv),
+                                     pack_bf16(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv),
+                                     pack_bf16(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv),
+                                     pack_bf16(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv));
+          *reinterpret_cast<uint4*>(orow + c + i) = v;
+        }
+      }
+    }
+    if (c < p.dp) {
+      uint32_t o[16];
+      tmem_ld16(tmem_O + lane_sel + c, o);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int i = 0; i < 16; i += 8) {
+          const uint4 v = make_uint4(pack_bf16(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv),
+                                     pack_bf16(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv),
+                                     pack_bf16(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv),
+                                     pack_bf16(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv));
+          *reinterpret_cast<uint4*>(orow + c + i) = v;
+        }
+      }
+    }
+    if (row_ok && p.lse) p.lse[(static_cast<long long>(b) * p.H + hd) * p.Sq + q] = l > 0.f ? m_used + log2f(l) : -INFINITY;
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace xf
+
+extern "C" int xf_attn_fwd(const XfAttnFwd* a, xf_stream_t stream_) {
+  using namespace xf;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (!a || !a->q || !a->k || !a->v || !a->out) return fail(-1, "xf_attn_fwd: null pointer");
+  if (a->dp % 16 || a->dp < 16 || a->dp > 256) return fail(-2, "xf_attn_fwd: padded head dim %d must be a multiple of 16 in [16,256]", a->dp);
+  if (a->B <= 0 || a->H <= 0 || a->Sq <= 0 || a->Sk <= 0) return fail(-3, "xf_attn_fwd: bad shape");
+  if ((a->ldo % 8) || (reinterpret_cast<uintptr_t>(a->out) & 15)) return fail(-4, "xf_attn_fwd: output must be 16-byte aligned with ld %% 8 == 0");
+  if (a->drop_p < 0.f || a->drop_p >= 1.f) return fail(-6, "xf_attn_fwd: drop_p out of range");
+  AttnFwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = a->B; p.H = a->H; p.Sq = a->Sq; p.Sk = a->Sk; p.dp = a->dp;
+  p.nchunk = (a->dp + 63) / 64;
+  p.q_tiles = (a->Sq + AF_BM - 1) / AF_BM;
+  p.sl2 = a->scale * 1.4426950408889634f;
+  p.kpm = a->key_padding_mask;
+  p.kpm_start = a->kpm_start;
+  p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
+  p.ldo = a->ldo;
+  p.lse = a->lse;
+  p.drop_p = a->drop_p;
+  p.drop_scale = a->drop_p > 0.f ? 1.f / (1.f - a->drop_p) : 1.f;
+  p.drop_seed = a->drop_seed; p.drop_stream = a->drop_stream;
+  p.drop_thresh = static_cast<uint32_t>(static_cast<double>(a->drop_p) * 4294967296.0);
+
+  CUtensorMap tq, tk, tv;
+  int rc;
+  const uint64_t cols = static_cast<uint64_t>(a->H) * a->dp;
+  if ((rc = make_tmap_3d_bf16(&tq, a->q, a->B, a->Sq, cols, a->ldq, 64, AF_BM))) return rc;
+  if ((rc = make_tmap_3d_bf16(&tk, a->k, a->B, a->Sk, cols, a->ldk, 64, AF_BN))) return rc;
+  if ((rc = make_tmap_3d_bf16(&tv, a->v, a->B, a->Sk, cols, a->ldv, 64, AF_BN))) return rc;
+
+  const int smem_bytes = 1024 + 1024 + p.nchunk * 16384 + 4 * p.nchunk * 8192 + 16384;
+  static bool attr_set = false;
+  if (!attr_set) {
+    XF_CUDA(cudaFuncSetAttribute(attn_fwd_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const int grid = a->B * a->H * p.q_tiles;
+  attn_fwd_tcgen05_kernel<<<grid, AF_THREADS, smem_bytes, stream>>>(tq, tk, tv, p);
+  g_launches.fetch_add(1);
+  XF_CUDA(cudaGetLastError());
+  return 0;
+}

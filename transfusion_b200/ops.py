@@ -8,7 +8,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import XfGemm, check, lib
+from ._lib import XfAttnFwd, XfGemm, XfLayerNorm, XfLayerNormBwd, check, lib
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -73,3 +73,124 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     g.max_ctas = max_ctas
     check(lib().xf_gemm(C.byref(g), _stream()), "xf_gemm")
     return out
+
+
+def _feat_dtype(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return 1
+    if t.dtype == torch.bfloat16:
+        return 0
+    raise _lib.XfError(f"feature map dtype {t.dtype} unsupported (fp32 or bf16)")
+
+
+def patchify(feat: torch.Tensor, p: int, tok: torch.Tensor) -> torch.Tensor:
+    """feat [B,C,H,W] (contiguous NCHW, fp32/bf16) -> tok bf16 [B*n, C*p*p] (utils.py:35-39 order)."""
+    B, Cc, H, W = feat.shape
+    if not feat.is_contiguous():
+        raise _lib.XfError("patchify: feature map must be contiguous NCHW")
+    _req(tok, torch.bfloat16, "tok")
+    check(lib().xf_patchify(_ptr(feat), _feat_dtype(feat), _ptr(tok), C.c_int64(tok.stride(0)), B, Cc, H, W, p, _stream()),
+          "xf_patchify")
+    return tok
+
+
+def fold(tok: torch.Tensor, feat: torch.Tensor, p: int, accumulate: bool = False) -> torch.Tensor:
+    """tok bf16 [B*n, C*p*p] -> feat [B,C,H,W] (utils.py:42-46)."""
+    B, Cc, H, W = feat.shape
+    if not feat.is_contiguous():
+        raise _lib.XfError("fold: feature map must be contiguous NCHW")
+    _req(tok, torch.bfloat16, "tok")
+    check(lib().xf_fold(_ptr(tok), C.c_int64(tok.stride(0)), _ptr(feat), _feat_dtype(feat), int(accumulate), B, Cc, H, W, p,
+                        _stream()), "xf_fold")
+    return feat
+
+
+def lang_rows_fwd(lang: torch.Tensor, kind: torch.Tensor, z: torch.Tensor, n: int):
+    B, L, D = lang.shape
+    S = z.shape[1]
+    _req(lang, torch.float32, "lang"); _req(kind, torch.float32, "kind"); _req(z, torch.bfloat16, "z")
+    check(lib().xf_lang_rows_fwd(_ptr(lang), _ptr(kind), _ptr(z), B, L, D, n, S, _stream()), "xf_lang_rows_fwd")
+
+
+def lang_rows_bwd(dz: torch.Tensor, dlang: Optional[torch.Tensor], dkind: torch.Tensor, B: int, L: int, n: int):
+    S, D = dz.shape[1], dz.shape[2]
+    _req(dz, torch.bfloat16, "dz"); _req(dkind, torch.float32, "dkind")
+    check(lib().xf_lang_rows_bwd(_ptr(dz), _ptr(dlang), _ptr(dkind), B, L, D, n, S, _stream()), "xf_lang_rows_bwd")
+
+
+def layernorm_fwd(x, y, gamma, beta, mean, rstd, rows: int, D: int, *, in_map=(0, 0, 0), out_map=(0, 0, 0),
+                  eps: float = 1e-5, drop_p: float = 0.0, drop_seed: int = 0, drop_stream: int = 0):
+    a = XfLayerNorm()
+    a.x, a.ldx = x.data_ptr(), x.stride(-2)
+    a.y, a.ldy = y.data_ptr(), y.stride(-2)
+    a.gamma, a.beta = gamma.data_ptr(), beta.data_ptr()
+    a.mean = mean.data_ptr() if mean is not None else None
+    a.rstd = rstd.data_ptr() if rstd is not None else None
+    a.rows, a.D = rows, D
+    a.in_rows_in, a.in_rows_out, a.in_row_off = in_map
+    a.out_rows_in, a.out_rows_out, a.out_row_off = out_map
+    a.eps = eps
+    a.drop_p, a.drop_seed, a.drop_stream = drop_p, drop_seed, drop_stream
+    check(lib().xf_layernorm_fwd(C.byref(a), _stream()), "xf_layernorm_fwd")
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, rows: int, D: int, *, dbias=None, dx2=None,
+                  in_map=(0, 0, 0), out_map=(0, 0, 0), dy_drop=(0.0, 0, 0), dx2_drop=(0.0, 0, 0)):
+    a = XfLayerNormBwd()
+    a.dy, a.lddy = dy.data_ptr(), dy.stride(-2)
+    a.x, a.ldx = x.data_ptr(), x.stride(-2)
+    a.gamma, a.mean, a.rstd = gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr()
+    a.dx, a.lddx = dx.data_ptr(), dx.stride(-2)
+    a.dx2 = dx2.data_ptr() if dx2 is not None else None
+    a.dgamma, a.dbeta = dgamma.data_ptr(), dbeta.data_ptr()
+    a.dbias = dbias.data_ptr() if dbias is not None else None
+    a.rows, a.D = rows, D
+    a.in_rows_in, a.in_rows_out, a.in_row_off = in_map
+    a.out_rows_in, a.out_rows_out, a.out_row_off = out_map
+    a.dy_drop_p, a.dy_drop_seed, a.dy_drop_stream = dy_drop
+    a.dx2_drop_p, a.dx2_drop_seed, a.dx2_drop_stream = dx2_drop
+    check(lib().xf_layernorm_bwd(C.byref(a), _stream()), "xf_layernorm_bwd")
+
+
+def colsum(x: torch.Tensor, out: torch.Tensor, rows: int, cols: int):
+    _req(x, torch.bfloat16, "x"); _req(out, torch.float32, "out")
+    check(lib().xf_colsum(_ptr(x), C.c_int64(x.stride(-2)), rows, cols, _ptr(out), _stream()), "xf_colsum")
+
+
+def cast_pad(src: torch.Tensor, dst: torch.Tensor, rows: int, cols: int, rin=0, rout=0, cin=0, cout=0):
+    _req(src, torch.float32, "src"); _req(dst, torch.bfloat16, "dst")
+    check(lib().xf_cast_pad(_ptr(src), C.c_int64(src.stride(0) if src.dim() > 1 else cols), _ptr(dst),
+                            C.c_int64(dst.stride(0) if dst.dim() > 1 else cols), rows, cols, rin, rout, cin, cout, _stream()),
+          "xf_cast_pad")
+
+
+def unpad_add(src: torch.Tensor, dst: torch.Tensor, rows: int, cols: int, rin=0, rout=0, cin=0, cout=0):
+    _req(src, torch.float32, "src"); _req(dst, torch.float32, "dst")
+    check(lib().xf_unpad_add(_ptr(src), C.c_int64(src.stride(0) if src.dim() > 1 else cols), _ptr(dst),
+                             C.c_int64(dst.stride(0) if dst.dim() > 1 else cols), rows, cols, rin, rout, cin, cout, _stream()),
+          "xf_unpad_add")
+
+
+def attn_delta(o: torch.Tensor, d_o: torch.Tensor, delta: torch.Tensor, rows: int, heads: int, dp: int):
+    check(lib().xf_attn_delta(_ptr(o), _ptr(d_o), C.c_int64(o.stride(-2)), rows, heads, dp, _ptr(delta), _stream()), "xf_attn_delta")
+
+
+def attn_fwd(q, k, v, out, lse, *, B: int, H: int, Sq: int, Sk: int, dp: int, scale: float,
+             key_padding_mask: Optional[torch.Tensor] = None, kpm_start: int = 0,
+             drop_p: float = 0.0, drop_seed: int = 0, drop_stream: int = 0):
+    """q/k/v/out: bf16 2-D views [B*S, >=H*dp] (may be column slices of one fused qkv buffer)."""
+    a = XfAttnFwd()
+    a.q, a.ldq = q.data_ptr(), q.stride(0)
+    a.k, a.ldk = k.data_ptr(), k.stride(0)
+    a.v, a.ldv = v.data_ptr(), v.stride(0)
+    a.out, a.ldo = out.data_ptr(), out.stride(0)
+    a.lse = lse.data_ptr() if lse is not None else None
+    if key_padding_mask is not None:
+        if key_padding_mask.dtype not in (torch.uint8, torch.bool):
+            raise _lib.XfError("key_padding_mask must be uint8/bool")
+        a.key_padding_mask = key_padding_mask.data_ptr()
+    a.kpm_start = kpm_start
+    a.B, a.H, a.Sq, a.Sk, a.dp = B, H, Sq, Sk, dp
+    a.scale = scale
+    a.drop_p, a.drop_seed, a.drop_stream = drop_p, drop_seed, drop_stream
+    check(lib().xf_attn_fwd(C.byref(a), _stream()), "xf_attn_fwd")
