@@ -139,9 +139,10 @@ int xf_cast_pad(const float* src, int64_t lds, void* dst_bf16, int64_t ldd, int 
 int xf_unpad_add(const float* src_padded, int64_t lds, float* dst, int64_t ldd, int rows, int cols, int rin, int rout, int cin,
                  int cout, xf_stream_t stream);
 
-/* delta[row, h] = sum_e O[row, h*dp+e] * dO[row, h*dp+e]  (attention backward pre-pass) */
-int xf_attn_delta(const void* o_bf16, const void* do_bf16, int64_t ld, int rows, int heads, int dp, float* delta,
-                  xf_stream_t stream);
+/* delta[b, h, s] = sum_e O[b*S+s, h*dp+e] * dO[b*S+s, h*dp+e]  (attention backward pre-pass);
+ * delta is [B, H, stat_stride] like the LSE. */
+int xf_attn_delta(const void* o_bf16, const void* do_bf16, int64_t ld, int B, int S, int heads, int dp, int stat_stride,
+                  float* delta, xf_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused multi-head attention (flash-style: no S x S tensor in HBM), tcgen05 + TMA + TMEM.
@@ -157,7 +158,8 @@ typedef struct XfAttnFwd {
   const void* k; int64_t ldk;
   const void* v; int64_t ldv;
   void* out; int64_t ldo;
-  float* lse;                        /* [B,H,Sq] fp32, log2-domain logsumexp of the scaled scores (for backward), or NULL */
+  float* lse;                        /* [B,H,lse_stride] fp32, log2-domain logsumexp of the scaled scores (for backward), or NULL */
+  int32_t lse_stride;                /* 0 = Sq; the backward wants a multiple of 32 >= Sq */
   const uint8_t* key_padding_mask;   /* [B,Sk] nonzero = ignore (True of src_key_padding_mask), or NULL */
   int32_t kpm_start;                 /* keys < kpm_start are never masked (visual tokens): lets tiles skip the mask */
   int32_t B, H, Sq, Sk, dp;
@@ -165,6 +167,25 @@ typedef struct XfAttnFwd {
   float drop_p; uint32_t drop_seed, drop_stream;   /* dropout on the attention probabilities */
 } XfAttnFwd;
 int xf_attn_fwd(const XfAttnFwd* a, xf_stream_t stream);
+
+/* Attention backward (recomputes the probabilities from q, k and the saved LSE): dq, dk, dv in the
+ * same token-major layout as q, k, v (pad columns come out zero).  Two tcgen05 passes: a
+ * query-stationary dQ pass and a key-stationary dK/dV pass.  dp must be a multiple of 32, <= 224. */
+typedef struct XfAttnBwd {
+  const void* q; int64_t ldq;
+  const void* k; int64_t ldk;
+  const void* v; int64_t ldv;
+  const void* d_out; int64_t lddo;
+  const float* lse; const float* delta; int32_t stat_stride;   /* [B,H,stat_stride] each */
+  void* dq; int64_t lddq;
+  void* dk; int64_t lddk;
+  void* dv; int64_t lddv;
+  const uint8_t* key_padding_mask;
+  int32_t B, H, Sq, Sk, dp;
+  float scale;
+  float drop_p; uint32_t drop_seed, drop_stream;   /* must equal the forward's */
+} XfAttnBwd;
+int xf_attn_bwd(const XfAttnBwd* a, xf_stream_t stream);
 
 #ifdef __cplusplus
 }

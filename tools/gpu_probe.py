@@ -102,6 +102,47 @@ def attn_case(B, H, Sq, Sk, d, mask=False, fused=True, seed=0):
         print("   pad-cols max:", padmax, flush=True)
 
 
+def attn_bwd_case(B, H, S, d, mask=True, seed=0):
+    torch.manual_seed(seed)
+    dev = "cuda"
+    dp = (d + 31) // 32 * 32
+    D = H * d
+    src = torch.randn(B, S, 3, H, d, device=dev).bfloat16()
+    qkv = torch.zeros(B * S, 3 * H * dp, device=dev, dtype=torch.bfloat16)
+    qkv.view(B, S, 3, H, dp)[..., :d] = src
+    q2, k2, v2 = qkv[:, :H * dp], qkv[:, H * dp:2 * H * dp], qkv[:, 2 * H * dp:]
+    kpm = None
+    if mask:
+        kpm = torch.zeros(B, S, dtype=torch.uint8, device=dev)
+        for b in range(B):
+            kpm[b, S - 1 - 5 * b - 2:] = 1
+    Sp = (S + 127) // 128 * 128
+    out = torch.zeros(B * S, H * dp, device=dev, dtype=torch.bfloat16)
+    lse = torch.zeros(B, H, Sp, device=dev)
+    ops.attn_fwd(q2, k2, v2, out, lse, B=B, H=H, Sq=S, Sk=S, dp=dp, scale=1.0 / d ** 0.5, key_padding_mask=kpm, kpm_start=0)
+    dout_src = torch.randn(B, S, H, d, device=dev).bfloat16()
+    dout = torch.zeros(B * S, H * dp, device=dev, dtype=torch.bfloat16)
+    dout.view(B, S, H, dp)[..., :d] = dout_src
+    delta = torch.zeros(B, H, Sp, device=dev)
+    ops.attn_delta(out, dout, delta, B, S, H, dp)
+    dqkv = torch.full((B * S, 3 * H * dp), 7.0, device=dev, dtype=torch.bfloat16)
+    ops.attn_bwd(q2, k2, v2, dout, lse, delta, dqkv[:, :H * dp], dqkv[:, H * dp:2 * H * dp], dqkv[:, 2 * H * dp:],
+                 B=B, H=H, Sq=S, Sk=S, dp=dp, scale=1.0 / d ** 0.5, key_padding_mask=kpm)
+    torch.cuda.synchronize()
+    # reference
+    qf, kf, vf = (src[:, :, i].float().reshape(B, S, D).requires_grad_(True) for i in range(3))
+    ref, _ = attn_ref(qf, kf, vf, H, d, kpm)
+    ref.backward(dout_src.float().reshape(B, S, D))
+    got = dqkv.view(B, S, 3, H, dp)
+    tag = f"attn_bwd B={B} H={H} S={S} d={d} mask={int(mask)}"
+    dref = (out.view(B, S, H, dp)[..., :d].float() * dout_src.float()).sum(-1).permute(0, 2, 1)
+    report(tag + " delta", rel(delta[:, :, :S], dref), 1e-4)
+    for i, (nm, g) in enumerate((("dq", qf.grad), ("dk", kf.grad), ("dv", vf.grad))):
+        report(tag + " " + nm, rel(got[:, :, i, :, :d].reshape(B, S, D).float(), g), 1.5e-2)
+    if dp != d:
+        print("   pad max:", float(got[..., d:].float().abs().max()), flush=True)
+
+
 def ln_case(rows, D, seed=0):
     torch.manual_seed(seed)
     dev = "cuda"
@@ -199,6 +240,13 @@ CASES = {
     "attn_cross": lambda: attn_case(2, 2, 200, 333, 32, mask=True, fused=False),
     "attn_d16": lambda: attn_case(2, 4, 70, 70, 16, mask=True),
     "attn_big": lambda: attn_case(2, 4, 3136, 3136, 224, mask=True),
+    "attn_bwd_small": lambda: attn_bwd_case(1, 1, 128, 32, mask=False),
+    "attn_bwd_s64": lambda: attn_bwd_case(1, 1, 64, 64, mask=False),
+    "attn_bwd_multi": lambda: attn_bwd_case(2, 2, 300, 64),
+    "attn_bwd_d224": lambda: attn_bwd_case(2, 4, 832, 224),
+    "attn_bwd_d178": lambda: attn_bwd_case(2, 4, 500, 178),
+    "attn_bwd_d16": lambda: attn_bwd_case(2, 4, 70, 16),
+    "attn_bwd_big": lambda: attn_bwd_case(1, 4, 3136, 224),
     "ln": lambda: (ln_case(999, 896), ln_case(300, 712), ln_case(129, 64)),
     "layout": lambda: (layout_case(2, 256, 16, 24, 4), layout_case(2, 512, 8, 12, 4, torch.bfloat16),
                        layout_case(2, 64, 12, 20, 2), layout_case(3, 2048, 24, 32, 1), layout_case(2, 8, 16, 24, 4)),

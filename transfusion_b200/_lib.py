@@ -71,8 +71,26 @@ class XfAttnFwd(C.Structure):
         ("v", C.c_void_p), ("ldv", C.c_int64),
         ("out", C.c_void_p), ("ldo", C.c_int64),
         ("lse", C.c_void_p),
+        ("lse_stride", C.c_int32),
         ("key_padding_mask", C.c_void_p),
         ("kpm_start", C.c_int32),
+        ("B", C.c_int32), ("H", C.c_int32), ("Sq", C.c_int32), ("Sk", C.c_int32), ("dp", C.c_int32),
+        ("scale", C.c_float),
+        ("drop_p", C.c_float), ("drop_seed", C.c_uint32), ("drop_stream", C.c_uint32),
+    ]
+
+
+class XfAttnBwd(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("ldq", C.c_int64),
+        ("k", C.c_void_p), ("ldk", C.c_int64),
+        ("v", C.c_void_p), ("ldv", C.c_int64),
+        ("d_out", C.c_void_p), ("lddo", C.c_int64),
+        ("lse", C.c_void_p), ("delta", C.c_void_p), ("stat_stride", C.c_int32),
+        ("dq", C.c_void_p), ("lddq", C.c_int64),
+        ("dk", C.c_void_p), ("lddk", C.c_int64),
+        ("dv", C.c_void_p), ("lddv", C.c_int64),
+        ("key_padding_mask", C.c_void_p),
         ("B", C.c_int32), ("H", C.c_int32), ("Sq", C.c_int32), ("Sk", C.c_int32), ("dp", C.c_int32),
         ("scale", C.c_float),
         ("drop_p", C.c_float), ("drop_seed", C.c_uint32), ("drop_stream", C.c_uint32),
@@ -106,7 +124,7 @@ EXPORTS = [
     "xf_version", "xf_last_error", "xf_launch_count", "xf_gemm",
     "xf_patchify", "xf_fold", "xf_lang_rows_fwd", "xf_lang_rows_bwd",
     "xf_layernorm_fwd", "xf_layernorm_bwd", "xf_colsum", "xf_cast_pad", "xf_unpad_add",
-    "xf_attn_delta", "xf_attn_fwd",
+    "xf_attn_delta", "xf_attn_fwd", "xf_attn_bwd",
 ]
 
 

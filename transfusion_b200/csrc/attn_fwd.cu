@@ -40,7 +40,8 @@ struct AttnFwdParams {
   int kpm_start;       // keys < kpm_start are never masked
   __nv_bfloat16* out;
   long long ldo;
-  float* lse;  // [B, H, Sq], log2 domain: m + log2(l)
+  float* lse;  // [B, H, lse_stride], log2 domain: m + log2(l)
+  int lse_stride;
   float drop_p, drop_scale;
   uint32_t drop_seed, drop_stream, drop_thresh;
 };
@@ -304,7 +305,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         }
       }
     }
-    if (row_ok && p.lse) p.lse[(static_cast<long long>(b) * p.H + hd) * p.Sq + q] = l > 0.f ? m_used + log2f(l) : -INFINITY;
+    if (row_ok && p.lse) p.lse[(static_cast<long long>(b) * p.H + hd) * p.lse_stride + q] = l > 0.f ? m_used + log2f(l) : -INFINITY;
   }
 
   tc_fence_before();
@@ -336,6 +337,7 @@ extern "C" int xf_attn_fwd(const XfAttnFwd* a, xf_stream_t stream_) {
   p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
   p.ldo = a->ldo;
   p.lse = a->lse;
+  p.lse_stride = a->lse_stride > 0 ? a->lse_stride : a->Sq;
   p.drop_p = a->drop_p;
   p.drop_scale = a->drop_p > 0.f ? 1.f / (1.f - a->drop_p) : 1.f;
   p.drop_seed = a->drop_seed; p.drop_stream = a->drop_stream;

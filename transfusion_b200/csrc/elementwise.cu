@@ -402,27 +402,29 @@ __global__ void unpad_add_kernel(const float* __restrict__ src, long long lds, f
   }
 }
 
-// delta[row, h] = sum_e O[row, h*dp + e] * dO[row, h*dp + e]   (attention backward pre-pass)
+// delta[b, h, s] = sum_e O[b*S+s, h*dp + e] * dO[b*S+s, h*dp + e]   (attention backward pre-pass)
 __global__ void __launch_bounds__(256)
-attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o, long long ld, int rows,
-                  int heads, int dp, float* __restrict__ delta) {
+attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o, long long ld, int B, int S,
+                  int heads, int dp, int stat_stride, float* __restrict__ delta) {
   const int warps_per_cta = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
-  const long long total = static_cast<long long>(rows) * heads;
+  const long long total = static_cast<long long>(B) * S * heads;
   for (long long w = blockIdx.x * static_cast<long long>(warps_per_cta) + (threadIdx.x >> 5); w < total;
        w += static_cast<long long>(gridDim.x) * warps_per_cta) {
     const int h = w % heads;
-    const long long r = w / heads;
+    const long long r = w / heads;   // token row b*S + s
+    const int sidx = r % S;
+    const int b = r / S;
     const __nv_bfloat16* po = o + r * ld + h * dp;
     const __nv_bfloat16* pd = d_o + r * ld + h * dp;
     float s = 0.f;
     for (int e = lane * 2; e < dp; e += 64) {
       const uint32_t a = *reinterpret_cast<const uint32_t*>(po + e);
-      const uint32_t b = *reinterpret_cast<const uint32_t*>(pd + e);
-      s += bf16_lo(a) * bf16_lo(b) + bf16_hi(a) * bf16_hi(b);
+      const uint32_t bb = *reinterpret_cast<const uint32_t*>(pd + e);
+      s += bf16_lo(a) * bf16_lo(bb) + bf16_hi(a) * bf16_hi(bb);
     }
     s = warp_sum(s);
-    if (lane == 0) delta[w] = s;
+    if (lane == 0) delta[(static_cast<long long>(b) * heads + h) * stat_stride + sidx] = s;
   }
 }
 
@@ -592,12 +594,14 @@ extern "C" int xf_unpad_add(const float* src, int64_t lds, float* dst, int64_t l
   return 0;
 }
 
-extern "C" int xf_attn_delta(const void* o, const void* d_o, int64_t ld, int rows, int heads, int dp, float* delta, xf_stream_t s) {
+extern "C" int xf_attn_delta(const void* o, const void* d_o, int64_t ld, int B, int S, int heads, int dp, int stat_stride,
+                             float* delta, xf_stream_t s) {
   if (!o || !d_o || !delta) return fail(-1, "xf_attn_delta: null pointer");
   if (dp % 2) return fail(-2, "xf_attn_delta: dp must be even");
-  if (rows == 0) return 0;
-  attn_delta_kernel<<<grid_for(static_cast<long long>(rows) * heads, 8), 256, 0, reinterpret_cast<cudaStream_t>(s)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(o), reinterpret_cast<const __nv_bfloat16*>(d_o), ld, rows, heads, dp, delta);
+  if (stat_stride < S) return fail(-3, "xf_attn_delta: stat_stride < S");
+  if (B * S == 0) return 0;
+  attn_delta_kernel<<<grid_for(static_cast<long long>(B) * S * heads, 8), 256, 0, reinterpret_cast<cudaStream_t>(s)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(o), reinterpret_cast<const __nv_bfloat16*>(d_o), ld, B, S, heads, dp, stat_stride, delta);
   g_launches.fetch_add(1);
   XF_CUDA(cudaGetLastError());
   return 0;

@@ -43,18 +43,19 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t
 }
 
 int make_tmap_3d_bf16(CUtensorMap* out, const void* ptr, uint64_t batch, uint64_t rows, uint64_t cols, uint64_t ld,
-                      uint32_t box_cols, uint32_t box_rows) {
+                      uint32_t box_cols, uint32_t box_rows, int swizzle_bytes) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return fail(-10, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return fail(-11, "TMA base pointer not 16-byte aligned");
   if ((ld * 2) % 16 != 0) return fail(-12, "TMA row pitch %llu B not a multiple of 16", (unsigned long long)(ld * 2));
-  if (box_cols * 2 > 128 || box_rows > 256) return fail(-13, "bad TMA box %u x %u", box_cols, box_rows);
+  if (static_cast<int>(box_cols * 2) > swizzle_bytes || box_rows > 256) return fail(-13, "bad TMA box %u x %u", box_cols, box_rows);
+  const CUtensorMapSwizzle swz = swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
   cuuint64_t gdim[3] = {cols, rows, batch};
   cuuint64_t gstr[2] = {ld * 2, rows * ld * 2};
   cuuint32_t box[3] = {box_cols, box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(-14, "cuTensorMapEncodeTiled(3d) failed: %d", (int)r);
   return 0;

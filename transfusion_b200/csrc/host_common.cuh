@@ -46,7 +46,7 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t
 // 3-D bf16 tensor [batch, rows, cols] (cols contiguous, row pitch ld, batch pitch rows*ld);
 // box = box_cols x box_rows x 1, SWIZZLE_128B, out-of-bounds reads as zero (per batch).
 int make_tmap_3d_bf16(CUtensorMap* out, const void* ptr, uint64_t batch, uint64_t rows, uint64_t cols, uint64_t ld,
-                      uint32_t box_cols, uint32_t box_rows);
+                      uint32_t box_cols, uint32_t box_rows, int swizzle_bytes = 128);
 
 int sm_count();
 

@@ -161,13 +161,15 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 //   K-major : rows of 128 B (64 bf16 along K); 8-row groups SBO apart; K advance = +32 B per UMMA_K.
 //   MN-major: 64-element MN chunks (128 B) x 8 K-rows = 1024 B atoms; SBO = stride between 8-row K
 //             groups, LBO = stride between 64-element MN chunks; K advance = +2*SBO per UMMA_K.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//   SWIZZLE_64B (layout code 4): same forms with 64-byte rows (32 bf16), 512-byte atoms.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout = 2) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= static_cast<uint64_t>(1) << 46;  // descriptor version (Blackwell)
-  d |= static_cast<uint64_t>(2) << 61;  // SWIZZLE_128B
+  d |= static_cast<uint64_t>(layout) << 61;  // 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
   return d;
 }
 

@@ -8,7 +8,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import XfAttnFwd, XfGemm, XfLayerNorm, XfLayerNormBwd, check, lib
+from ._lib import XfAttnBwd, XfAttnFwd, XfGemm, XfLayerNorm, XfLayerNormBwd, check, lib
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -171,8 +171,10 @@ def unpad_add(src: torch.Tensor, dst: torch.Tensor, rows: int, cols: int, rin=0,
           "xf_unpad_add")
 
 
-def attn_delta(o: torch.Tensor, d_o: torch.Tensor, delta: torch.Tensor, rows: int, heads: int, dp: int):
-    check(lib().xf_attn_delta(_ptr(o), _ptr(d_o), C.c_int64(o.stride(-2)), rows, heads, dp, _ptr(delta), _stream()), "xf_attn_delta")
+def attn_delta(o: torch.Tensor, d_o: torch.Tensor, delta: torch.Tensor, B: int, S: int, heads: int, dp: int):
+    """delta [B, heads, stat_stride] fp32 (stat_stride = delta.shape[-1])."""
+    check(lib().xf_attn_delta(_ptr(o), _ptr(d_o), C.c_int64(o.stride(-2)), B, S, heads, dp, delta.shape[-1], _ptr(delta),
+                              _stream()), "xf_attn_delta")
 
 
 def attn_fwd(q, k, v, out, lse, *, B: int, H: int, Sq: int, Sk: int, dp: int, scale: float,
@@ -185,6 +187,7 @@ def attn_fwd(q, k, v, out, lse, *, B: int, H: int, Sq: int, Sk: int, dp: int, sc
     a.v, a.ldv = v.data_ptr(), v.stride(0)
     a.out, a.ldo = out.data_ptr(), out.stride(0)
     a.lse = lse.data_ptr() if lse is not None else None
+    a.lse_stride = lse.shape[-1] if lse is not None else 0
     if key_padding_mask is not None:
         if key_padding_mask.dtype not in (torch.uint8, torch.bool):
             raise _lib.XfError("key_padding_mask must be uint8/bool")
@@ -194,3 +197,25 @@ def attn_fwd(q, k, v, out, lse, *, B: int, H: int, Sq: int, Sk: int, dp: int, sc
     a.scale = scale
     a.drop_p, a.drop_seed, a.drop_stream = drop_p, drop_seed, drop_stream
     check(lib().xf_attn_fwd(C.byref(a), _stream()), "xf_attn_fwd")
+
+
+def attn_bwd(q, k, v, d_out, lse, delta, dq, dk, dv, *, B: int, H: int, Sq: int, Sk: int, dp: int, scale: float,
+             key_padding_mask: Optional[torch.Tensor] = None, drop_p: float = 0.0, drop_seed: int = 0,
+             drop_stream: int = 0):
+    a = XfAttnBwd()
+    a.q, a.ldq = q.data_ptr(), q.stride(0)
+    a.k, a.ldk = k.data_ptr(), k.stride(0)
+    a.v, a.ldv = v.data_ptr(), v.stride(0)
+    a.d_out, a.lddo = d_out.data_ptr(), d_out.stride(0)
+    a.lse, a.delta, a.stat_stride = lse.data_ptr(), delta.data_ptr(), lse.shape[-1]
+    if delta.shape[-1] != lse.shape[-1]:
+        raise _lib.XfError("lse and delta must share their last-dim stride")
+    a.dq, a.lddq = dq.data_ptr(), dq.stride(0)
+    a.dk, a.lddk = dk.data_ptr(), dk.stride(0)
+    a.dv, a.lddv = dv.data_ptr(), dv.stride(0)
+    if key_padding_mask is not None:
+        a.key_padding_mask = key_padding_mask.data_ptr()
+    a.B, a.H, a.Sq, a.Sk, a.dp = B, H, Sq, Sk, dp
+    a.scale = scale
+    a.drop_p, a.drop_seed, a.drop_stream = drop_p, drop_seed, drop_stream
+    check(lib().xf_attn_bwd(C.byref(a), _stream()), "xf_attn_bwd")
