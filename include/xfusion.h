@@ -187,6 +187,12 @@ typedef struct XfAttnBwd {
 } XfAttnBwd;
 int xf_attn_bwd(const XfAttnBwd* a, xf_stream_t stream);
 
+/* out[r,:] = in[(r / rin) * rout + r % rin + roff, :] with the dropout mask of the forward write at
+ * the source position, colsum += column sums of out (may be NULL).  Patch-embed backward: gathers the
+ * visual rows of d(sequence) (cross_f_box_layers.py:72-74 backward; colsum = image_kind_embedding grad). */
+int xf_rows_gather(const void* in_bf16, int64_t ldi, void* out_bf16, int64_t ldo, int rows, int D, int rin, int rout, int roff,
+                   float* colsum, float drop_p, uint32_t drop_seed, uint32_t drop_stream, xf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -231,7 +231,81 @@ def misc_case():
     report("attn_delta", rel(delta, (o.float() * do.float()).view(50, 4, 32).sum(-1)), 1e-5)
 
 
+def level_debug(name="c4_d40_oddhead", level=0):
+    """Stage-by-stage comparison of one level of a golden case against a torch fp32 restatement."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    from tests.golden_utils import load_golden
+    from tests.fusion_testlib import build_module
+    from transfusion_b200.cross_fusion import level_fn
+    from oracle import ref_math
+    g = load_golden(name)
+    feats = g["features"]
+    keys = sorted(feats, key=int)
+    shapes = [tuple(feats[k].shape[2:]) for k in keys]
+    channels = [feats[k].shape[1] for k in keys]
+    D = g["lang"].shape[-1]
+    m = build_module(D, shapes, channels, g["patch"], g["layers"], g["heads"], lm=g["lm_on"])
+    m.load_state_dict(g["params"], strict=False)
+    m.train()
+    sink = {}
+    level_fn.DEBUG_SINK = sink
+    i = level
+    feat = feats[keys[i]].cuda()
+    lang = g["lang"].cuda()
+    pad = ~(g["att_mask"].bool()).cuda()
+    with torch.no_grad():
+        fused, _ = m.run_level(i, feat, lang, pad)
+    torch.cuda.synchronize()
+    level_fn.DEBUG_SINK = None
+    # reference intermediates (fp32, on GPU)
+    sd = {k: v.cuda() for k, v in g["params"].items()}
+    p = g["patch"][i]; H = g["heads"]; nl = g["layers"][i]
+    B, C, h, w = feat.shape
+    n = (h // p) * (w // p)
+    enc = f"cross_fusion_encoders.{i}."
+    tok = ref_math.patchify(feat, p)
+    report("tok", rel(sink["tok"].view_as(tok), tok), 5e-3)
+    x = tok @ sd[f"patches_to_token.{i}.weight"].reshape(D, -1).t() + ref_math.sin1d_table(n, D).cuda() + sd[enc + "image_kind_embedding"].reshape(D)
+    lg = lang + sd[enc + "lang_kind_embedding"].reshape(D)
+    z = torch.cat([x, lg], 1)
+    report("z0", rel(sink["z0"], z), 5e-3)
+    key_pad = torch.cat([torch.zeros(B, n, dtype=torch.bool, device="cuda"), pad], 1)
+    d = D // H; dp = (d + 31) // 32 * 32
+    S = z.shape[1]
+    for l in range(nl):
+        pre = enc + f"t_encoder.layers.{l}."
+        qkv = z @ sd[pre + "self_attn.in_proj_weight"].t() + sd[pre + "self_attn.in_proj_bias"]
+        got = sink[f"l{l}.qkv"].view(B, S, 3, H, dp)
+        report(f"l{l}.qkv", rel(got[..., :d].reshape(B, S, 3 * D), qkv), 5e-3)
+        print("    qkv pad max", float(got[..., d:].abs().max()) if dp != d else 0.0)
+        q, k, v = qkv.split(D, -1)
+        o = ref_math.attention(q, k, v, key_pad, H)
+        got = sink[f"l{l}.att"].view(B, S, H, dp)[..., :d].reshape(B, S, D)
+        report(f"l{l}.att", rel(got, o), 8e-3)
+        y1 = z + o @ sd[pre + "self_attn.out_proj.weight"].t() + sd[pre + "self_attn.out_proj.bias"]
+        report(f"l{l}.y1", rel(sink[f"l{l}.y1"].view_as(y1), y1), 8e-3)
+        x1 = ref_math.layer_norm(y1, sd[pre + "norm1.weight"], sd[pre + "norm1.bias"])
+        report(f"l{l}.x1", rel(sink[f"l{l}.x1"].view_as(x1), x1), 8e-3)
+        hh = ref_math.gelu_erf(x1 @ sd[pre + "linear1.weight"].t() + sd[pre + "linear1.bias"])
+        report(f"l{l}.h", rel(sink[f"l{l}.h"].view_as(hh), hh), 8e-3)
+        y2 = x1 + hh @ sd[pre + "linear2.weight"].t() + sd[pre + "linear2.bias"]
+        report(f"l{l}.y2", rel(sink[f"l{l}.y2"].view_as(y2), y2), 8e-3)
+        z = ref_math.layer_norm(y2, sd[pre + "norm2.weight"], sd[pre + "norm2.bias"])
+        report(f"l{l}.x2", rel(sink[f"l{l}.x2"].view_as(z), z), 8e-3)
+    vis = ref_math.layer_norm(z[:, :n], sd[enc + "final_norm_layer.weight"], sd[enc + "final_norm_layer.bias"])
+    report("vis", rel(sink["vis"].view_as(vis), vis), 8e-3)
+    yb = vis @ sd[f"tokens_to_features.{i}.linear.weight"].t() + sd[f"tokens_to_features.{i}.linear.bias"]
+    report("yb", rel(sink["yb"].view_as(yb), yb), 8e-3)
+    out = ref_math.fold(yb, C, p, h // p, w // p)
+    report("fused", rel(fused.float(), out), 8e-3)
+    report("fused vs golden", rel(fused.float().cpu(), g["out"][keys[i]]), 8e-3)
+
+
 CASES = {
+    "dbg_c4": lambda: level_debug("c4_d40_oddhead", 0),
+    "dbg_f4_l0": lambda: level_debug("fusion4_d32", 0),
+    "dbg_f4_l3": lambda: level_debug("fusion4_d32", 3),
+    "dbg_c5": lambda: level_debug("c5_d64_lm", 0),
     "attn_small": lambda: attn_case(1, 1, 128, 64, 64),
     "attn_2tiles": lambda: attn_case(1, 1, 128, 128, 64),
     "attn_multi": lambda: attn_case(2, 4, 300, 300, 64, mask=True),

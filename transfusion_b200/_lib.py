@@ -124,7 +124,7 @@ EXPORTS = [
     "xf_version", "xf_last_error", "xf_launch_count", "xf_gemm",
     "xf_patchify", "xf_fold", "xf_lang_rows_fwd", "xf_lang_rows_bwd",
     "xf_layernorm_fwd", "xf_layernorm_bwd", "xf_colsum", "xf_cast_pad", "xf_unpad_add",
-    "xf_attn_delta", "xf_attn_fwd", "xf_attn_bwd",
+    "xf_attn_delta", "xf_attn_fwd", "xf_attn_bwd", "xf_rows_gather",
 ]
 
 

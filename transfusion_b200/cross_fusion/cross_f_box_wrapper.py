@@ -1,0 +1,195 @@
+"""Drop-in mirror of modeling/cross_fusion/ego_fusion/cross_f_box_wrapper.py:41-303
+(``CrossFusionBoxWrapper``): same constructor arguments, ``forward(x, targets)`` contract, helper
+methods and state_dict keys, so ``modeling/model_factory.get_fusion_model`` and
+the ``runner/nao`` trainer pick it up unchanged.
+
+Per FPN level the reference runs Conv2d patch-embed -> CrossTransformerModuleBox -> RegroupPatchesLayerBox
+as ~60 ATen calls; here each level is ONE autograd node (FusionLevelFunction) that schedules the
+hand-written sm_100a kernels of libxfusion_sm100a.so.  There is no PyTorch fallback."""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from .cross_f_box_layers import CrossTransformerModuleBox
+from .level_fn import FusionLevelFunction, LevelConfig
+from .lm_layers import get_lm_layer
+from .utils import PositionalEmbeddingLayer, RegroupPatchesLayerBox, get_visual_token_mask
+
+MAX_NUM_PATCHES = 8192  # cross_f_box_wrapper.py:21
+
+
+def _default_pooling_factory(narr_embed_args, cross_layer_args):
+    """The language-context producer (SBert/MiniLM etc., narr_pooling_layers.py) is outside this path.
+    Inside the reference tree its own factory is used; elsewhere the caller injects a module."""
+    try:
+        from modeling.narration_embeds.narr_pooling_layers import get_narr_pooling_layer  # type: ignore
+    except Exception as e:  # not running inside the reference tree
+        raise RuntimeError(
+            "narr_pooling_layer: pass `narr_pooling_layer=<module>` to CrossFusionBoxWrapper when the "
+            "reference's modeling.narration_embeds package is not importable") from e
+    return get_narr_pooling_layer(narr_embed_args["text_pooling"])(narr_embed_args, cross_layer_args["narr_out_mode"])
+
+
+class CrossFusionBoxWrapper(nn.Module):
+    def __init__(self, rcnn_model, cross_layer_args, narr_embed_args, criterion=None, narr_pooling_layer=None):
+        super().__init__()
+        self.rcnn_model = rcnn_model
+        self.narr_embed_args = narr_embed_args
+        if "final_ln" in cross_layer_args["args"]:  # compatibility shim, reference :49-52
+            w_ln = cross_layer_args["args"].pop("final_ln")
+            cross_layer_args["args"]["final_norm"] = "ln" if w_ln else False
+        self.cross_encoder_args = cross_layer_args
+        self.forward_language_f = self.cross_encoder_args.get("forward_language_f", False)
+        self.vis_mask_type = self.cross_encoder_args.get("vis_mask_type", "global")
+        if self.cross_encoder_args.get("type", "cross_transformer") != "cross_transformer":
+            raise NotImplementedError("only type: cross_transformer (the shipped, constructible variant) is implemented")
+        if self.cross_encoder_args.get("narr_out_mode", "tokens") != "tokens":
+            raise NotImplementedError("narr_out_mode 'embedding' is dead code in the reference box model")
+        if self.cross_encoder_args.get("pos_embedding", "sin1d") != "sin1d":
+            raise NotImplementedError("only the shipped sin1d positional embedding is implemented")
+        pn = self.cross_encoder_args.get("patch_norm", {}) or {}
+        if pn.get("visual") or pn.get("language"):
+            raise NotImplementedError("patch_norm is null in the shipped config")
+
+        self.dsampled_shapes = rcnn_model.get_dsampled_shapes()
+        self.in_rgb_channels = rcnn_model.get_features_out_channels()
+        self.fpn_features_idx = self.cross_encoder_args["fpn_features"][: len(self.dsampled_shapes)]
+        self.vis_input_key = "image"
+        self.token_dim = self.cross_encoder_args["args"]["input_f_size"]
+
+        if narr_pooling_layer is not None:
+            self.narr_pooling_layer = narr_pooling_layer
+        else:
+            self.narr_pooling_layer = _default_pooling_factory(narr_embed_args, cross_layer_args)
+
+        self.cross_fusion_encoders = nn.ModuleList(self.setup_cross_fusion_encoders(self.cross_encoder_args))
+        self.patches_to_token = nn.ModuleList(self.setup_patches_to_token())
+        self.tokens_to_features = nn.ModuleList(self.setup_token_to_features_layers())
+
+        self.criterion = criterion if criterion is not None else {}
+        if self.criterion.get("lm", None):
+            self.lm_layer = get_lm_layer(self)
+        self.lm_on = self.criterion.get("lm", False)
+        self.use_lm_f = self.cross_encoder_args["lm_args"].get("use_lm_f", False)
+        self.multi_lm = self.cross_encoder_args["lm_args"].get("multi", False) and self.lm_on and not self.use_lm_f
+        self._step = 0
+
+    # ---- construction (reference :83-163, 266-294) ------------------------------------------
+    def setup_cross_fusion_encoders(self, cross_encoder_args):
+        encoders = []
+        all_num_layers = cross_encoder_args["args"].pop("num_layers")
+        if not isinstance(all_num_layers, list):
+            all_num_layers = [all_num_layers] * len(self.dsampled_shapes)
+        for i in range(len(self.dsampled_shapes)):
+            pos = PositionalEmbeddingLayer(cross_encoder_args["pos_embedding"], MAX_NUM_PATCHES, self.token_dim)
+            encoders.append(CrossTransformerModuleBox(no_patches=MAX_NUM_PATCHES, pos_embedding_layer=pos,
+                                                      lang_pos_embedding=None, num_layers=all_num_layers[i],
+                                                      **cross_encoder_args["args"]))
+        return encoders
+
+    def setup_token_to_features_layers(self):
+        layers = []
+        for i, shape in enumerate(self.dsampled_shapes):
+            layers.append(RegroupPatchesLayerBox(self.token_dim, shape[0], shape[1], self.cross_encoder_args["patch_h"][i],
+                                                 self.cross_encoder_args["patch_w"][i], self.in_rgb_channels[i],
+                                                 self.cross_encoder_args["backproj_dropout"],
+                                                 self.cross_encoder_args.get("backproj_activ_f", None)))
+        return layers
+
+    def setup_patches_to_token(self):
+        mods = []
+        for i, _ in enumerate(self.dsampled_shapes):
+            ph, pw = self.cross_encoder_args["patch_h"][i], self.cross_encoder_args["patch_w"][i]
+            mods.append(self.setup_patch_to_token(self.cross_encoder_args["patch_norm"], self.in_rgb_channels[i] * ph * pw,
+                                                  self.token_dim, in_channels=self.in_rgb_channels[i], patch_h=ph, patch_w=pw))
+        return mods
+
+    def setup_patch_to_token(self, patch_norm, patch_dim, token_dim, in_channels=None, patch_h=None, patch_w=None):
+        if in_channels is None:
+            raise NotImplementedError("linear patch embedding without channels is not used by the box model")
+        return nn.Conv2d(in_channels=in_channels, out_channels=token_dim, kernel_size=(patch_h, patch_w),
+                         stride=(patch_h, patch_w), bias=False)
+
+    # ---- the hot path -----------------------------------------------------------------------
+    def run_level(self, i: int, feat: torch.Tensor, language_f: torch.Tensor, lang_pad_mask, need_lang_out=False):
+        """One FPN level: reference :180-212.  Returns (fused [B,C,h,w], fused language tokens or None)."""
+        enc: CrossTransformerModuleBox = self.cross_fusion_encoders[i]
+        t2f: RegroupPatchesLayerBox = self.tokens_to_features[i]
+        pe = self.patches_to_token[i]
+        get_visual_token_mask(None, self.vis_mask_type)
+        p = t2f.patch_h
+        n = (feat.shape[2] // p) * (feat.shape[3] // p)
+        if n > MAX_NUM_PATCHES:
+            raise ValueError(f"{n} visual tokens exceed MAX_NUM_PATCHES={MAX_NUM_PATCHES}")
+        if feat.shape[2] % p or feat.shape[3] % p:
+            raise ValueError("feature map size must be divisible by the patch size")
+        seed = 0
+        if self.training:
+            seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
+        cfg = LevelConfig(level=i, patch=p, num_heads=enc.num_heads, num_layers=enc.num_layers, training=self.training,
+                          patch_dropout=float(enc.patch_dropout), token_dropout=float(enc.token_dropout),
+                          backproj_dropout=float(t2f.back_dropout.p), seed=seed, need_lang_out=need_lang_out)
+        params = [pe.weight, enc.image_kind_embedding, enc.lang_kind_embedding, enc.pos_embedding_layer.table(),
+                  *enc.level_params(), enc.final_norm_layer.weight, enc.final_norm_layer.bias, t2f.linear.weight,
+                  t2f.linear.bias]
+        fused, lang_out = FusionLevelFunction.apply(cfg, feat, language_f, lang_pad_mask, *params)
+        return fused, (lang_out if need_lang_out else None)
+
+    def forward(self, x, targets=None):
+        visual_data = x[self.vis_input_key]
+        features_dict = self.rcnn_model.forward_features(visual_data, targets)
+        language_f, att_w, att_mask = self.narr_pooling_layer(x["language_f"], pad_mask=True)
+        lang_pad = None if att_mask is None else ~(att_mask.type(torch.bool))  # reference :196
+        need_lang_out = bool(self.multi_lm or self.forward_language_f or (self.lm_on and not self.use_lm_f))
+        mscale_l_features = []
+        fused_l_features = None
+        for i, key in enumerate(self.fpn_features_idx):
+            key = str(key)
+            feat = features_dict["features"][key]
+            self.tokens_to_features[i].init_h = feat.shape[2]
+            self.tokens_to_features[i].init_w = feat.shape[3]
+            fused, fused_l_features = self.run_level(i, feat, language_f, lang_pad, need_lang_out)
+            if self.multi_lm:
+                mscale_l_features.append(fused_l_features)
+            if self.forward_language_f:
+                if self.forward_language_f == "direct":
+                    language_f = fused_l_features
+                elif self.forward_language_f == "sum":
+                    language_f = language_f + fused_l_features
+                else:
+                    raise NotImplementedError()
+            features_dict["features"][key] = fused
+        features_dict = self.rcnn_model.apply_fpn(features_dict)
+        if "hand_boxes" in x:
+            features_dict["hand_boxes"] = x["hand_boxes"]
+        if "hand_poses" in x:
+            features_dict["hand_poses"] = x["hand_poses"]
+        rcnn_outs = self.rcnn_model.apply_rpn_roi_on_features(features_dict)
+        if self.lm_on:
+            rcnn_outs["lm"] = self.lm_layer(
+                mscale_l_features if self.multi_lm else fused_l_features if not self.use_lm_f else language_f,
+                None if att_mask is None else att_mask.type(torch.bool))
+        return rcnn_outs
+
+    # ---- delegations (reference :232-264) ---------------------------------------------------
+    def call_model_epoch_triggers(self, epoch):
+        if epoch >= self.narr_embed_args["train_ep"] and self.narr_embed_args["train_ep"] != -1:
+            self.narr_pooling_layer.unfreeze_embeddings()
+        self.rcnn_model.call_model_epoch_triggers(epoch)
+
+    def dets_from_outs(self, outs, orig_img_shapes=None, targets=None, hand_poses=None, hand_boxes=None):
+        return self.rcnn_model.dets_from_outs(outs, orig_img_shapes, targets=targets, hand_poses=hand_poses,
+                                              hand_boxes=hand_boxes)
+
+    def forward_w_dets(self, x, targets=None):
+        outs = self(x, targets)
+        original_image_shapes = [tuple(img.shape[1:]) for img in x["image"]]
+        return self.dets_from_outs(outs, orig_img_shapes=original_image_shapes, targets=targets,
+                                   hand_poses=x.get("hand_poses"), hand_boxes=x.get("hand_boxes"))
+
+    def postprocess_detections(self, detections, proposals, image_sizes, original_image_shapes):
+        return self.rcnn_model.postprocess_detections(detections, proposals, image_sizes, original_image_shapes)
+
+    def compute_rpn_loss(self, objectness, pred_bbox_deltas, labels, regression_targets):
+        return self.rcnn_model.compute_rpn_loss(objectness, pred_bbox_deltas, labels, regression_targets)

@@ -1,0 +1,363 @@
+"""The per-FPN-level schedule of the fusion hot path as one ``torch.autograd.Function`` over the
+C-ABI CUDA library (cross_f_box_wrapper.py:177-212 + cross_f_box_layers.py:69-108 + the encoder
+layers of torch18_adapters.py:108-113).  Torch supplies device memory, streams and the autograd
+edge; every FLOP and every byte moved on this path is a hand-written sm_100a kernel.
+
+Data layout in HBM (bf16 activations, fp32 statistics / gradients):
+  tok   [B*n, C*p*p]   patchified feature map (A operand of the patch-embed GEMM)
+  z     [B, S, D]      token sequence, S = n + L; visual rows first, language rows last
+  qkv   [B*S, 3*H*dp]  fused in-proj output, head hd of Q/K/V at columns (w*H + hd)*dp (dp = head
+                       dim padded to a multiple of 32 with zero weights, e.g. 178 -> 192)
+  att   [B*S, H*dp]    attention output, heads merged (A operand of out_proj)
+  u, h  [B*S, 2D]      FFN pre-activation / activation
+  lse   [B, H, Sp]     log2-domain logsumexp (Sp = S rounded up to 128)
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+
+from .. import ops
+
+LN_EPS = 1e-5
+
+# dropout sites inside one encoder layer (stream ids for the counter-based RNG)
+SITE_ATTN, SITE_DROP1, SITE_FFN, SITE_DROP2 = 0, 1, 2, 3
+SITE_PATCH, SITE_BACKPROJ = 60, 61
+
+
+@dataclass
+class LevelConfig:
+    level: int
+    patch: int
+    num_heads: int
+    num_layers: int
+    training: bool
+    patch_dropout: float
+    token_dropout: float
+    backproj_dropout: float
+    seed: int = 0
+    need_lang_out: bool = False
+
+    def stream(self, layer: int, site: int) -> int:
+        return ((self.level * 16 + layer) * 64 + site) & 0xFFFFFFFF
+
+
+# dev aid: when set to a dict, the forward stores clones of its intermediates in it (tools/gpu_probe.py)
+DEBUG_SINK = None
+
+
+def _dbg(name, t):
+    if DEBUG_SINK is not None and t is not None:
+        DEBUG_SINK[name] = t.detach().float().clone()
+
+
+N_HEAD_PARAMS = 4       # patch-embed weight, image_kind, lang_kind, pos table (buffer, no grad)
+N_LAYER_PARAMS = 12
+N_TAIL_PARAMS = 4       # final LN weight/bias, back-projection weight/bias
+
+
+def _split_k_for(tiles: int, total_kb: int) -> int:
+    """Enough work items to fill ~2 waves of 148 CTAs, at least 4 k-blocks per split."""
+    want = max(1, (2 * 148 + tiles - 1) // tiles)
+    return max(1, min(want, max(1, total_kb // 4)))
+
+
+def _wgrad(dy: torch.Tensor, x: torch.Tensor, out_f32: torch.Tensor, n_out: int, k_in: int, tokens: int):
+    """out_f32[n_out, k_in] += dy[tokens, n_out]^T @ x[tokens, k_in]  (both operands MN-major)."""
+    tile_n = 0
+    tn = 256 if k_in % 256 == 0 else (224 if k_in % 224 == 0 else (192 if k_in % 192 == 0 else 128))
+    tiles = ((n_out + 127) // 128) * ((k_in + tn - 1) // tn)
+    split = _split_k_for(tiles, (tokens + 63) // 64)
+    ops.gemm(dy, x, out_f32, M=n_out, N=k_in, K=tokens, a_mn_major=True, b_mn_major=True, accumulate=True,
+             split_k=split, tile_n=tile_n)
+
+
+class FusionLevelFunction(torch.autograd.Function):
+    """fused, lang_out = f(feat, lang, key_pad, *params).  See module docstring."""
+
+    @staticmethod
+    def forward(ctx, cfg: LevelConfig, feat: torch.Tensor, lang: torch.Tensor, key_pad: Optional[torch.Tensor], *params):
+        if not feat.is_cuda:
+            raise RuntimeError("transfusion_b200: the fusion path has no CPU implementation (CUDA tensors required)")
+        dev = feat.device
+        B, C, Hf, Wf = feat.shape
+        p = cfg.patch
+        gh, gw = Hf // p, Wf // p
+        n = gh * gw
+        L = lang.shape[1]
+        D = lang.shape[2]
+        S = n + L
+        H = cfg.num_heads
+        d = D // H
+        dp = (d + 31) // 32 * 32
+        Dp = H * dp
+        F = params[N_HEAD_PARAMS + 4].shape[0]  # linear1.weight [F, D]
+        K = C * p * p
+        M = B * S
+        Sp = (S + 127) // 128 * 128
+        nl = cfg.num_layers
+        train = cfg.training
+        need_grad = any(ctx.needs_input_grad)  # grad mode is off inside Function.forward; this is the autograd edge
+        bf = torch.bfloat16
+        scale = 1.0 / math.sqrt(d)
+
+        wpe, img_kind, lang_kind, pos_table = params[:N_HEAD_PARAMS]
+        layer_params = [params[N_HEAD_PARAMS + i * N_LAYER_PARAMS: N_HEAD_PARAMS + (i + 1) * N_LAYER_PARAMS] for i in range(nl)]
+        lnf_w, lnf_b, wbp, bbp = params[N_HEAD_PARAMS + nl * N_LAYER_PARAMS:]
+
+        def empty(*shape, dtype=bf):
+            return torch.empty(*shape, device=dev, dtype=dtype)
+
+        feat_c = feat.contiguous()
+        if feat_c.dtype not in (torch.float32, torch.bfloat16):
+            feat_c = feat_c.float()
+        lang_c = lang.contiguous().float()
+        kpm = None
+        if key_pad is not None:
+            kpm = torch.zeros(B, S, device=dev, dtype=torch.uint8)
+            kpm[:, n:] = key_pad.to(torch.uint8)
+
+        pd_patch = cfg.patch_dropout if train else 0.0
+        pd_tok = cfg.token_dropout if train else 0.0
+        pd_back = cfg.backproj_dropout if train else 0.0
+        seed = cfg.seed
+
+        # ---- bf16 weight copies (head dim padded d -> dp with zero rows / columns)
+        wpe_b = empty(D, K); ops.cast_pad(wpe.reshape(D, K), wpe_b, D, K)
+        wbp_b = empty(K, D); ops.cast_pad(wbp, wbp_b, K, D)
+        lw = []
+        for (in_w, in_b, out_w, out_b, w1, b1, w2, b2, n1w, n1b, n2w, n2b) in layer_params:
+            if dp != d:
+                win_b = torch.zeros(3 * Dp, D, device=dev, dtype=bf)
+                ops.cast_pad(in_w, win_b, 3 * D, D, rin=d, rout=dp)
+                bin_p = torch.zeros(3 * H, dp, device=dev, dtype=torch.float32)
+                bin_p[:, :d] = in_b.reshape(3 * H, d)
+                bin_p = bin_p.reshape(3 * Dp)
+                wo_b = torch.zeros(D, Dp, device=dev, dtype=bf)
+                ops.cast_pad(out_w, wo_b, D, D, cin=d, cout=dp)
+            else:
+                win_b = empty(3 * D, D); ops.cast_pad(in_w, win_b, 3 * D, D)
+                bin_p = in_b
+                wo_b = empty(D, D); ops.cast_pad(out_w, wo_b, D, D)
+            w1_b = empty(F, D); ops.cast_pad(w1, w1_b, F, D)
+            w2_b = empty(D, F); ops.cast_pad(w2, w2_b, D, F)
+            lw.append((win_b, bin_p, wo_b, w1_b, w2_b))
+
+        # ---- patch embedding + positional / kind embeddings, language rows   (K1-K4)
+        tok = empty(B * n, K)
+        ops.patchify(feat_c, p, tok)
+        z = empty(B, S, D)
+        z2 = z.view(M, D)
+        ops.gemm(tok, wpe_b, z2, M=B * n, N=D, K=K, bias=img_kind.reshape(D), pos_table=pos_table,
+                 rows_in=n, rows_out=S, drop_p=pd_patch, drop_seed=seed, drop_stream=cfg.stream(0, SITE_PATCH))
+        ops.lang_rows_fwd(lang_c, lang_kind.reshape(D).contiguous(), z, n)
+        _dbg("tok", tok); _dbg("z0", z)
+
+        saved_layers = []
+        x = z2
+        for l in range(nl):
+            (in_w, in_b, out_w, out_b, w1, b1, w2, b2, n1w, n1b, n2w, n2b) = layer_params[l]
+            win_b, bin_p, wo_b, w1_b, w2_b = lw[l]
+            qkv = torch.zeros(M, 3 * Dp, device=dev, dtype=bf) if False else empty(M, 3 * Dp)
+            ops.gemm(x, win_b, qkv, M=M, N=3 * Dp, K=D, bias=bin_p)                                   # K5
+            att = empty(M, Dp)
+            lse = empty(B, H, Sp, dtype=torch.float32) if need_grad else None
+            ops.attn_fwd(qkv[:, :Dp], qkv[:, Dp:2 * Dp], qkv[:, 2 * Dp:], att, lse, B=B, H=H, Sq=S, Sk=S, dp=dp,
+                         scale=scale, key_padding_mask=kpm, kpm_start=n, drop_p=pd_tok, drop_seed=seed,
+                         drop_stream=cfg.stream(l, SITE_ATTN))                                       # K6
+            y1 = empty(M, D)
+            ops.gemm(att, wo_b, y1, M=M, N=D, K=Dp, bias=out_b, residual=x, drop_p=pd_tok, drop_seed=seed,
+                     drop_stream=cfg.stream(l, SITE_DROP1))                                           # K7
+            x1 = empty(M, D)
+            mean1 = empty(M, dtype=torch.float32) if need_grad else None
+            rstd1 = empty(M, dtype=torch.float32) if need_grad else None
+            ops.layernorm_fwd(y1, x1, n1w, n1b, mean1, rstd1, M, D, eps=LN_EPS)
+            u = empty(M, F) if need_grad else None
+            h = empty(M, F)
+            ops.gemm(x1, w1_b, h, M=M, N=F, K=D, bias=b1, act=1, preact_out=u, drop_p=pd_tok, drop_seed=seed,
+                     drop_stream=cfg.stream(l, SITE_FFN))                                             # K8
+            y2 = empty(M, D)
+            ops.gemm(h, w2_b, y2, M=M, N=D, K=F, bias=b2, residual=x1, drop_p=pd_tok, drop_seed=seed,
+                     drop_stream=cfg.stream(l, SITE_DROP2))                                           # K9
+            x2 = empty(M, D)
+            mean2 = empty(M, dtype=torch.float32) if need_grad else None
+            rstd2 = empty(M, dtype=torch.float32) if need_grad else None
+            ops.layernorm_fwd(y2, x2, n2w, n2b, mean2, rstd2, M, D, eps=LN_EPS)
+            for nm, t in (("qkv", qkv), ("att", att), ("y1", y1), ("x1", x1), ("h", h), ("y2", y2), ("x2", x2)):
+                _dbg(f"l{l}.{nm}", t)
+            if need_grad:
+                saved_layers.append((x, qkv, att, lse, y1, mean1, rstd1, x1, u, h, y2, mean2, rstd2))
+            x = x2
+
+        # ---- final LN on the visual rows, back-projection, fold   (K10-K12)
+        vis = empty(B * n, D)
+        meanf = empty(B * n, dtype=torch.float32) if need_grad else None
+        rstdf = empty(B * n, dtype=torch.float32) if need_grad else None
+        ops.layernorm_fwd(x, vis, lnf_w, lnf_b, meanf, rstdf, B * n, D, in_map=(n, S, 0), eps=LN_EPS,
+                          drop_p=pd_back, drop_seed=seed, drop_stream=cfg.stream(0, SITE_BACKPROJ))
+        yb = empty(B * n, K)
+        ops.gemm(vis, wbp_b, yb, M=B * n, N=K, K=D, bias=bbp)
+        _dbg("vis", vis); _dbg("yb", yb)
+        fused = torch.empty(B, C, Hf, Wf, device=dev, dtype=feat_c.dtype)
+        ops.fold(yb, fused, p)
+        lang_out = x.view(B, S, D)[:, n:].float() if cfg.need_lang_out else lang.new_zeros(())
+
+        if need_grad:
+            ctx.cfg = cfg
+            ctx.dims = (B, C, Hf, Wf, p, n, L, D, S, H, d, dp, Dp, F, K, M, Sp)
+            ctx.pd = (pd_patch, pd_tok, pd_back)
+            ctx.kpm = kpm
+            ctx.tok = tok
+            ctx.xfinal = x
+            ctx.vis = vis
+            ctx.statf = (meanf, rstdf)
+            ctx.saved_layers = saved_layers
+            ctx.lw = lw
+            ctx.wpe_b, ctx.wbp_b = wpe_b, wbp_b
+            ctx.param_refs = params
+            ctx.needs = (feat.requires_grad, lang.requires_grad)
+            ctx.feat_dtype = feat_c.dtype
+        return fused, lang_out
+
+    @staticmethod
+    def backward(ctx, d_fused, d_lang_out):
+        cfg: LevelConfig = ctx.cfg
+        (B, C, Hf, Wf, p, n, L, D, S, H, d, dp, Dp, F, K, M, Sp) = ctx.dims
+        pd_patch, pd_tok, pd_back = ctx.pd
+        params = ctx.param_refs
+        nl = cfg.num_layers
+        seed = cfg.seed
+        dev = d_fused.device
+        bf = torch.bfloat16
+        f32 = torch.float32
+        scale = 1.0 / math.sqrt(d)
+        kpm = ctx.kpm
+        wpe, img_kind, lang_kind, pos_table = params[:N_HEAD_PARAMS]
+        layer_params = [params[N_HEAD_PARAMS + i * N_LAYER_PARAMS: N_HEAD_PARAMS + (i + 1) * N_LAYER_PARAMS] for i in range(nl)]
+        lnf_w, lnf_b, wbp, bbp = params[N_HEAD_PARAMS + nl * N_LAYER_PARAMS:]
+
+        def empty(*shape, dtype=bf):
+            return torch.empty(*shape, device=dev, dtype=dtype)
+
+        def zeros(*shape, dtype=f32):
+            return torch.zeros(*shape, device=dev, dtype=dtype)
+
+        grads: List[Optional[torch.Tensor]] = [None] * len(params)
+
+        # ---- fold^T, back-projection
+        d_fused_c = d_fused.contiguous()
+        if d_fused_c.dtype not in (torch.float32, torch.bfloat16):
+            d_fused_c = d_fused_c.float()
+        dyb = empty(B * n, K)
+        ops.patchify(d_fused_c, p, dyb)
+        g_bbp = zeros(K); ops.colsum(dyb, g_bbp, B * n, K)
+        g_wbp = zeros(K, D); _wgrad(dyb, ctx.vis, g_wbp, K, D, B * n)
+        dvis = empty(B * n, D)
+        ops.gemm(dyb, ctx.wbp_b, dvis, M=B * n, N=D, K=K, b_mn_major=True)
+        del dyb
+        # ---- final LN backward into the visual rows of dz; language rows from d_lang_out (or zero)
+        dx = empty(B, S, D)
+        if cfg.need_lang_out and d_lang_out is not None and d_lang_out.dim() == 3:
+            dx[:, n:] = d_lang_out.to(bf)
+        else:
+            dx[:, n:].zero_()
+        dxf = dx.view(M, D)
+        g_lnf_w, g_lnf_b = zeros(D), zeros(D)
+        meanf, rstdf = ctx.statf
+        ops.layernorm_bwd(dvis, ctx.xfinal, lnf_w, meanf, rstdf, dxf, g_lnf_w, g_lnf_b, B * n, D,
+                          in_map=(n, S, 0), dy_drop=(pd_back, seed, cfg.stream(0, SITE_BACKPROJ)))
+        base_tail = N_HEAD_PARAMS + nl * N_LAYER_PARAMS
+        grads[base_tail + 0], grads[base_tail + 1] = g_lnf_w, g_lnf_b
+        grads[base_tail + 2], grads[base_tail + 3] = g_wbp, g_bbp
+        del dvis
+
+        dcur = dxf  # gradient w.r.t. the layer output x2
+        for l in reversed(range(nl)):
+            (in_w, in_b, out_w, out_b, w1, b1, w2, b2, n1w, n1b, n2w, n2b) = layer_params[l]
+            win_b, bin_p, wo_b, w1_b, w2_b = ctx.lw[l]
+            (x, qkv, att, lse, y1, mean1, rstd1, x1, u, h, y2, mean2, rstd2) = ctx.saved_layers[l]
+            base = N_HEAD_PARAMS + l * N_LAYER_PARAMS
+            # LN2 backward: dY2 (+ dropout2-masked copy G2 feeding linear2's gradients), b2 grad
+            dy2 = empty(M, D)
+            g2 = empty(M, D) if pd_tok > 0 else None
+            g_n2w, g_n2b, g_b2 = zeros(D), zeros(D), zeros(D)
+            ops.layernorm_bwd(dcur, y2, n2w, mean2, rstd2, dy2, g_n2w, g_n2b, M, D, dbias=g_b2, dx2=g2,
+                              dx2_drop=(pd_tok, seed, cfg.stream(l, SITE_DROP2)))
+            G2 = g2 if g2 is not None else dy2
+            # linear2: wgrad, dgrad fused with dropout(ffn) mask and GELU'
+            g_w2 = zeros(D, F); _wgrad(G2, h, g_w2, D, F, M)
+            du = empty(M, F)
+            ops.gemm(G2, w2_b, du, M=M, N=F, K=D, b_mn_major=True, dact_in=u, drop_p=pd_tok, drop_seed=seed,
+                     drop_stream=cfg.stream(l, SITE_FFN), drop_first=True)
+            # linear1
+            g_b1 = zeros(F); ops.colsum(du, g_b1, M, F)
+            g_w1 = zeros(F, D); _wgrad(du, x1, g_w1, F, D, M)
+            dx1 = empty(M, D)
+            ops.gemm(du, w1_b, dx1, M=M, N=D, K=F, b_mn_major=True, residual=dy2)
+            del du
+            # LN1 backward
+            dy1 = empty(M, D)
+            g1 = empty(M, D) if pd_tok > 0 else None
+            g_n1w, g_n1b, g_bo = zeros(D), zeros(D), zeros(D)
+            ops.layernorm_bwd(dx1, y1, n1w, mean1, rstd1, dy1, g_n1w, g_n1b, M, D, dbias=g_bo, dx2=g1,
+                              dx2_drop=(pd_tok, seed, cfg.stream(l, SITE_DROP1)))
+            G1 = g1 if g1 is not None else dy1
+            # out_proj
+            g_wo_p = zeros(D, Dp); _wgrad(G1, att, g_wo_p, D, Dp, M)
+            datt = empty(M, Dp)
+            ops.gemm(G1, wo_b, datt, M=M, N=Dp, K=D, b_mn_major=True)
+            # attention backward
+            delta = empty(B, H, Sp, dtype=f32)
+            ops.attn_delta(att, datt, delta, B, S, H, dp)
+            dqkv = empty(M, 3 * Dp)
+            ops.attn_bwd(qkv[:, :Dp], qkv[:, Dp:2 * Dp], qkv[:, 2 * Dp:], datt, lse, delta,
+                         dqkv[:, :Dp], dqkv[:, Dp:2 * Dp], dqkv[:, 2 * Dp:], B=B, H=H, Sq=S, Sk=S, dp=dp, scale=scale,
+                         key_padding_mask=kpm, drop_p=pd_tok, drop_seed=seed, drop_stream=cfg.stream(l, SITE_ATTN))
+            del datt
+            # in_proj
+            g_bin_p = zeros(3 * Dp); ops.colsum(dqkv, g_bin_p, M, 3 * Dp)
+            g_win_p = zeros(3 * Dp, D); _wgrad(dqkv, x, g_win_p, 3 * Dp, D, M)
+            dxin = empty(M, D)
+            ops.gemm(dqkv, win_b, dxin, M=M, N=D, K=3 * Dp, b_mn_major=True, residual=dy1)
+            del dqkv
+            if dp != d:
+                g_win = zeros(3 * D, D); ops.unpad_add(g_win_p, g_win, 3 * D, D, rin=d, rout=dp)
+                g_bin = g_bin_p.view(3 * H, dp)[:, :d].reshape(3 * D).contiguous()
+                g_wo = zeros(D, D); ops.unpad_add(g_wo_p, g_wo, D, D, cin=d, cout=dp)
+            else:
+                g_win, g_bin, g_wo = g_win_p, g_bin_p, g_wo_p
+            grads[base: base + N_LAYER_PARAMS] = [g_win, g_bin, g_wo, g_bo, g_w1, g_b1, g_w2, g_b2, g_n1w, g_n1b, g_n2w, g_n2b]
+            dcur = dxin
+            ctx.saved_layers[l] = None
+
+        # ---- sequence assembly backward: language rows and visual rows
+        dz0 = dcur.view(B, S, D)
+        g_lang_kind = zeros(D)
+        d_lang = zeros(B, L, D) if ctx.needs[1] else None
+        ops.lang_rows_bwd(dz0, d_lang, g_lang_kind, B, L, n)
+        dz0v = empty(B * n, D)
+        g_img_kind = zeros(D)
+        ops.rows_gather(dz0, dz0v, B * n, D, in_map=(n, S, 0), colsum=g_img_kind, drop_p=pd_patch, drop_seed=seed,
+                        drop_stream=cfg.stream(0, SITE_PATCH))
+        g_wpe = zeros(D, K); _wgrad(dz0v, ctx.tok, g_wpe, D, K, B * n)
+        d_feat = None
+        if ctx.needs[0]:
+            dtok = empty(B * n, K)
+            ops.gemm(dz0v, ctx.wpe_b, dtok, M=B * n, N=K, K=D, b_mn_major=True)
+            d_feat = torch.empty(B, C, Hf, Wf, device=dev, dtype=ctx.feat_dtype)
+            ops.fold(dtok, d_feat, p)
+        grads[0] = g_wpe.view_as(wpe)
+        grads[1] = g_img_kind.view_as(img_kind)
+        grads[2] = g_lang_kind.view_as(lang_kind)
+        grads[3] = None  # positional table: buffer (sin1d)
+        out_grads = []
+        for prm, g in zip(params, grads):
+            if g is None or not prm.requires_grad:
+                out_grads.append(None)
+            else:
+                out_grads.append(g.view_as(prm) if g.shape != prm.shape else g)
+        return (None, d_feat, d_lang, None, *out_grads)

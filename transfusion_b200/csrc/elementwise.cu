@@ -428,6 +428,40 @@ attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __re
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// rows gather: out[r, :] = in[remap(r), :] (optionally dropout-masked with the mask of the forward
+// write at that source position) and colsum += sum_r out[r, :].  Used for the visual rows of dz0
+// (patch-embed backward: cross_f_box_layers.py:72-74 backward).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rows_gather_kernel(const __nv_bfloat16* __restrict__ in, long long ldi, __nv_bfloat16* __restrict__ out, long long ldo, int rows,
+                   int D, int rin, int rout, int roff, int rows_per_cta, float* __restrict__ colsum, float drop_p,
+                   uint32_t seed, uint32_t stream, uint32_t thresh, float drop_scale) {
+  const int vc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (vc * 8 >= D) return;
+  const int r0 = blockIdx.y * rows_per_cta;
+  const int r1 = min(rows, r0 + rows_per_cta);
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int r = r0; r < r1; ++r) {
+    const long long ir = remap_row(r, rin, rout, roff);
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(in + ir * ldi) + vc);
+    float v[8] = {bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y), bf16_lo(q.z), bf16_hi(q.z), bf16_lo(q.w), bf16_hi(q.w)};
+    if (drop_p > 0.f) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        v[k] = dropout_keep(seed, stream, static_cast<uint64_t>(ir * ldi + vc * 8 + k), thresh) ? v[k] * drop_scale : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s[k] += v[k];
+    *(reinterpret_cast<uint4*>(out + static_cast<long long>(r) * ldo) + vc) =
+        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+  }
+  if (colsum) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) atomicAdd(colsum + vc * 8 + k, s[k]);
+  }
+}
+
 static inline int grid_for(long long work_items, int per_cta, int waves = 8) {
   long long ctas = (work_items + per_cta - 1) / per_cta;
   long long cap = static_cast<long long>(sm_count()) * waves;
@@ -602,6 +636,25 @@ extern "C" int xf_attn_delta(const void* o, const void* d_o, int64_t ld, int B, 
   if (B * S == 0) return 0;
   attn_delta_kernel<<<grid_for(static_cast<long long>(B) * S * heads, 8), 256, 0, reinterpret_cast<cudaStream_t>(s)>>>(
       reinterpret_cast<const __nv_bfloat16*>(o), reinterpret_cast<const __nv_bfloat16*>(d_o), ld, B, S, heads, dp, stat_stride, delta);
+  g_launches.fetch_add(1);
+  XF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int xf_rows_gather(const void* in, int64_t ldi, void* out, int64_t ldo, int rows, int D, int rin, int rout, int roff,
+                              float* colsum, float drop_p, uint32_t seed, uint32_t stream_id, xf_stream_t s) {
+  if (!in || !out) return fail(-1, "xf_rows_gather: null pointer");
+  if (D % 8 || ldi % 8 || ldo % 8) return fail(-2, "xf_rows_gather: D and leading dims must be multiples of 8");
+  if (rows == 0) return 0;
+  const int gx = (D / 8 + 255) / 256;
+  int gy = (4 * sm_count() + gx - 1) / gx;
+  if (gy > rows) gy = rows;
+  const int rows_per_cta = (rows + gy - 1) / gy;
+  gy = (rows + rows_per_cta - 1) / rows_per_cta;
+  rows_gather_kernel<<<dim3(gx, gy), 256, 0, reinterpret_cast<cudaStream_t>(s)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(in), ldi, reinterpret_cast<__nv_bfloat16*>(out), ldo, rows, D, rin, rout, roff,
+      rows_per_cta, colsum, drop_p, seed, stream_id, static_cast<uint32_t>(static_cast<double>(drop_p) * 4294967296.0),
+      drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f);
   g_launches.fetch_add(1);
   XF_CUDA(cudaGetLastError());
   return 0;

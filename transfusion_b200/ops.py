@@ -219,3 +219,11 @@ def attn_bwd(q, k, v, d_out, lse, delta, dq, dk, dv, *, B: int, H: int, Sq: int,
     a.scale = scale
     a.drop_p, a.drop_seed, a.drop_stream = drop_p, drop_seed, drop_stream
     check(lib().xf_attn_bwd(C.byref(a), _stream()), "xf_attn_bwd")
+
+
+def rows_gather(src: torch.Tensor, dst: torch.Tensor, rows: int, D: int, in_map=(0, 0, 0), colsum: Optional[torch.Tensor] = None,
+                drop_p: float = 0.0, drop_seed: int = 0, drop_stream: int = 0):
+    _req(src, torch.bfloat16, "src"); _req(dst, torch.bfloat16, "dst")
+    check(lib().xf_rows_gather(_ptr(src), C.c_int64(src.stride(-2)), _ptr(dst), C.c_int64(dst.stride(-2)), rows, D,
+                               in_map[0], in_map[1], in_map[2], _ptr(colsum), C.c_float(drop_p), C.c_uint32(drop_seed),
+                               C.c_uint32(drop_stream), _stream()), "xf_rows_gather")
