@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py — cross_fusion fwd+bwd samples/sec on B200 (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps 10 --warmup 3                 # this repo's CUDA path
+    python bench.py --impl reference --steps 2 --warmup 1          # CPU baseline arm (oracle port)
+    torchrun --nproc-per-node N bench.py --gpus N ...              # one rank per GPU, NCCL
+
+A "step" = one pass of the hot path (all 4 FPN levels x 4 encoder layers, forward + backward) over
+one per-GPU batch of synthetic inputs of the Ego4Dv2 shape (`--workload
+ego4dv1` selects config 2).  Dropout is ON (training mode, the shipped probabilities), gradients of
+every fusion parameter are produced, and for N > 1 they are all-reduced over NCCL every step
+(one process per GPU, one bucket per FPN level, weak scaling: per-GPU batch fixed).
+
+Prints ONE JSON line (rank 0).  `value` = device-timed throughput with inputs resident in HBM;
+`e2e` = same path through CrossFusionBoxWrapper.forward with HOST (pinned) inputs copied in and the
+scalar loss read back every step; `roofline` = the dominant kernel family against the measured bf16
+peak; `cpu_baseline` = the CPU oracle port timed on this box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch
+
+METRIC = "cross_fusion fwd+bwd samples/sec"
+UNIT = "samples/s"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"tflops": float(p.get("bf16_tflops_sustained", p.get("bf16_tflops", 1400.0))),
+                "tflops_burst": float(p.get("bf16_tflops", 1590.0)), "hbm_gbs": float(p.get("hbm_gbs", 6650.0)),
+                "source": "MEASURED_PEAKS.json (bf16_tflops_sustained: kernel timed inside a long step)"}
+    return {"tflops": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.lines = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu_index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1])); smax.append(float(parts[2])); power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def algorithmic_flops_fwd(workload: dict, L: int) -> float:
+    """F_fwd = sum_l [4 n K D + layers (16 S D^2 + 4 S^2 D)] per sample."""
+    from transfusion_b200.configs import level_shapes
+    D = workload["token_dim"]
+    tot = 0.0
+    for (h, w), C, p, nl in zip(level_shapes(workload), workload["channels"], workload["patch"], workload["num_layers"]):
+        n = (h // p) * (w // p)
+        K = C * p * p
+        S = n + L
+        tot += 4.0 * n * K * D + nl * (16.0 * S * D * D + 4.0 * S * S * D)
+    return tot
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (oracle/ref_math.py, torch fp32, all host threads).  The reference is
+# pure Python and cannot travel to the GPU box, so kind = "port" (its restatement is pinned to the
+# reference by tests/golden and tests/test_oracle_vs_reference.py).
+# ------------------------------------------------------------------------------------------------
+def cpu_oracle_step(workload_name: str, batch: int, L: int, seed: int = 0):
+    from oracle import ref_math
+    from transfusion_b200.configs import WORKLOADS
+    from transfusion_b200.harness import build_workload_module, synthetic_inputs
+    w = WORKLOADS[workload_name]
+    m = build_workload_module(workload_name, device="cpu", dropout=False, seed=seed)
+    sd = {k: p.detach().clone().requires_grad_(True) for k, p in m.named_parameters()
+          if not k.startswith(("rcnn_model", "narr_pooling_layer"))}
+    feats, lang, mask = synthetic_inputs(workload_name, batch, L, seed + 1)
+    g = torch.Generator().manual_seed(seed + 2)
+    cot = {k: torch.randn(v.shape, generator=g) for k, v in feats.items()}
+
+    def step():
+        for v in sd.values():
+            v.grad = None
+        lg = lang.clone().requires_grad_(True)
+        out, _ = ref_math.cross_fusion_forward(feats, lg, mask, sd, w["patch"], w["num_heads"], w["num_layers"])
+        loss = sum((out[k] * cot[k]).sum() for k in out)
+        loss.backward()
+        return float(loss.detach())
+
+    return step
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    from transfusion_b200.configs import WORKLOADS
+    w = WORKLOADS[args.workload]
+    L = args.lang_len or w["lang_len"]
+    bs = args.cpu_batch
+    step = cpu_oracle_step(args.workload, bs, L)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = bs * args.steps / dt
+    sample = f"{bs} sample(s)/step of the {args.workload} 4-level workload (L={L}), fwd+bwd, fp32, dropout p=0"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload} cross_fusion fwd+bwd (CPU oracle port of the reference module)",
+                       "per_step_batch": bs, "lang_len": L},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from transfusion_b200 import _lib, ops
+    from transfusion_b200.configs import WORKLOADS
+    from transfusion_b200.harness import build_workload_module, synthetic_inputs
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    w = WORKLOADS[args.workload]
+    L = args.lang_len or w["lang_len"]
+    B = args.batch or (w["train_batch"] if args.mode == "train" else w["eval_batch"])
+    train = args.mode == "train"
+
+    model = build_workload_module(args.workload, device=dev, dropout=not args.no_dropout, seed=0)
+    model.train(train)
+    for k, p in model.named_parameters():
+        if k.endswith("heatmap_token"):
+            p.requires_grad_(False)  # registered but unused in forward (reference cross_f_box_layers.py:43)
+    net = model
+    reducer = None
+    if world > 1 and train:
+        # same initial weights on every rank (seeded construction); gradients averaged per level bucket,
+        # each bucket's NCCL all-reduce launched as soon as that level's backward has been enqueued
+        from transfusion_b200.parallel import BucketedGradAllReduce, level_buckets
+        reducer = BucketedGradAllReduce(level_buckets(model))
+
+    feat_dtype = torch.float32 if args.feat_dtype == "f32" else torch.bfloat16
+    feats_h, lang_h, mask_h = synthetic_inputs(args.workload, B, L, seed=1234 + rank, feat_dtype=feat_dtype, pin=True)
+    feats_d = {k: v.to(dev) for k, v in feats_h.items()}
+    lang_d, mask_d = lang_h.to(dev), mask_h.to(dev)
+    gen = torch.Generator(device=dev).manual_seed(99 + rank)
+    cot = {k: torch.randn(v.shape, device=dev, dtype=torch.float32, generator=gen) for k, v in feats_d.items()}
+    keys = sorted(feats_d, key=int)
+
+    def step_resident():
+        model.rcnn_model.features = feats_d
+        if train:
+            net.zero_grad(set_to_none=True)
+            if reducer is not None:
+                reducer.reset()
+            out = net({"image": None, "language_f": (lang_d, mask_d)})["features"]
+            torch.autograd.backward([out[k] for k in keys], [cot[k].to(out[k].dtype) for k in keys])
+            if reducer is not None:
+                reducer.finish()
+        else:
+            with torch.no_grad():
+                net({"image": None, "language_f": (lang_d, mask_d)})
+
+    def step_e2e():
+        f = {k: v.to(dev, non_blocking=True) for k, v in feats_h.items()}
+        lg, mk = lang_h.to(dev, non_blocking=True), mask_h.to(dev, non_blocking=True)
+        model.rcnn_model.features = f
+        if train:
+            net.zero_grad(set_to_none=True)
+            if reducer is not None:
+                reducer.reset()
+            out = net({"image": None, "language_f": (lg, mk)})["features"]
+            loss = sum((out[k].float() * cot[k]).sum() for k in keys)
+            loss.backward()
+            if reducer is not None:
+                reducer.finish()
+        else:
+            with torch.no_grad():
+                out = net({"image": None, "language_f": (lg, mk)})["features"]
+                loss = sum(out[k].float().sum() for k in keys)
+        return float(loss.item())  # device -> host read of the step's result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.lib().xf_launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = _lib.lib().xf_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ms / args.steps
+    value = world * B * args.steps / (ms / 1e3)
+
+    # ---- end-to-end: host (pinned) inputs in, scalar loss out, every step
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e_value = world * B * args.steps / (ms_e2e / 1e3)
+    h2d = sum(v.numel() * v.element_size() for v in feats_h.values()) + lang_h.numel() * 4 + mask_h.numel() * 8
+    d2h = 4
+
+    # ---- per-kernel roofline pass: CUDA events around every launch (rank 0, separate from the timed run)
+    roofline, kernels = None, None
+    if rank == 0:
+        peaks = load_peaks()
+        ops.PROFILE = []
+        step_resident()
+        torch.cuda.synchronize()
+        prof, ops.PROFILE = ops.PROFILE, None
+        fam = {}
+        for (name, flops, nbytes, e0, e1) in prof:
+            d = fam.setdefault(name, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
+            d["ms"] += e0.elapsed_time(e1); d["flops"] += flops; d["bytes"] += nbytes; d["launches"] += 1
+        tot_ms = sum(d["ms"] for d in fam.values()) or 1.0
+        kernels = {}
+        for name, d in sorted(fam.items(), key=lambda kv: -kv[1]["ms"]):
+            kernels[name] = {"ms_per_step": round(d["ms"], 4), "share": round(d["ms"] / tot_ms, 4), "launches": d["launches"]}
+            if d["flops"] > 0:
+                kernels[name]["tflops"] = round(d["flops"] / (d["ms"] * 1e-3) / 1e12, 2)
+            elif d["bytes"] > 0:
+                kernels[name]["gbs"] = round(d["bytes"] / (d["ms"] * 1e-3) / 1e9, 1)
+        top = next(iter(kernels))
+        kname = {"gemm": "gemm_bf16_tcgen05_kernel", "attn_fwd": "attn_fwd_tcgen05_kernel",
+                 "attn_bwd": "attn_bwd_tcgen05_kernel<DKV>"}.get(top, top)
+        if "tflops" in kernels[top]:
+            roofline = {"bound": "tensor", "kernel": kname, "achieved": kernels[top]["tflops"], "peak": peaks["tflops"],
+                        "unit": "TFLOP/s", "frac": round(kernels[top]["tflops"] / peaks["tflops"], 4), "traffic": None,
+                        "share_of_step": kernels[top]["share"], "peak_source": peaks["source"]}
+        else:
+            roofline = {"bound": "hbm", "kernel": kname, "achieved": kernels[top].get("gbs"), "peak": peaks["hbm_gbs"],
+                        "unit": "GB/s", "frac": round((kernels[top].get("gbs") or 0.0) / peaks["hbm_gbs"], 4), "traffic": None,
+                        "share_of_step": kernels[top]["share"], "peak_source": peaks["source"]}
+        f_fwd = algorithmic_flops_fwd(w, L)
+        from transfusion_b200.configs import level_shapes
+        pe_dgrad = sum(2.0 * ((h // p) * (ww // p)) * (C * p * p) * w["token_dim"]
+                       for (h, ww), C, p in zip(level_shapes(w), w["channels"], w["patch"]))
+        # fwd+bwd = 3 F_fwd minus the patch-embed dgrad (visual inputs do not require grad: frozen backbone)
+        step_flops = (3.0 * f_fwd - pe_dgrad) if train else f_fwd
+        roofline["whole_path_tflops"] = round(value / world * step_flops / 1e12, 2)
+        roofline["whole_path_frac"] = round(value / world * step_flops / 1e12 / peaks["tflops"], 4)
+
+    # ---- CPU baseline (rank 0, N = 1 only): oracle port on a bounded sample of the same workload
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        stepc = cpu_oracle_step(args.workload, args.cpu_batch, L)
+        t0 = time.perf_counter()
+        stepc()
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": args.cpu_batch / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                        "sample": f"{args.cpu_batch} sample(s) of the {args.workload} 4-level workload (L={L}), one fwd+bwd, fp32, "
+                                  f"dropout p=0 ({dt:.1f} s)"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"{args.workload} cross_fusion {'fwd+bwd' if train else 'fwd'}: 4 FPN levels x 4 layers, "
+                                       f"D={w['token_dim']}, image {w['image'][0]}x{w['image'][1]}",
+                           "per_gpu_batch": B, "global_batch": B * world, "lang_len": L,
+                           "dropout": "off" if (args.no_dropout or not train) else "on (0.1/0.15/0.1)",
+                           "feature_dtype": args.feat_dtype, "parallelism": f"dp{world}",
+                           "l2": "inputs and activations (>1 GB per step) exceed the 126 MB L2; no explicit flush",
+                           "visual_input_grad": False},
+                "clocks": clocks, "gpu_launches": int(launches),
+                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                        "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+                "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="ego4dv2", choices=["ego4dv2", "ego4dv1"])
+    ap.add_argument("--mode", default="train", choices=["train", "infer"])
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the reference's per-GPU batch)")
+    ap.add_argument("--lang-len", type=int, default=0)
+    ap.add_argument("--feat-dtype", default="f32", choices=["f32", "bf16"])
+    ap.add_argument("--no-dropout", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-batch", type=int, default=1)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -144,7 +144,13 @@ class CrossFusionBoxWrapper(nn.Module):
         need_lang_out = bool(self.multi_lm or self.forward_language_f or (self.lm_on and not self.use_lm_f))
         mscale_l_features = []
         fused_l_features = None
-        for i, key in enumerate(self.fpn_features_idx):
+        # Levels are independent given the shared language input (forward_language_f: False, fusion yml :27),
+        # so they are visited coarsest-first: autograd then runs the largest level's backward FIRST and its
+        # gradient all-reduce overlaps the remaining levels.  With forward_language_f the reference order holds.
+        level_order = list(enumerate(self.fpn_features_idx))
+        if not self.forward_language_f and not self.multi_lm:
+            level_order = level_order[::-1]
+        for i, key in level_order:
             key = str(key)
             feat = features_dict["features"][key]
             self.tokens_to_features[i].init_h = feat.shape[2]

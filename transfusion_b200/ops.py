@@ -11,6 +11,32 @@ from . import _lib
 from ._lib import XfAttnBwd, XfAttnFwd, XfGemm, XfLayerNorm, XfLayerNormBwd, check, lib
 
 
+# When set to a list, every op appends (family, algorithmic flops, algorithmic bytes, start event, end event):
+# bench.py's per-kernel roofline pass (CUDA events on the launching stream).
+PROFILE = None
+
+
+class _Prof:
+    __slots__ = ("fam", "flops", "nbytes", "e0")
+
+    def __init__(self, fam, flops=0.0, nbytes=0.0):
+        self.fam, self.flops, self.nbytes = fam, flops, nbytes
+        self.e0 = None
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None and self.e0 is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            PROFILE.append((self.fam, self.flops, self.nbytes, self.e0, e1))
+        return False
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -71,7 +97,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     g.accumulate = int(accumulate)
     g.drop_p, g.drop_seed, g.drop_stream, g.drop_first = drop_p, drop_seed, drop_stream, int(drop_first)
     g.max_ctas = max_ctas
-    check(lib().xf_gemm(C.byref(g), _stream()), "xf_gemm")
+    with _Prof("gemm", 2.0 * M * N * K):
+        check(lib().xf_gemm(C.byref(g), _stream()), "xf_gemm")
     return out
 
 
@@ -89,8 +116,9 @@ def patchify(feat: torch.Tensor, p: int, tok: torch.Tensor) -> torch.Tensor:
     if not feat.is_contiguous():
         raise _lib.XfError("patchify: feature map must be contiguous NCHW")
     _req(tok, torch.bfloat16, "tok")
-    check(lib().xf_patchify(_ptr(feat), _feat_dtype(feat), _ptr(tok), C.c_int64(tok.stride(0)), B, Cc, H, W, p, _stream()),
-          "xf_patchify")
+    with _Prof("patchify_fold", 0.0, feat.numel() * (feat.element_size() + 2.0)):
+        check(lib().xf_patchify(_ptr(feat), _feat_dtype(feat), _ptr(tok), C.c_int64(tok.stride(0)), B, Cc, H, W, p, _stream()),
+              "xf_patchify")
     return tok
 
 
@@ -100,8 +128,9 @@ def fold(tok: torch.Tensor, feat: torch.Tensor, p: int, accumulate: bool = False
     if not feat.is_contiguous():
         raise _lib.XfError("fold: feature map must be contiguous NCHW")
     _req(tok, torch.bfloat16, "tok")
-    check(lib().xf_fold(_ptr(tok), C.c_int64(tok.stride(0)), _ptr(feat), _feat_dtype(feat), int(accumulate), B, Cc, H, W, p,
-                        _stream()), "xf_fold")
+    with _Prof("patchify_fold", 0.0, feat.numel() * (feat.element_size() + 2.0)):
+        check(lib().xf_fold(_ptr(tok), C.c_int64(tok.stride(0)), _ptr(feat), _feat_dtype(feat), int(accumulate), B, Cc, H, W, p,
+                            _stream()), "xf_fold")
     return feat
 
 
@@ -131,7 +160,8 @@ def layernorm_fwd(x, y, gamma, beta, mean, rstd, rows: int, D: int, *, in_map=(0
     a.out_rows_in, a.out_rows_out, a.out_row_off = out_map
     a.eps = eps
     a.drop_p, a.drop_seed, a.drop_stream = drop_p, drop_seed, drop_stream
-    check(lib().xf_layernorm_fwd(C.byref(a), _stream()), "xf_layernorm_fwd")
+    with _Prof("layernorm_fwd", 0.0, 4.0 * rows * D):
+        check(lib().xf_layernorm_fwd(C.byref(a), _stream()), "xf_layernorm_fwd")
 
 
 def layernorm_bwd(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, rows: int, D: int, *, dbias=None, dx2=None,
@@ -149,17 +179,20 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, rows: int, D: int
     a.out_rows_in, a.out_rows_out, a.out_row_off = out_map
     a.dy_drop_p, a.dy_drop_seed, a.dy_drop_stream = dy_drop
     a.dx2_drop_p, a.dx2_drop_seed, a.dx2_drop_stream = dx2_drop
-    check(lib().xf_layernorm_bwd(C.byref(a), _stream()), "xf_layernorm_bwd")
+    with _Prof("layernorm_bwd", 0.0, (6.0 if dx2 is None else 8.0) * rows * D):
+        check(lib().xf_layernorm_bwd(C.byref(a), _stream()), "xf_layernorm_bwd")
 
 
 def colsum(x: torch.Tensor, out: torch.Tensor, rows: int, cols: int):
     _req(x, torch.bfloat16, "x"); _req(out, torch.float32, "out")
-    check(lib().xf_colsum(_ptr(x), C.c_int64(x.stride(-2)), rows, cols, _ptr(out), _stream()), "xf_colsum")
+    with _Prof("colsum", 0.0, 2.0 * rows * cols):
+        check(lib().xf_colsum(_ptr(x), C.c_int64(x.stride(-2)), rows, cols, _ptr(out), _stream()), "xf_colsum")
 
 
 def cast_pad(src: torch.Tensor, dst: torch.Tensor, rows: int, cols: int, rin=0, rout=0, cin=0, cout=0):
     _req(src, torch.float32, "src"); _req(dst, torch.bfloat16, "dst")
-    check(lib().xf_cast_pad(_ptr(src), C.c_int64(src.stride(0) if src.dim() > 1 else cols), _ptr(dst),
+    with _Prof("cast", 0.0, 6.0 * rows * cols):
+      check(lib().xf_cast_pad(_ptr(src), C.c_int64(src.stride(0) if src.dim() > 1 else cols), _ptr(dst),
                             C.c_int64(dst.stride(0) if dst.dim() > 1 else cols), rows, cols, rin, rout, cin, cout, _stream()),
           "xf_cast_pad")
 
@@ -173,8 +206,9 @@ def unpad_add(src: torch.Tensor, dst: torch.Tensor, rows: int, cols: int, rin=0,
 
 def attn_delta(o: torch.Tensor, d_o: torch.Tensor, delta: torch.Tensor, B: int, S: int, heads: int, dp: int):
     """delta [B, heads, stat_stride] fp32 (stat_stride = delta.shape[-1])."""
-    check(lib().xf_attn_delta(_ptr(o), _ptr(d_o), C.c_int64(o.stride(-2)), B, S, heads, dp, delta.shape[-1], _ptr(delta),
-                              _stream()), "xf_attn_delta")
+    with _Prof("attn_delta", 0.0, 4.0 * B * S * heads * dp):
+        check(lib().xf_attn_delta(_ptr(o), _ptr(d_o), C.c_int64(o.stride(-2)), B, S, heads, dp, delta.shape[-1], _ptr(delta),
+                                  _stream()), "xf_attn_delta")
 
 
 def attn_fwd(q, k, v, out, lse, *, B: int, H: int, Sq: int, Sk: int, dp: int, scale: float,
@@ -196,7 +230,9 @@ def attn_fwd(q, k, v, out, lse, *, B: int, H: int, Sq: int, Sk: int, dp: int, sc
     a.B, a.H, a.Sq, a.Sk, a.dp = B, H, Sq, Sk, dp
     a.scale = scale
     a.drop_p, a.drop_seed, a.drop_stream = drop_p, drop_seed, drop_stream
-    check(lib().xf_attn_fwd(C.byref(a), _stream()), "xf_attn_fwd")
+    d_true = 1.0 / (scale * scale)
+    with _Prof("attn_fwd", 4.0 * B * H * Sq * Sk * d_true):
+        check(lib().xf_attn_fwd(C.byref(a), _stream()), "xf_attn_fwd")
 
 
 def attn_bwd(q, k, v, d_out, lse, delta, dq, dk, dv, *, B: int, H: int, Sq: int, Sk: int, dp: int, scale: float,
@@ -218,12 +254,15 @@ def attn_bwd(q, k, v, d_out, lse, delta, dq, dk, dv, *, B: int, H: int, Sq: int,
     a.B, a.H, a.Sq, a.Sk, a.dp = B, H, Sq, Sk, dp
     a.scale = scale
     a.drop_p, a.drop_seed, a.drop_stream = drop_p, drop_seed, drop_stream
-    check(lib().xf_attn_bwd(C.byref(a), _stream()), "xf_attn_bwd")
+    d_true = 1.0 / (scale * scale)
+    with _Prof("attn_bwd", 8.0 * B * H * Sq * Sk * d_true):
+        check(lib().xf_attn_bwd(C.byref(a), _stream()), "xf_attn_bwd")
 
 
 def rows_gather(src: torch.Tensor, dst: torch.Tensor, rows: int, D: int, in_map=(0, 0, 0), colsum: Optional[torch.Tensor] = None,
                 drop_p: float = 0.0, drop_seed: int = 0, drop_stream: int = 0):
     _req(src, torch.bfloat16, "src"); _req(dst, torch.bfloat16, "dst")
-    check(lib().xf_rows_gather(_ptr(src), C.c_int64(src.stride(-2)), _ptr(dst), C.c_int64(dst.stride(-2)), rows, D,
+    with _Prof("rows_gather", 0.0, 4.0 * rows * D):
+      check(lib().xf_rows_gather(_ptr(src), C.c_int64(src.stride(-2)), _ptr(dst), C.c_int64(dst.stride(-2)), rows, D,
                                in_map[0], in_map[1], in_map[2], _ptr(colsum), C.c_float(drop_p), C.c_uint32(drop_seed),
                                C.c_uint32(drop_stream), _stream()), "xf_rows_gather")

@@ -1,0 +1,101 @@
+"""Data-parallel plumbing for the fusion path (one process per GPU, torch.distributed / NCCL).
+
+The path shards by batch exactly like the reference's Lightning DDP (run_experiment.py:373-374,452):
+rank r takes samples [r*B, (r+1)*B), there is no forward collective, and the only exchange is one
+sum-all-reduce of the parameter gradients per step.  ``BucketedGradAllReduce`` launches that
+all-reduce per bucket (one bucket per FPN level by default) as soon as every gradient of the bucket
+has been accumulated, so it overlaps the backward of the remaining levels; NCCL runs it over
+NVLink 5 / NVSwitch.  Works with any backend (gloo on CPU for the tests)."""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(global_batch: int, rank: int, world: int):
+    """Per-rank slice of a global batch: the reference splits ``bs // n_devices`` per process
+    (run_experiment.py:373-374); the remainder is dropped, as there."""
+    per = global_batch // world
+    return rank * per, (rank + 1) * per
+
+
+class BucketedGradAllReduce:
+    def __init__(self, buckets: Sequence[Iterable[torch.nn.Parameter]], group: Optional[dist.ProcessGroup] = None,
+                 average: bool = True):
+        self.group = group
+        self.average = average
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.buckets: List[List[torch.nn.Parameter]] = [[p for p in b if p.requires_grad] for b in buckets]
+        self.buckets = [b for b in self.buckets if b]
+        self.flat: List[Optional[torch.Tensor]] = [None] * len(self.buckets)
+        self.pending = [0] * len(self.buckets)
+        self.works = []
+        self._handles = []
+        for bi, bucket in enumerate(self.buckets):
+            for p in bucket:
+                self._handles.append(p.register_post_accumulate_grad_hook(self._make_hook(bi)))
+        self.reset()
+
+    def _offsets(self, bi):
+        off, out = 0, []
+        for p in self.buckets[bi]:
+            out.append((off, p.numel()))
+            off += p.numel()
+        return out, off
+
+    def _make_hook(self, bi):
+        def hook(param):
+            self.pending[bi] -= 1
+            if self.pending[bi] == 0:
+                self._launch(bi)
+        return hook
+
+    def _launch(self, bi):
+        bucket = self.buckets[bi]
+        offs, total = self._offsets(bi)
+        if self.flat[bi] is None or self.flat[bi].device != bucket[0].grad.device:
+            self.flat[bi] = torch.empty(total, dtype=torch.float32, device=bucket[0].grad.device)
+        flat = self.flat[bi]
+        for p, (o, n) in zip(bucket, offs):
+            flat[o:o + n].copy_(p.grad.reshape(-1))
+        if self.world > 1:
+            self.works.append((bi, dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)))
+        else:
+            self.works.append((bi, None))
+
+    def reset(self):
+        """Call before each backward."""
+        self.pending = [len(b) for b in self.buckets]
+        self.works = []
+
+    def finish(self):
+        """Wait for the outstanding all-reduces and scatter the (averaged) result back into .grad."""
+        for bi, work in self.works:
+            if work is not None:
+                work.wait()
+            flat = self.flat[bi]
+            if self.average and self.world > 1:
+                flat.div_(self.world)
+            offs, _ = self._offsets(bi)
+            for p, (o, n) in zip(self.buckets[bi], offs):
+                p.grad = flat[o:o + n].view_as(p)
+        self.works = []
+
+    def remove(self):
+        for h in self._handles:
+            h.remove()
+        self._handles = []
+
+
+def level_buckets(wrapper) -> List[List[torch.nn.Parameter]]:
+    """One gradient bucket per FPN level (patch-embed + encoder + back-projection of that level)."""
+    out = []
+    for i in range(len(wrapper.cross_fusion_encoders)):
+        ps = list(wrapper.patches_to_token[i].parameters()) + list(wrapper.cross_fusion_encoders[i].parameters()) + \
+            list(wrapper.tokens_to_features[i].parameters())
+        out.append(ps)
+    if hasattr(wrapper, "lm_layer"):
+        out.append(list(wrapper.lm_layer.parameters()))
+    return out
