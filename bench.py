@@ -306,7 +306,8 @@ def run_ours(args):
             elif d["bytes"] > 0:
                 kernels[name]["gbs"] = round(d["bytes"] / (d["ms"] * 1e-3) / 1e9, 1)
         top = next(iter(kernels))
-        kname = {"gemm": "gemm_bf16_tcgen05_kernel", "attn_fwd": "attn_fwd_tcgen05_kernel",
+        kname = {"gemm_fwd": "gemm_bf16_tcgen05_kernel (forward x W^T)", "gemm_dgrad": "gemm_bf16_tcgen05_kernel (dgrad)",
+                 "gemm_wgrad": "gemm_bf16_tcgen05_kernel (wgrad, split-K)", "attn_fwd": "attn_fwd_tcgen05_kernel",
                  "attn_bwd": "attn_bwd_tcgen05_kernel<DKV>"}.get(top, top)
         if "tflops" in kernels[top]:
             roofline = {"bound": "tensor", "kernel": kname, "achieved": kernels[top]["tflops"], "peak": peaks["tflops"],

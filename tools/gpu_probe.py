@@ -339,6 +339,50 @@ CASES = {
     "gemm_f32": lambda: gemm_case(256, 256, 512, False, False, f32=True),
 }
 
+
+
+def drop_debug():
+    torch.manual_seed(3)
+    M, N, K, p = 2048, 896, 64, 0.1
+    A = torch.randn(M, K, device="cuda").bfloat16(); W = torch.randn(N, K, device="cuda").bfloat16()
+    outs = []
+    for first in (False, True, False, True):
+        o = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+        ops.gemm(A, W, o, M=M, N=N, K=K, drop_p=p, drop_seed=123, drop_stream=7, drop_first=first)
+        torch.cuda.synchronize()
+        outs.append(o != 0)
+    for i in range(1, 4):
+        diff = outs[0] != outs[i]
+        idx = diff.nonzero()
+        print(f"run{i} vs run0: mismatches {int(diff.sum())}", idx[:10].tolist(), flush=True)
+        if idx.numel():
+            print("   rows mod 128:", sorted(set((idx[:, 0] % 128).tolist()))[:20], " cols mod 32:", sorted(set((idx[:, 1] % 32).tolist()))[:32])
+
+
+def drop_debug2():
+    torch.manual_seed(3)
+    M, N, K, p = 2048, 896, 64, 0.1
+    A = torch.randn(M, K, device="cuda").bfloat16(); W = torch.randn(N, K, device="cuda").bfloat16()
+    ref = A.float() @ W.float().t()
+    out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(A, W, out, M=M, N=N, K=K, drop_p=p, drop_seed=123, drop_stream=7)
+    keep = out != 0
+    A2 = (torch.rand(M, K, device="cuda") + 0.5).bfloat16(); W2 = (torch.rand(N, K, device="cuda") + 0.5).bfloat16()
+    out2 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(A2, W2, out2, M=M, N=N, K=K, drop_p=p, drop_seed=123, drop_stream=7, drop_first=True)
+    torch.cuda.synchronize()
+    k2 = out2 != 0
+    diff = keep != k2
+    idx = diff.nonzero()
+    print("mismatches", int(diff.sum()), idx[:10].tolist())
+    for (r, c) in idx[:10].tolist():
+        print("  at", r, c, "out", float(out[r, c]), "ref", float(ref[r, c]), "out2", float(out2[r, c]))
+
+
+CASES["drop_debug2"] = drop_debug2
+CASES["drop_debug"] = drop_debug
+
+
 if __name__ == "__main__":
     name = sys.argv[1]
     if name == "list":

@@ -214,13 +214,19 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gri
         const int key = t0 + lane;
         const bool bad = key >= p.Sk || (p.kpm && p.kpm[static_cast<long long>(b) * p.Sk + key] != 0);
         const uint32_t badbits = __ballot_sync(0xffffffffu, bad);
-        const uint64_t drop_row = (bh * p.Sq + row_g) * static_cast<uint64_t>(p.Sk) + t0;
+        const uint64_t drop_row = (bh * p.Sq + row_g) * static_cast<uint64_t>(p.Sk + (p.Sk & 1)) + t0;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const float pr = ((badbits >> c) & 1u) ? 0.f : fast_exp2(__uint_as_float(c1[c]) * p.sl2 - lse_row);
-          float dpv = __uint_as_float(c2[c]);
-          if (p.drop_p > 0.f) dpv = dropout_keep(p.drop_seed, p.drop_stream, drop_row + c, p.drop_thresh) ? dpv * p.drop_scale : 0.f;
-          e2[c] = pr * (dpv - delta_row) * p.scale;
+        for (int c = 0; c < 32; c += 2) {
+          const float pr0 = ((badbits >> c) & 1u) ? 0.f : fast_exp2(__uint_as_float(c1[c]) * p.sl2 - lse_row);
+          const float pr1 = ((badbits >> (c + 1)) & 1u) ? 0.f : fast_exp2(__uint_as_float(c1[c + 1]) * p.sl2 - lse_row);
+          float dp0 = __uint_as_float(c2[c]), dp1 = __uint_as_float(c2[c + 1]);
+          if (p.drop_p > 0.f) {
+            const uint32_t hsh = drop_pair(p.drop_seed, drop_row + c);
+            dp0 = drop_keep_lo(hsh, p.drop_thresh) ? dp0 * p.drop_scale : 0.f;
+            dp1 = drop_keep_hi(hsh, p.drop_thresh) ? dp1 * p.drop_scale : 0.f;
+          }
+          e2[c] = pr0 * (dp0 - delta_row) * p.scale;
+          e2[c + 1] = pr1 * (dp1 - delta_row) * p.scale;
         }
       } else {
         // columns = queries t0 + c ; per-column statistics
@@ -241,7 +247,9 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gri
             float dpv = __uint_as_float(c2[c]);
             float pd = pr;
             if (p.drop_p > 0.f) {
-              const bool keep = dropout_keep(p.drop_seed, p.drop_stream, (bh * p.Sq + qi) * static_cast<uint64_t>(p.Sk) + row_g, p.drop_thresh);
+              const uint64_t eidx = (bh * p.Sq + qi) * static_cast<uint64_t>(p.Sk + (p.Sk & 1)) + row_g;
+              const uint32_t hsh = drop_pair(p.drop_seed, eidx & ~1ull);
+              const bool keep = (eidx & 1) ? drop_keep_hi(hsh, p.drop_thresh) : drop_keep_lo(hsh, p.drop_thresh);
               dpv = keep ? dpv * p.drop_scale : 0.f;
               pd = keep ? pr * p.drop_scale : 0.f;
             }
@@ -322,8 +330,8 @@ extern "C" int xf_attn_bwd(const XfAttnBwd* a, xf_stream_t stream_) {
   p.lse = a->lse; p.delta = a->delta; p.stat_stride = a->stat_stride;
   p.drop_p = a->drop_p;
   p.drop_scale = a->drop_p > 0.f ? 1.f / (1.f - a->drop_p) : 1.f;
-  p.drop_seed = a->drop_seed; p.drop_stream = a->drop_stream;
-  p.drop_thresh = static_cast<uint32_t>(static_cast<double>(a->drop_p) * 4294967296.0);
+  p.drop_seed = drop_key(a->drop_seed, a->drop_stream); p.drop_stream = a->drop_stream;
+  p.drop_thresh = drop_thresh16(a->drop_p);
 
   const uint64_t cols = static_cast<uint64_t>(a->H) * a->dp;
   CUtensorMap q128, do128, k32, v32, k128, v128, q32, do32;

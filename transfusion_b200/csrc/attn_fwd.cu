@@ -167,7 +167,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     const int q = q0 + r;
     const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
     float m_used = 0.f, l = 0.f;
-    const uint64_t drop_row = (static_cast<uint64_t>(b * p.H + hd) * p.Sq + q) * static_cast<uint64_t>(p.Sk);
+    const uint64_t drop_row = (static_cast<uint64_t>(b * p.H + hd) * p.Sq + q) * static_cast<uint64_t>(p.Sk + (p.Sk & 1));
     uint8_t* prow = sP + r * 128;
 
     for (int j = 0; j < nkv; ++j) {
@@ -228,8 +228,11 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       l += psum;
       if (p.drop_p > 0.f) {
 #pragma unroll
-        for (int c = 0; c < 64; ++c)
-          x[c] = dropout_keep(p.drop_seed, p.drop_stream, drop_row + static_cast<uint64_t>(k0 + c), p.drop_thresh) ? x[c] * p.drop_scale : 0.f;
+        for (int c = 0; c < 64; c += 2) {
+          const uint32_t hsh = drop_pair(p.drop_seed, drop_row + static_cast<uint64_t>(k0 + c));
+          x[c] = drop_keep_lo(hsh, p.drop_thresh) ? x[c] * p.drop_scale : 0.f;
+          x[c + 1] = drop_keep_hi(hsh, p.drop_thresh) ? x[c + 1] * p.drop_scale : 0.f;
+        }
       }
       if (j > 0) {
         mbar_wait(O_READY, (j - 1) & 1);  // PV_{j-1} retired: P buffer free, O stable
@@ -340,8 +343,8 @@ extern "C" int xf_attn_fwd(const XfAttnFwd* a, xf_stream_t stream_) {
   p.lse_stride = a->lse_stride > 0 ? a->lse_stride : a->Sq;
   p.drop_p = a->drop_p;
   p.drop_scale = a->drop_p > 0.f ? 1.f / (1.f - a->drop_p) : 1.f;
-  p.drop_seed = a->drop_seed; p.drop_stream = a->drop_stream;
-  p.drop_thresh = static_cast<uint32_t>(static_cast<double>(a->drop_p) * 4294967296.0);
+  p.drop_seed = drop_key(a->drop_seed, a->drop_stream); p.drop_stream = a->drop_stream;
+  p.drop_thresh = drop_thresh16(a->drop_p);
 
   CUtensorMap tq, tk, tv;
   int rc;

@@ -159,35 +159,57 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+__device__ __forceinline__ void unpack8(const uint4& q, float (&v)[8]) {
+  v[0] = bf16_lo(q.x); v[1] = bf16_hi(q.x); v[2] = bf16_lo(q.y); v[3] = bf16_hi(q.y);
+  v[4] = bf16_lo(q.z); v[5] = bf16_hi(q.z); v[6] = bf16_lo(q.w); v[7] = bf16_hi(q.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+  return make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+}
+__device__ __forceinline__ void load8f(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+// dropout on 8 consecutive elements starting at the even linear index idx0
+__device__ __forceinline__ void drop8(float (&v)[8], uint32_t key, uint64_t idx0, uint32_t t16, float scale) {
+#pragma unroll
+  for (int k = 0; k < 8; k += 2) {
+    const uint32_t h = drop_pair(key, idx0 + k);
+    v[k] = drop_keep_lo(h, t16) ? v[k] * scale : 0.f;
+    v[k + 1] = drop_keep_hi(h, t16) ? v[k + 1] * scale : 0.f;
+  }
+}
+
+// NV = 16-byte vectors per lane (row cached in registers as packed bf16)
+template <int NV>
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const LnParams p) {
   const int warps_per_cta = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nvec = p.D >> 3;
   for (int r = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); r < p.rows; r += gridDim.x * warps_per_cta) {
     const __nv_bfloat16* xr = p.x + remap_row(r, p.in_rows_in, p.in_rows_out, p.in_row_off) * p.ldx;
-    uint4 q[LN_MAXV];
+    uint4 q[NV];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int vidx = lane + 32 * i;
       if (vidx < nvec) {
         q[i] = __ldg(reinterpret_cast<const uint4*>(xr) + vidx);
-        s += bf16_lo(q[i].x) + bf16_hi(q[i].x) + bf16_lo(q[i].y) + bf16_hi(q[i].y) + bf16_lo(q[i].z) + bf16_hi(q[i].z) +
-             bf16_lo(q[i].w) + bf16_hi(q[i].w);
+        float v[8]; unpack8(q[i], v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += v[k];
       }
     }
     const float mean = warp_sum(s) / p.D;
     float ss = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int vidx = lane + 32 * i;
       if (vidx < nvec) {
-        const uint32_t w[4] = {q[i].x, q[i].y, q[i].z, q[i].w};
+        float v[8]; unpack8(q[i], v);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float a = bf16_lo(w[k]) - mean, b = bf16_hi(w[k]) - mean;
-          ss += a * a + b * b;
-        }
+        for (int k = 0; k < 8; ++k) { const float a = v[k] - mean; ss += a * a; }
       }
     }
     const float rstd = rsqrtf(warp_sum(ss) / p.D + p.eps);
@@ -195,39 +217,27 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const LnParams p) {
     const long long orow = remap_row(r, p.out_rows_in, p.out_rows_out, p.out_row_off);
     __nv_bfloat16* yr = p.y + orow * p.ldy;
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int vidx = lane + 32 * i;
       if (vidx < nvec) {
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma) + 2 * vidx);
-        const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gamma) + 2 * vidx + 1);
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.beta) + 2 * vidx);
-        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.beta) + 2 * vidx + 1);
-        float o[8];
-        o[0] = (bf16_lo(q[i].x) - mean) * rstd * g0.x + b0.x;
-        o[1] = (bf16_hi(q[i].x) - mean) * rstd * g0.y + b0.y;
-        o[2] = (bf16_lo(q[i].y) - mean) * rstd * g0.z + b0.z;
-        o[3] = (bf16_hi(q[i].y) - mean) * rstd * g0.w + b0.w;
-        o[4] = (bf16_lo(q[i].z) - mean) * rstd * g1.x + b1.x;
-        o[5] = (bf16_hi(q[i].z) - mean) * rstd * g1.y + b1.y;
-        o[6] = (bf16_lo(q[i].w) - mean) * rstd * g1.z + b1.z;
-        o[7] = (bf16_hi(q[i].w) - mean) * rstd * g1.w + b1.w;
-        if (p.drop_p > 0.f) {
+        float v[8], g[8], b[8];
+        unpack8(q[i], v);
+        load8f(p.gamma + vidx * 8, g);
+        load8f(p.beta + vidx * 8, b);
 #pragma unroll
-          for (int k = 0; k < 8; ++k)
-            o[k] = dropout_keep(p.drop_seed, p.drop_stream, static_cast<uint64_t>(orow * p.ldy + vidx * 8 + k), p.drop_thresh)
-                       ? o[k] * p.drop_scale : 0.f;
-        }
-        *(reinterpret_cast<uint4*>(yr) + vidx) =
-            make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+        for (int k = 0; k < 8; ++k) v[k] = (v[k] - mean) * rstd * g[k] + b[k];
+        if (p.drop_p > 0.f) drop8(v, p.drop_seed, static_cast<uint64_t>(orow * p.ldy + vidx * 8), p.drop_thresh, p.drop_scale);
+        *(reinterpret_cast<uint4*>(yr) + vidx) = pack8(v);
       }
     }
   }
 }
 
 // LayerNorm backward.  dx = rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy * gamma.
-// Also: dgamma += sum dy*xhat, dbeta += sum dy (fp32 atomics, one per column per CTA) and, optionally,
-// colsum(dx) (= bias grad of the linear that produced the pre-LN sum) and a second output
-// dx2 = dropout-masked copy of dx (gradient flowing into that linear when dropout1/2 are on).
+// Also: dgamma += sum dy*xhat, dbeta += sum dy (fp32) and, optionally, colsum of the gradient that
+// enters the producing linear (= its bias grad) and a dropout-masked copy dx2 of dx (the gradient of
+// that linear's output when dropout1/2 are on).  Rows are cached as packed bf16; per-lane column
+// accumulators are combined through shared memory, then one global atomic per column per CTA.
 struct LnBwdParams {
   const __nv_bfloat16* dy; long long lddy;     // indexed by "out" remap of the forward
   const __nv_bfloat16* x; long long ldx;       // forward input (pre-LN), "in" remap
@@ -238,61 +248,60 @@ struct LnBwdParams {
   int rows, D;
   int in_rows_in, in_rows_out, in_row_off;
   int out_rows_in, out_rows_out, out_row_off;
-  // dropout applied to the forward LN output (mask on dy) and/or to the branch that fed the LN input (dx2)
   float dy_drop_p; uint32_t dy_seed, dy_stream, dy_thresh; float dy_scale;
   float dx2_drop_p; uint32_t dx2_seed, dx2_stream, dx2_thresh; float dx2_scale;
 };
 
+template <int NV>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const LnBwdParams p) {
-  extern __shared__ float red[];  // [3][warps][D] would be large; instead reduce with atomics per CTA via smem [3][D]
+  extern __shared__ float red[];  // [3][D]
   const int warps_per_cta = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nvec = p.D >> 3;
-  float* s_dg = red;
-  float* s_db = red + p.D;
-  float* s_dbias = red + 2 * p.D;
   for (int i = threadIdx.x; i < 3 * p.D; i += blockDim.x) red[i] = 0.f;
-  __syncthreads();
 
-  float acc_dg[LN_MAXV][8], acc_db[LN_MAXV][8], acc_dbias[LN_MAXV][8];
+  float acc_dg[NV][8], acc_db[NV][8], acc_dbias[NV][8];
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i)
+  for (int i = 0; i < NV; ++i)
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc_dg[i][k] = acc_db[i][k] = acc_dbias[i][k] = 0.f;
 
-  for (int r = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); r < p.rows; r += gridDim.x * warps_per_cta) {
+  for (int r = blockIdx.x * warps_per_cta + warp; r < p.rows; r += gridDim.x * warps_per_cta) {
     const long long irow = remap_row(r, p.in_rows_in, p.in_rows_out, p.in_row_off);
     const long long orow = remap_row(r, p.out_rows_in, p.out_rows_out, p.out_row_off);
     const __nv_bfloat16* xr = p.x + irow * p.ldx;
     const __nv_bfloat16* dyr = p.dy + orow * p.lddy;
     const float mean = p.mean[r], rstd = p.rstd[r];
-    float xh[LN_MAXV][8], g[LN_MAXV][8];
+    uint4 qx[NV], qd[NV];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int vidx = lane + 32 * i;
       if (vidx < nvec) {
-        const uint4 qx = __ldg(reinterpret_cast<const uint4*>(xr) + vidx);
-        const uint4 qd = __ldg(reinterpret_cast<const uint4*>(dyr) + vidx);
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma) + 2 * vidx);
-        const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gamma) + 2 * vidx + 1);
-        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-        const uint32_t wx[4] = {qx.x, qx.y, qx.z, qx.w};
-        const uint32_t wd[4] = {qd.x, qd.y, qd.z, qd.w};
+        qx[i] = __ldg(reinterpret_cast<const uint4*>(xr) + vidx);
+        qd[i] = __ldg(reinterpret_cast<const uint4*>(dyr) + vidx);
+      }
+    }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          float d0 = bf16_lo(wd[k]), d1 = bf16_hi(wd[k]);
-          if (p.dy_drop_p > 0.f) {
-            d0 = dropout_keep(p.dy_seed, p.dy_stream, static_cast<uint64_t>(orow * p.lddy + vidx * 8 + 2 * k), p.dy_thresh) ? d0 * p.dy_scale : 0.f;
-            d1 = dropout_keep(p.dy_seed, p.dy_stream, static_cast<uint64_t>(orow * p.lddy + vidx * 8 + 2 * k + 1), p.dy_thresh) ? d1 * p.dy_scale : 0.f;
-          }
-          const float x0 = (bf16_lo(wx[k]) - mean) * rstd, x1 = (bf16_hi(wx[k]) - mean) * rstd;
-          xh[i][2 * k] = x0; xh[i][2 * k + 1] = x1;
-          g[i][2 * k] = d0 * gm[2 * k]; g[i][2 * k + 1] = d1 * gm[2 * k + 1];
-          acc_dg[i][2 * k] += d0 * x0; acc_dg[i][2 * k + 1] += d1 * x1;
-          acc_db[i][2 * k] += d0; acc_db[i][2 * k + 1] += d1;
-          s1 += g[i][2 * k] + g[i][2 * k + 1];
-          s2 += g[i][2 * k] * x0 + g[i][2 * k + 1] * x1;
+    for (int i = 0; i < NV; ++i) {
+      const int vidx = lane + 32 * i;
+      if (vidx < nvec) {
+        float xv[8], dv[8], gm[8];
+        unpack8(qx[i], xv); unpack8(qd[i], dv);
+        load8f(p.gamma + vidx * 8, gm);
+        if (p.dy_drop_p > 0.f) {
+          drop8(dv, p.dy_seed, static_cast<uint64_t>(orow * p.lddy + vidx * 8), p.dy_thresh, p.dy_scale);
+          qd[i] = pack8(dv);  // keep the masked gradient (exactly representable: scale applied in fp32, re-rounded once)
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float xh = (xv[k] - mean) * rstd;
+          const float g = dv[k] * gm[k];
+          acc_dg[i][k] += dv[k] * xh;
+          acc_db[i][k] += dv[k];
+          s1 += g;
+          s2 += g * xh;
         }
       }
     }
@@ -300,53 +309,49 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const LnBwdParams p)
     s2 = warp_sum(s2) / p.D;
     __nv_bfloat16* dxr = p.dx + irow * p.lddx;
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int vidx = lane + 32 * i;
       if (vidx < nvec) {
-        float o[8];
+        float xv[8], dv[8], gm[8], o[8];
+        unpack8(qx[i], xv); unpack8(qd[i], dv);
+        load8f(p.gamma + vidx * 8, gm);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          o[k] = rstd * (g[i][k] - s1 - xh[i][k] * s2);
-          // bias grad of the producing linear sees the (dropout-masked) gradient
-        }
-        *(reinterpret_cast<uint4*>(dxr) + vidx) =
-            make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+        for (int k = 0; k < 8; ++k) o[k] = rstd * (dv[k] * gm[k] - s1 - (xv[k] - mean) * rstd * s2);
+        *(reinterpret_cast<uint4*>(dxr) + vidx) = pack8(o);
         if (p.dx2) {
-          float o2[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            o2[k] = o[k];
-            if (p.dx2_drop_p > 0.f)
-              o2[k] = dropout_keep(p.dx2_seed, p.dx2_stream, static_cast<uint64_t>(irow * p.lddx + vidx * 8 + k), p.dx2_thresh) ? o[k] * p.dx2_scale : 0.f;
-            acc_dbias[i][k] += o2[k];
-          }
-          *(reinterpret_cast<uint4*>(p.dx2 + irow * p.lddx) + vidx) =
-              make_uint4(pack_bf16(o2[0], o2[1]), pack_bf16(o2[2], o2[3]), pack_bf16(o2[4], o2[5]), pack_bf16(o2[6], o2[7]));
-        } else {
+          if (p.dx2_drop_p > 0.f) drop8(o, p.dx2_seed, static_cast<uint64_t>(irow * p.lddx + vidx * 8), p.dx2_thresh, p.dx2_scale);
+          *(reinterpret_cast<uint4*>(p.dx2 + irow * p.lddx) + vidx) = pack8(o);
+        }
+        if (p.dbias) {
 #pragma unroll
           for (int k = 0; k < 8; ++k) acc_dbias[i][k] += o[k];
         }
       }
     }
   }
-  // CTA-level reduction in shared memory, then one global atomic per column per CTA
+  // combine the 8 warps' column accumulators in shared memory (warp-serialised, no atomics)
+  __syncthreads();
+  for (int w = 0; w < warps_per_cta; ++w) {
+    if (warp == w) {
 #pragma unroll
-  for (int i = 0; i < LN_MAXV; ++i) {
-    const int vidx = lane + 32 * i;
-    if (vidx < nvec) {
+      for (int i = 0; i < NV; ++i) {
+        const int vidx = lane + 32 * i;
+        if (vidx < nvec) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        atomicAdd(&s_dg[vidx * 8 + k], acc_dg[i][k]);
-        atomicAdd(&s_db[vidx * 8 + k], acc_db[i][k]);
-        if (p.dbias) atomicAdd(&s_dbias[vidx * 8 + k], acc_dbias[i][k]);
+          for (int k = 0; k < 8; ++k) {
+            red[vidx * 8 + k] += acc_dg[i][k];
+            red[p.D + vidx * 8 + k] += acc_db[i][k];
+            if (p.dbias) red[2 * p.D + vidx * 8 + k] += acc_dbias[i][k];
+          }
+        }
       }
     }
+    __syncthreads();
   }
-  __syncthreads();
   for (int i = threadIdx.x; i < p.D; i += blockDim.x) {
-    atomicAdd(p.dgamma + i, s_dg[i]);
-    atomicAdd(p.dbeta + i, s_db[i]);
-    if (p.dbias) atomicAdd(p.dbias + i, s_dbias[i]);
+    atomicAdd(p.dgamma + i, red[i]);
+    atomicAdd(p.dbeta + i, red[p.D + i]);
+    if (p.dbias) atomicAdd(p.dbias + i, red[2 * p.D + i]);
   }
 }
 
@@ -446,11 +451,7 @@ rows_gather_kernel(const __nv_bfloat16* __restrict__ in, long long ldi, __nv_bfl
     const long long ir = remap_row(r, rin, rout, roff);
     const uint4 q = __ldg(reinterpret_cast<const uint4*>(in + ir * ldi) + vc);
     float v[8] = {bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y), bf16_lo(q.z), bf16_hi(q.z), bf16_lo(q.w), bf16_hi(q.w)};
-    if (drop_p > 0.f) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        v[k] = dropout_keep(seed, stream, static_cast<uint64_t>(ir * ldi + vc * 8 + k), thresh) ? v[k] * drop_scale : 0.f;
-    }
+    if (drop_p > 0.f) drop8(v, seed, static_cast<uint64_t>(ir * ldi + vc * 8), thresh, drop_scale);
 #pragma unroll
     for (int k = 0; k < 8; ++k) s[k] += v[k];
     *(reinterpret_cast<uint4*>(out + static_cast<long long>(r) * ldo) + vc) =
@@ -550,10 +551,16 @@ extern "C" int xf_layernorm_fwd(const XfLayerNorm* a, xf_stream_t s) {
   p.in_rows_in = a->in_rows_in; p.in_rows_out = a->in_rows_out; p.in_row_off = a->in_row_off;
   p.out_rows_in = a->out_rows_in; p.out_rows_out = a->out_rows_out; p.out_row_off = a->out_row_off;
   p.eps = a->eps;
-  p.drop_p = a->drop_p; p.drop_seed = a->drop_seed; p.drop_stream = a->drop_stream;
-  p.drop_thresh = static_cast<uint32_t>(static_cast<double>(a->drop_p) * 4294967296.0);
+  p.drop_p = a->drop_p; p.drop_seed = drop_key(a->drop_seed, a->drop_stream); p.drop_stream = a->drop_stream;
+  p.drop_thresh = drop_thresh16(a->drop_p);
   p.drop_scale = a->drop_p > 0.f ? 1.f / (1.f - a->drop_p) : 1.f;
-  layernorm_fwd_kernel<<<grid_for(a->rows, 8), 256, 0, reinterpret_cast<cudaStream_t>(s)>>>(p);
+  const int nv = (a->D / 8 + 31) / 32;
+  const int grid = grid_for(a->rows, 8);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(s);
+  if (nv <= 1) layernorm_fwd_kernel<1><<<grid, 256, 0, st>>>(p);
+  else if (nv <= 2) layernorm_fwd_kernel<2><<<grid, 256, 0, st>>>(p);
+  else if (nv <= 4) layernorm_fwd_kernel<4><<<grid, 256, 0, st>>>(p);
+  else layernorm_fwd_kernel<8><<<grid, 256, 0, st>>>(p);
   g_launches.fetch_add(1);
   XF_CUDA(cudaGetLastError());
   return 0;
@@ -576,14 +583,22 @@ extern "C" int xf_layernorm_bwd(const XfLayerNormBwd* a, xf_stream_t s) {
   p.rows = a->rows; p.D = a->D;
   p.in_rows_in = a->in_rows_in; p.in_rows_out = a->in_rows_out; p.in_row_off = a->in_row_off;
   p.out_rows_in = a->out_rows_in; p.out_rows_out = a->out_rows_out; p.out_row_off = a->out_row_off;
-  p.dy_drop_p = a->dy_drop_p; p.dy_seed = a->dy_drop_seed; p.dy_stream = a->dy_drop_stream;
-  p.dy_thresh = static_cast<uint32_t>(static_cast<double>(a->dy_drop_p) * 4294967296.0);
+  p.dy_drop_p = a->dy_drop_p; p.dy_seed = drop_key(a->dy_drop_seed, a->dy_drop_stream); p.dy_stream = a->dy_drop_stream;
+  p.dy_thresh = drop_thresh16(a->dy_drop_p);
   p.dy_scale = a->dy_drop_p > 0.f ? 1.f / (1.f - a->dy_drop_p) : 1.f;
-  p.dx2_drop_p = a->dx2_drop_p; p.dx2_seed = a->dx2_drop_seed; p.dx2_stream = a->dx2_drop_stream;
-  p.dx2_thresh = static_cast<uint32_t>(static_cast<double>(a->dx2_drop_p) * 4294967296.0);
+  p.dx2_drop_p = a->dx2_drop_p; p.dx2_seed = drop_key(a->dx2_drop_seed, a->dx2_drop_stream); p.dx2_stream = a->dx2_drop_stream;
+  p.dx2_thresh = drop_thresh16(a->dx2_drop_p);
   p.dx2_scale = a->dx2_drop_p > 0.f ? 1.f / (1.f - a->dx2_drop_p) : 1.f;
-  const int ctas = grid_for(a->rows, 8 * 16, 2);  // >= 16 rows per warp so the per-CTA column atomics amortise
-  layernorm_bwd_kernel<<<ctas, 256, 3 * a->D * sizeof(float), reinterpret_cast<cudaStream_t>(s)>>>(p);
+  int ctas = (a->rows + 8 * 8 - 1) / (8 * 8);  // >= 8 rows per warp so the per-CTA column reduction amortises
+  if (ctas > 2 * sm_count()) ctas = 2 * sm_count();
+  if (ctas < 1) ctas = 1;
+  const int nv = (a->D / 8 + 31) / 32;
+  const size_t sh = 3 * a->D * sizeof(float);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(s);
+  if (nv <= 1) layernorm_bwd_kernel<1><<<ctas, 256, sh, st>>>(p);
+  else if (nv <= 2) layernorm_bwd_kernel<2><<<ctas, 256, sh, st>>>(p);
+  else if (nv <= 4) layernorm_bwd_kernel<4><<<ctas, 256, sh, st>>>(p);
+  else layernorm_bwd_kernel<8><<<ctas, 256, sh, st>>>(p);
   g_launches.fetch_add(1);
   XF_CUDA(cudaGetLastError());
   return 0;
@@ -653,7 +668,7 @@ extern "C" int xf_rows_gather(const void* in, int64_t ldi, void* out, int64_t ld
   gy = (rows + rows_per_cta - 1) / rows_per_cta;
   rows_gather_kernel<<<dim3(gx, gy), 256, 0, reinterpret_cast<cudaStream_t>(s)>>>(
       reinterpret_cast<const __nv_bfloat16*>(in), ldi, reinterpret_cast<__nv_bfloat16*>(out), ldo, rows, D, rin, rout, roff,
-      rows_per_cta, colsum, drop_p, seed, stream_id, static_cast<uint32_t>(static_cast<double>(drop_p) * 4294967296.0),
+      rows_per_cta, colsum, drop_p, drop_key(seed, stream_id), stream_id, drop_thresh16(drop_p),
       drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f);
   g_launches.fetch_add(1);
   XF_CUDA(cudaGetLastError());

@@ -107,8 +107,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int m, int n
   const long long orow = static_cast<long long>(m_out) * p.ldc + n0;
   if (p.drop_p > 0.f && p.drop_first) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i)
-      v[i] = dropout_keep(p.drop_seed, p.drop_stream, static_cast<uint64_t>(orow + i), p.drop_thresh) ? v[i] * p.drop_scale : 0.f;
+    for (int i = 0; i < 32; i += 2) {
+      const uint32_t hsh = drop_pair(p.drop_seed, static_cast<uint64_t>(orow + i));
+      v[i] = drop_keep_lo(hsh, p.drop_thresh) ? v[i] * p.drop_scale : 0.f;
+      v[i + 1] = drop_keep_hi(hsh, p.drop_thresh) ? v[i + 1] * p.drop_scale : 0.f;
+    }
   }
   if (p.act == 1) {
     if (p.preact_out) {
@@ -148,8 +151,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int m, int n
   }
   if (p.drop_p > 0.f && !p.drop_first) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i)
-      v[i] = dropout_keep(p.drop_seed, p.drop_stream, static_cast<uint64_t>(orow + i), p.drop_thresh) ? v[i] * p.drop_scale : 0.f;
+    for (int i = 0; i < 32; i += 2) {
+      const uint32_t hsh = drop_pair(p.drop_seed, static_cast<uint64_t>(orow + i));
+      v[i] = drop_keep_lo(hsh, p.drop_thresh) ? v[i] * p.drop_scale : 0.f;
+      v[i + 1] = drop_keep_hi(hsh, p.drop_thresh) ? v[i + 1] * p.drop_scale : 0.f;
+    }
   }
   if (p.residual) {
     const __nv_bfloat16* rs = p.residual + static_cast<long long>(m_out) * p.ldr + n0;
@@ -408,10 +414,11 @@ extern "C" int xf_gemm(const XfGemm* g, xf_stream_t stream_) {
              (!g->pos_table || ((reinterpret_cast<uintptr_t>(g->pos_table) & 15) == 0)) &&
              (!g->bias || ((reinterpret_cast<uintptr_t>(g->bias) & 15) == 0));
   p.drop_p = g->drop_p;
-  p.drop_seed = g->drop_seed;
+  p.drop_seed = drop_key(g->drop_seed, g->drop_stream);  // per-call key
   p.drop_stream = g->drop_stream;
   p.drop_first = g->drop_first;
-  p.drop_thresh = static_cast<uint32_t>(static_cast<double>(g->drop_p) * 4294967296.0);
+  p.drop_thresh = drop_thresh16(g->drop_p);
+  if (g->drop_p > 0.f && (g->ldc % 2)) return fail(-7, "xf_gemm: dropout needs an even ldc");
   p.drop_scale = g->drop_p > 0.f ? 1.0f / (1.0f - g->drop_p) : 1.0f;
 
   CUtensorMap ta, tb;

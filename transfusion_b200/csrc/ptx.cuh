@@ -207,15 +207,26 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-// Counter-based dropout decision: keep iff hash(seed, idx) >= thresh (thresh = p * 2^32).
-__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+// Counter-based dropout (no mask storage; the backward recomputes the same bits).  One 32-bit hash
+// (lowbias32 finaliser over the pair counter XOR a per-call key) decides TWO adjacent elements: element
+// 2j keeps iff the low 16 bits >= t16, element 2j+1 iff the high 16 bits >= t16, t16 = round(p * 65536).
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
   x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
   return x;
 }
-__device__ __forceinline__ bool dropout_keep(uint32_t seed, uint32_t stream, uint64_t idx, uint32_t thresh) {
-  uint32_t h = mix32(static_cast<uint32_t>(idx) ^ seed);
-  h = mix32(h + static_cast<uint32_t>(idx >> 32) * 0x9E3779B9U + stream);
-  return h >= thresh;
+__host__ __device__ __forceinline__ uint32_t drop_key(uint32_t seed, uint32_t stream) {
+  return mix32(seed ^ (stream * 0x9E3779B9U) ^ 0x5bd1e995U);
 }
+__host__ __device__ __forceinline__ uint32_t drop_thresh16(float p) {
+  return static_cast<uint32_t>(static_cast<double>(p) * 65536.0 + 0.5);
+}
+// even_idx: linear index of the even element of the pair
+__device__ __forceinline__ uint32_t drop_pair(uint32_t key, uint64_t even_idx) {
+  const uint32_t lo = static_cast<uint32_t>(even_idx >> 1);
+  const uint32_t hi = static_cast<uint32_t>(even_idx >> 33);
+  return mix32(lo ^ key ^ (hi * 0x85EBCA6BU));
+}
+__device__ __forceinline__ bool drop_keep_lo(uint32_t h, uint32_t t16) { return (h & 0xFFFFu) >= t16; }
+__device__ __forceinline__ bool drop_keep_hi(uint32_t h, uint32_t t16) { return (h >> 16) >= t16; }
 
 }  // namespace xf

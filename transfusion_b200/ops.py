@@ -97,7 +97,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     g.accumulate = int(accumulate)
     g.drop_p, g.drop_seed, g.drop_stream, g.drop_first = drop_p, drop_seed, drop_stream, int(drop_first)
     g.max_ctas = max_ctas
-    with _Prof("gemm", 2.0 * M * N * K):
+    fam = "gemm_wgrad" if a_mn_major else ("gemm_dgrad" if b_mn_major else "gemm_fwd")
+    with _Prof(fam, 2.0 * M * N * K):
         check(lib().xf_gemm(C.byref(g), _stream()), "xf_gemm")
     return out
 
