@@ -72,6 +72,7 @@ typedef struct XfGemm {
   uint32_t drop_seed, drop_stream;
   int32_t drop_first;
   int32_t max_ctas;         /* 0 = one per SM */
+  int32_t cta_group;        /* 0 = auto (CTA pairs, 256 x tile_n tiles via cta_group::2), 1 = single-CTA 128 x tile_n tiles, 2 = force pairs */
 } XfGemm;
 
 int xf_gemm(const XfGemm* g, xf_stream_t stream);
@@ -181,6 +182,7 @@ typedef struct XfAttnBwd {
   void* dk; int64_t lddk;
   void* dv; int64_t lddv;
   const uint8_t* key_padding_mask;
+  int32_t kpm_start;                               /* keys < kpm_start are never masked */
   int32_t B, H, Sq, Sk, dp;
   float scale;
   float drop_p; uint32_t drop_seed, drop_stream;   /* must equal the forward's */

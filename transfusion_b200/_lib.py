@@ -30,7 +30,7 @@ class XfGemm(C.Structure):
         ("out", C.c_void_p), ("ldc", C.c_int64),
         ("out_dtype", C.c_int32), ("accumulate", C.c_int32),
         ("drop_p", C.c_float), ("drop_seed", C.c_uint32), ("drop_stream", C.c_uint32),
-        ("drop_first", C.c_int32), ("max_ctas", C.c_int32),
+        ("drop_first", C.c_int32), ("max_ctas", C.c_int32), ("cta_group", C.c_int32),
     ]
 
 
@@ -91,6 +91,7 @@ class XfAttnBwd(C.Structure):
         ("dk", C.c_void_p), ("lddk", C.c_int64),
         ("dv", C.c_void_p), ("lddv", C.c_int64),
         ("key_padding_mask", C.c_void_p),
+        ("kpm_start", C.c_int32),
         ("B", C.c_int32), ("H", C.c_int32), ("Sq", C.c_int32), ("Sk", C.c_int32), ("dp", C.c_int32),
         ("scale", C.c_float),
         ("drop_p", C.c_float), ("drop_seed", C.c_uint32), ("drop_stream", C.c_uint32),

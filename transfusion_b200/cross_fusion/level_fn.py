@@ -316,7 +316,7 @@ class FusionLevelFunction(torch.autograd.Function):
             dqkv = empty(M, 3 * Dp)
             ops.attn_bwd(qkv[:, :Dp], qkv[:, Dp:2 * Dp], qkv[:, 2 * Dp:], datt, lse, delta,
                          dqkv[:, :Dp], dqkv[:, Dp:2 * Dp], dqkv[:, 2 * Dp:], B=B, H=H, Sq=S, Sk=S, dp=dp, scale=scale,
-                         key_padding_mask=kpm, drop_p=pd_tok, drop_seed=seed, drop_stream=cfg.stream(l, SITE_ATTN))
+                         key_padding_mask=kpm, kpm_start=n, drop_p=pd_tok, drop_seed=seed, drop_stream=cfg.stream(l, SITE_ATTN))
             del datt
             # in_proj
             g_bin_p = zeros(3 * Dp); ops.colsum(dqkv, g_bin_p, M, 3 * Dp)

@@ -38,6 +38,7 @@ struct AttnBwdParams {
   int B, H, Sq, Sk, dp, nch, r_tiles, n_stream, ncbuf;
   float sl2, scale;
   const uint8_t* kpm;      // [B, Sk] 1 = ignore, or null
+  int kpm_start;           // keys < kpm_start are never masked
   const float* lse;        // [B, H, stat_stride] log2 domain
   const float* delta;      // [B, H, stat_stride]
   int stat_stride;
@@ -126,28 +127,40 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gri
     }
   } else if (warp == 1) {
     if (lane == 0) {
+      // The score MMAs are N = 32 (16 tensor-pipe cycles each), so this thread has to issue one every few
+      // cycles: all shared-memory descriptors are built once (only the low word varies: start address),
+      // the loop body is an add + the MMA.
       const uint32_t idesc_c = make_idesc_bf16(AB_BN, 0, 0);
       const uint32_t idesc_acc = make_idesc_bf16(p.dp, 0, 1);
       const int ksteps = p.dp / 16;
       const uint32_t r1a = smem_u32(sR1), r2a = smem_u32(sR2), e1a = smem_u32(sE1), e2a = smem_u32(sE2);
+      const uint64_t dk = make_smem_desc(0, 16, 512, SW64);      // K-major template (start = 0)
+      const uint64_t dmn = make_smem_desc(0, 2048, 512, SW64);   // MN-major template
+      const uint32_t hi_k = static_cast<uint32_t>(dk >> 32), hi_mn = static_cast<uint32_t>(dmn >> 32);
+      const uint32_t lo_k = static_cast<uint32_t>(dk), lo_mn = static_cast<uint32_t>(dmn);
+      auto mk = [](uint32_t hi, uint32_t lo) { return (static_cast<uint64_t>(hi) << 32) | lo; };
+      constexpr int MAXK = 14;  // dp <= 224
+      uint32_t r1lo[MAXK], r2lo[MAXK];
+#pragma unroll
+      for (int kk = 0; kk < MAXK; ++kk) {
+        const uint32_t off = (kk >> 1) * 8192 + (kk & 1) * 32;
+        r1lo[kk] = lo_k + ((r1a + off) >> 4);
+        r2lo[kk] = lo_k + ((r2a + off) >> 4);
+      }
+      const uint32_t e1lo = lo_k + (e1a >> 4), e2lo = lo_k + (e2a >> 4);
+      const uint32_t t_base = smem_u32(sT);
       auto do_acc = [&](int i) {
         const int st = i % AB_STAGES;
-        const uint32_t t1 = smem_u32(sT + st * 2 * t_bytes), t2 = t1 + t_bytes;
+        const uint32_t t1s = (t_base + st * 2 * t_bytes) >> 4, t2s = t1s + (t_bytes >> 4);
         mbar_wait(E_FULL, i & 1);
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < AB_BN / 16; ++k) {
-          const uint64_t da = make_smem_desc(e2a + k * 32, 16, 512, SW64);
-          const uint64_t db = make_smem_desc(t1 + k * 1024, 2048, 512, SW64);
-          umma_bf16(tmem_acc2, da, db, idesc_acc, (i | k) != 0);
-        }
+        for (int k = 0; k < AB_BN / 16; ++k)
+          umma_bf16(tmem_acc2, mk(hi_k, e2lo + k * 2), mk(hi_mn, lo_mn + t1s + k * 64), idesc_acc, (i | k) != 0);
         if (DKV) {
 #pragma unroll
-          for (int k = 0; k < AB_BN / 16; ++k) {
-            const uint64_t da = make_smem_desc(e1a + k * 32, 16, 512, SW64);
-            const uint64_t db = make_smem_desc(t2 + k * 1024, 2048, 512, SW64);
-            umma_bf16(tmem_acc1, da, db, idesc_acc, (i | k) != 0);
-          }
+          for (int k = 0; k < AB_BN / 16; ++k)
+            umma_bf16(tmem_acc1, mk(hi_k, e1lo + k * 2), mk(hi_mn, lo_mn + t2s + k * 64), idesc_acc, (i | k) != 0);
         }
         umma_commit(T_EMPTY(st));
         umma_commit(E_EMPTY);
@@ -158,18 +171,14 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gri
         mbar_wait(T_FULL(st), (i / AB_STAGES) & 1);
         mbar_wait(C_EMPTY(cb), ((i / p.ncbuf) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t t1 = smem_u32(sT + st * 2 * t_bytes), t2 = t1 + t_bytes;
+        const uint32_t t1s = lo_k + ((t_base + st * 2 * t_bytes) >> 4), t2s = t1s + (t_bytes >> 4);
         const uint32_t c1 = tmem_C + cb * 64, c2 = c1 + 32;
-        for (int kk = 0; kk < ksteps; ++kk) {
-          const uint64_t da = make_smem_desc(r1a + (kk >> 1) * 8192 + (kk & 1) * 32, 16, 512, SW64);
-          const uint64_t db = make_smem_desc(t1 + (kk >> 1) * 2048 + (kk & 1) * 32, 16, 512, SW64);
-          umma_bf16(c1, da, db, idesc_c, kk != 0);
-        }
-        for (int kk = 0; kk < ksteps; ++kk) {
-          const uint64_t da = make_smem_desc(r2a + (kk >> 1) * 8192 + (kk & 1) * 32, 16, 512, SW64);
-          const uint64_t db = make_smem_desc(t2 + (kk >> 1) * 2048 + (kk & 1) * 32, 16, 512, SW64);
-          umma_bf16(c2, da, db, idesc_c, kk != 0);
-        }
+#pragma unroll
+        for (int kk = 0; kk < MAXK; ++kk)
+          if (kk < ksteps) umma_bf16(c1, mk(hi_k, r1lo[kk]), mk(hi_k, t1s + (kk >> 1) * 128 + (kk & 1) * 2), idesc_c, kk != 0);
+#pragma unroll
+        for (int kk = 0; kk < MAXK; ++kk)
+          if (kk < ksteps) umma_bf16(c2, mk(hi_k, r2lo[kk]), mk(hi_k, t2s + (kk >> 1) * 128 + (kk & 1) * 2), idesc_c, kk != 0);
         umma_commit(C_FULL(cb));
         if (i >= 1) do_acc(i - 1);
       }
@@ -198,6 +207,26 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gri
     for (int i = 0; i < n; ++i) {
       const int cb = i % p.ncbuf;
       const int t0 = i * AB_BN;
+      // global-memory operands of this iteration are requested BEFORE waiting on the MMA so their
+      // latency hides behind it: key-padding bits (dQ pass) / per-query LSE and delta (dK/dV pass)
+      uint32_t badbits = 0;
+      float ls[32], ds[32];
+      if (!DKV) {
+        const int key = t0 + lane;
+        bool bad = key >= p.Sk;
+        if (!bad && p.kpm && t0 + AB_BN > p.kpm_start) bad = p.kpm[static_cast<long long>(b) * p.Sk + key] != 0;
+        badbits = __ballot_sync(0xffffffffu, bad);
+      } else {
+        const float4* lp = reinterpret_cast<const float4*>(p.lse + stat_base + t0);
+        const float4* dl = reinterpret_cast<const float4*>(p.delta + stat_base + t0);
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 L = __ldg(lp + c4);
+          const float4 Dl = __ldg(dl + c4);
+          ls[4 * c4] = L.x; ls[4 * c4 + 1] = L.y; ls[4 * c4 + 2] = L.z; ls[4 * c4 + 3] = L.w;
+          ds[4 * c4] = Dl.x; ds[4 * c4 + 1] = Dl.y; ds[4 * c4 + 2] = Dl.z; ds[4 * c4 + 3] = Dl.w;
+        }
+      }
       mbar_wait(C_FULL(cb), (i / p.ncbuf) & 1);
       tc_fence_after();
       uint32_t c1[32], c2[32];
@@ -211,9 +240,6 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gri
       float e1[32], e2[32];
       if (!DKV) {
         // columns = keys t0 + c
-        const int key = t0 + lane;
-        const bool bad = key >= p.Sk || (p.kpm && p.kpm[static_cast<long long>(b) * p.Sk + key] != 0);
-        const uint32_t badbits = __ballot_sync(0xffffffffu, bad);
         const uint64_t drop_row = (bh * p.Sq + row_g) * static_cast<uint64_t>(p.Sk + (p.Sk & 1)) + t0;
 #pragma unroll
         for (int c = 0; c < 32; c += 2) {
@@ -230,32 +256,22 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gri
         }
       } else {
         // columns = queries t0 + c ; per-column statistics
-        const float4* lp = reinterpret_cast<const float4*>(p.lse + stat_base + t0);
-        const float4* dl = reinterpret_cast<const float4*>(p.delta + stat_base + t0);
 #pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
-          const float4 L = __ldg(lp + c4);
-          const float4 Dl = __ldg(dl + c4);
-          const float ls[4] = {L.x, L.y, L.z, L.w};
-          const float ds[4] = {Dl.x, Dl.y, Dl.z, Dl.w};
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int c = c4 * 4 + u;
-            const int qi = t0 + c;
-            const bool ok = row_valid && qi < p.Sq;
-            const float pr = ok ? fast_exp2(__uint_as_float(c1[c]) * p.sl2 - ls[u]) : 0.f;
-            float dpv = __uint_as_float(c2[c]);
-            float pd = pr;
-            if (p.drop_p > 0.f) {
-              const uint64_t eidx = (bh * p.Sq + qi) * static_cast<uint64_t>(p.Sk + (p.Sk & 1)) + row_g;
-              const uint32_t hsh = drop_pair(p.drop_seed, eidx & ~1ull);
-              const bool keep = (eidx & 1) ? drop_keep_hi(hsh, p.drop_thresh) : drop_keep_lo(hsh, p.drop_thresh);
-              dpv = keep ? dpv * p.drop_scale : 0.f;
-              pd = keep ? pr * p.drop_scale : 0.f;
-            }
-            e1[c] = pd;
-            e2[c] = ok ? pr * (dpv - ds[u]) * p.scale : 0.f;
+        for (int c = 0; c < 32; ++c) {
+          const int qi = t0 + c;
+          const bool ok = row_valid && qi < p.Sq;
+          const float pr = ok ? fast_exp2(__uint_as_float(c1[c]) * p.sl2 - ls[c]) : 0.f;
+          float dpv = __uint_as_float(c2[c]);
+          float pd = pr;
+          if (p.drop_p > 0.f) {
+            const uint64_t eidx = (bh * p.Sq + qi) * static_cast<uint64_t>(p.Sk + (p.Sk & 1)) + row_g;
+            const uint32_t hsh = drop_pair(p.drop_seed, eidx & ~1ull);
+            const bool keep = (eidx & 1) ? drop_keep_hi(hsh, p.drop_thresh) : drop_keep_lo(hsh, p.drop_thresh);
+            dpv = keep ? dpv * p.drop_scale : 0.f;
+            pd = keep ? pr * p.drop_scale : 0.f;
           }
+          e1[c] = pd;
+          e2[c] = ok ? pr * (dpv - ds[c]) * p.scale : 0.f;
         }
       }
       if (i > 0) mbar_wait(E_EMPTY, (i - 1) & 1);
@@ -327,6 +343,7 @@ extern "C" int xf_attn_bwd(const XfAttnBwd* a, xf_stream_t stream_) {
   p.sl2 = a->scale * 1.4426950408889634f;
   p.scale = a->scale;
   p.kpm = a->key_padding_mask;
+  p.kpm_start = a->kpm_start;
   p.lse = a->lse; p.delta = a->delta; p.stat_stride = a->stat_stride;
   p.drop_p = a->drop_p;
   p.drop_scale = a->drop_p > 0.f ? 1.f / (1.f - a->drop_p) : 1.f;

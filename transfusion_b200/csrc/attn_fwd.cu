@@ -124,20 +124,31 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     }
   } else if (warp == 1) {
     if (lane == 0) {
+      // descriptors are built once; only the start-address word changes per MMA (issue-rate matters
+      // for the N = 64 score MMAs)
       const uint32_t idesc_s = make_idesc_bf16(AF_BN, 0, 0);
       const uint32_t idesc_o = make_idesc_bf16(p.dp, 0, 1);
       const int ksteps = p.dp / 16;
+      const uint64_t dk = make_smem_desc(0, 16, 1024);       // K-major SWIZZLE_128B template
+      const uint64_t dmn = make_smem_desc(0, 8192, 1024);    // MN-major template (V)
+      const uint32_t hi_k = static_cast<uint32_t>(dk >> 32), hi_mn = static_cast<uint32_t>(dmn >> 32);
+      const uint32_t lo_k = static_cast<uint32_t>(dk), lo_mn = static_cast<uint32_t>(dmn);
+      auto mk = [](uint32_t hi, uint32_t lo) { return (static_cast<uint64_t>(hi) << 32) | lo; };
+      constexpr int MAXK = 16;  // dp <= 256
+      uint32_t qlo[MAXK];
+      const uint32_t qa = smem_u32(sQ);
+#pragma unroll
+      for (int k = 0; k < MAXK; ++k) qlo[k] = lo_k + ((qa + (k >> 2) * 16384 + (k & 3) * 32) >> 4);
+      const uint32_t k_base = smem_u32(sK), v_base = smem_u32(sV), plo = lo_k + (smem_u32(sP) >> 4);
       auto issue_s = [&](int j) {
         const int st = j & 1, sb = j & 1;
         mbar_wait(K_FULL(st), (j >> 1) & 1);
         mbar_wait(S_EMPTY(sb), ((j >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t qa = smem_u32(sQ), ka = smem_u32(sK + st * kv_bytes);
-        for (int k = 0; k < ksteps; ++k) {
-          const uint64_t da = make_smem_desc(qa + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024);
-          const uint64_t db = make_smem_desc(ka + (k >> 2) * 8192 + (k & 3) * 32, 16, 1024);
-          umma_bf16(tmem_S + sb * AF_BN, da, db, idesc_s, k != 0);
-        }
+        const uint32_t klo = lo_k + ((k_base + st * kv_bytes) >> 4);
+#pragma unroll
+        for (int k = 0; k < MAXK; ++k)
+          if (k < ksteps) umma_bf16(tmem_S + sb * AF_BN, mk(hi_k, qlo[k]), mk(hi_k, klo + (k >> 2) * 512 + (k & 3) * 2), idesc_s, k != 0);
         umma_commit(S_FULL(sb));
         umma_commit(K_EMPTY(st));
       };
@@ -149,13 +160,9 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         mbar_wait(P_FULL, j & 1);
         mbar_wait(V_FULL(st), (j >> 1) & 1);
         tc_fence_after();
-        const uint32_t pa = smem_u32(sP), va = smem_u32(sV + st * kv_bytes);
+        const uint32_t vlo = lo_mn + ((v_base + st * kv_bytes) >> 4);
 #pragma unroll
-        for (int k = 0; k < AF_BN / 16; ++k) {
-          const uint64_t da = make_smem_desc(pa + k * 32, 16, 1024);
-          const uint64_t db = make_smem_desc(va + k * 2048, 8192, 1024);
-          umma_bf16(tmem_O, da, db, idesc_o, (j | k) != 0);
-        }
+        for (int k = 0; k < AF_BN / 16; ++k) umma_bf16(tmem_O, mk(hi_k, plo + k * 2), mk(hi_mn, vlo + k * 128), idesc_o, (j | k) != 0);
         umma_commit(V_EMPTY(st));
         umma_commit(O_READY);
       }

@@ -27,65 +27,80 @@ template <typename T> __device__ __forceinline__ T from_f32(float v);
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16(v); }
 
-template <typename FT, bool FOLD, bool ACC>
+template <typename FT, int P, bool FOLD, bool ACC>
 __global__ void __launch_bounds__(256)
-patchify_fold_kernel(FT* __restrict__ feat, __nv_bfloat16* __restrict__ tok, int B, int Cc, int H, int W, int p,
-                     long long tok_ld) {
+patchify_fold_kernel(FT* __restrict__ feat, __nv_bfloat16* __restrict__ tok, int B, int Cc, int H, int W, long long tok_ld) {
   __shared__ float tile[PF_TJ][PF_TK + 1];
-  const int gh = H / p, gw = W / p;
-  const int K = Cc * p * p;
+  constexpr int PP = P * P;
+  constexpr int WRUN = PF_TJ * P;  // contiguous elements along w per (c,u)
+  const int gh = H / P, gw = W / P;
+  const int K = Cc * PP;
   const int jt = (gw + PF_TJ - 1) / PF_TJ;
   int bid = blockIdx.x;
   const int j0 = (bid % jt) * PF_TJ; bid /= jt;
   const int i = bid % gh; bid /= gh;
   const int b = bid;
   const int k0 = blockIdx.y * PF_TK;
-  const int pp = p * p;
-  const int c0 = k0 / pp;          // PF_TK is a multiple of p*p for p in {1,2,4,8}
-  const int nc = PF_TK / pp;       // channels in this tile
-  const int wrun = PF_TJ * p;      // contiguous elements along w per (c,u)
+  const int c0 = k0 / PP;
   const long long row0 = (static_cast<long long>(b) * gh + i) * gw + j0;
-  const int total = PF_TJ * PF_TK;
+  constexpr int TOTAL = PF_TJ * PF_TK;
 
   if (!FOLD) {
-    for (int t = threadIdx.x; t < total; t += blockDim.x) {
-      const int wl = t % wrun;
-      const int cu = t / wrun;
-      const int u = cu % p, cl = cu / p;
-      const int jl = wl / p, v = wl - jl * p;
+#pragma unroll 4
+    for (int t = threadIdx.x; t < TOTAL; t += 256) {
+      const int wl = t % WRUN;
+      const int cu = t / WRUN;
+      const int u = cu % P, cl = cu / P;
+      const int jl = wl / P, v = wl % P;
       const int c = c0 + cl, j = j0 + jl;
       float x = 0.f;
-      if (c < Cc && j < gw) x = to_f32<FT>(feat[((static_cast<long long>(b) * Cc + c) * H + i * p + u) * W + j * p + v]);
-      tile[jl][cl * pp + u * p + v] = x;
+      if (c < Cc && j < gw) x = to_f32<FT>(feat[((static_cast<long long>(b) * Cc + c) * H + i * P + u) * W + j * P + v]);
+      tile[jl][cl * PP + u * P + v] = x;
     }
     __syncthreads();
-    for (int t = threadIdx.x; t < total; t += blockDim.x) {
-      const int kl = t % PF_TK, jl = t / PF_TK;
-      if (j0 + jl < gw && k0 + kl < K) tok[(row0 + jl) * tok_ld + k0 + kl] = __float2bfloat16(tile[jl][kl]);
+#pragma unroll 4
+    for (int t = threadIdx.x; t < TOTAL / 2; t += 256) {
+      const int kl = (t % (PF_TK / 2)) * 2, jl = t / (PF_TK / 2);
+      if (j0 + jl < gw && k0 + kl < K)
+        *reinterpret_cast<uint32_t*>(tok + (row0 + jl) * tok_ld + k0 + kl) = pack_bf16(tile[jl][kl], tile[jl][kl + 1]);
     }
   } else {
-    for (int t = threadIdx.x; t < total; t += blockDim.x) {
-      const int kl = t % PF_TK, jl = t / PF_TK;
-      float x = 0.f;
-      if (j0 + jl < gw && k0 + kl < K) x = __bfloat162float(tok[(row0 + jl) * tok_ld + k0 + kl]);
-      tile[jl][kl] = x;
+#pragma unroll 4
+    for (int t = threadIdx.x; t < TOTAL / 2; t += 256) {
+      const int kl = (t % (PF_TK / 2)) * 2, jl = t / (PF_TK / 2);
+      uint32_t q = 0;
+      if (j0 + jl < gw && k0 + kl < K) q = *reinterpret_cast<const uint32_t*>(tok + (row0 + jl) * tok_ld + k0 + kl);
+      tile[jl][kl] = bf16_lo(q);
+      tile[jl][kl + 1] = bf16_hi(q);
     }
     __syncthreads();
-    for (int t = threadIdx.x; t < total; t += blockDim.x) {
-      const int wl = t % wrun;
-      const int cu = t / wrun;
-      const int u = cu % p, cl = cu / p;
-      const int jl = wl / p, v = wl - jl * p;
+#pragma unroll 4
+    for (int t = threadIdx.x; t < TOTAL; t += 256) {
+      const int wl = t % WRUN;
+      const int cu = t / WRUN;
+      const int u = cu % P, cl = cu / P;
+      const int jl = wl / P, v = wl % P;
       const int c = c0 + cl, j = j0 + jl;
       if (c < Cc && j < gw) {
-        FT* dst = feat + ((static_cast<long long>(b) * Cc + c) * H + i * p + u) * W + j * p + v;
-        const float x = tile[jl][cl * pp + u * p + v];
+        FT* dst = feat + ((static_cast<long long>(b) * Cc + c) * H + i * P + u) * W + j * P + v;
+        const float x = tile[jl][cl * PP + u * P + v];
         if (ACC) *dst = from_f32<FT>(to_f32<FT>(*dst) + x);
         else *dst = from_f32<FT>(x);
       }
     }
   }
-  (void)nc;
+}
+
+template <typename FT, bool FOLD, bool ACC>
+static void launch_patchify_fold(FT* feat, __nv_bfloat16* tok, int B, int C, int H, int W, int p, long long tok_ld, cudaStream_t st) {
+  const int gh = H / p, gw = W / p, K = C * p * p;
+  dim3 grid(B * gh * ((gw + PF_TJ - 1) / PF_TJ), (K + PF_TK - 1) / PF_TK);
+  switch (p) {
+    case 1: patchify_fold_kernel<FT, 1, FOLD, ACC><<<grid, 256, 0, st>>>(feat, tok, B, C, H, W, tok_ld); break;
+    case 2: patchify_fold_kernel<FT, 2, FOLD, ACC><<<grid, 256, 0, st>>>(feat, tok, B, C, H, W, tok_ld); break;
+    case 4: patchify_fold_kernel<FT, 4, FOLD, ACC><<<grid, 256, 0, st>>>(feat, tok, B, C, H, W, tok_ld); break;
+    default: patchify_fold_kernel<FT, 8, FOLD, ACC><<<grid, 256, 0, st>>>(feat, tok, B, C, H, W, tok_ld); break;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -393,6 +408,15 @@ __global__ void cast_pad_kernel(const float* __restrict__ src, long long lds, __
   }
 }
 
+// contiguous, unpadded fast path: 8 elements per thread (2 x 128-bit loads, 1 x 128-bit store)
+__global__ void __launch_bounds__(256) cast_vec8_kernel(const float4* __restrict__ src, uint4* __restrict__ dst, long long nvec) {
+  for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < nvec;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 a = __ldg(src + 2 * t), b = __ldg(src + 2 * t + 1);
+    dst[t] = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+  }
+}
+
 __global__ void unpad_add_kernel(const float* __restrict__ src, long long lds, float* __restrict__ dst, long long ldd,
                                  int rows, int cols, int rin, int rout, int cin, int cout) {
   // dst is compact [rows, cols]; src is padded
@@ -479,15 +503,11 @@ extern "C" int xf_patchify(const void* feat, int feat_dtype, void* tok, int64_t 
                            xf_stream_t s) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(s);
   if (!feat || !tok) return fail(-1, "xf_patchify: null pointer");
-  if (p <= 0 || PF_TK % (p * p) != 0 || H % p || W % p) return fail(-2, "xf_patchify: unsupported patch %d for %dx%d", p, H, W);
-  const int gh = H / p, gw = W / p, K = C * p * p;
-  dim3 grid(B * gh * ((gw + PF_TJ - 1) / PF_TJ), (K + PF_TK - 1) / PF_TK);
-  if (feat_dtype == 1)
-    patchify_fold_kernel<float, false, false><<<grid, 256, 0, stream>>>(const_cast<float*>(reinterpret_cast<const float*>(feat)),
-                                                                        reinterpret_cast<__nv_bfloat16*>(tok), B, C, H, W, p, tok_ld);
-  else if (feat_dtype == 0)
-    patchify_fold_kernel<__nv_bfloat16, false, false><<<grid, 256, 0, stream>>>(
-        const_cast<__nv_bfloat16*>(reinterpret_cast<const __nv_bfloat16*>(feat)), reinterpret_cast<__nv_bfloat16*>(tok), B, C, H, W, p, tok_ld);
+  if (!(p == 1 || p == 2 || p == 4 || p == 8) || H % p || W % p) return fail(-2, "xf_patchify: unsupported patch %d for %dx%d", p, H, W);
+  if (tok_ld % 2 || (C * p * p) % 2) return fail(-4, "xf_patchify: token matrix width must be even");
+  __nv_bfloat16* t = reinterpret_cast<__nv_bfloat16*>(tok);
+  if (feat_dtype == 1) launch_patchify_fold<float, false, false>(const_cast<float*>(reinterpret_cast<const float*>(feat)), t, B, C, H, W, p, tok_ld, stream);
+  else if (feat_dtype == 0) launch_patchify_fold<__nv_bfloat16, false, false>(const_cast<__nv_bfloat16*>(reinterpret_cast<const __nv_bfloat16*>(feat)), t, B, C, H, W, p, tok_ld, stream);
   else return fail(-3, "xf_patchify: bad dtype");
   g_launches.fetch_add(1);
   XF_CUDA(cudaGetLastError());
@@ -498,16 +518,15 @@ extern "C" int xf_fold(const void* tok, int64_t tok_ld, void* feat, int feat_dty
                        int p, xf_stream_t s) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(s);
   if (!feat || !tok) return fail(-1, "xf_fold: null pointer");
-  if (p <= 0 || PF_TK % (p * p) != 0 || H % p || W % p) return fail(-2, "xf_fold: unsupported patch %d for %dx%d", p, H, W);
-  const int gh = H / p, gw = W / p, K = C * p * p;
-  dim3 grid(B * gh * ((gw + PF_TJ - 1) / PF_TJ), (K + PF_TK - 1) / PF_TK);
+  if (!(p == 1 || p == 2 || p == 4 || p == 8) || H % p || W % p) return fail(-2, "xf_fold: unsupported patch %d for %dx%d", p, H, W);
+  if (tok_ld % 2 || (C * p * p) % 2) return fail(-4, "xf_fold: token matrix width must be even");
   __nv_bfloat16* t = const_cast<__nv_bfloat16*>(reinterpret_cast<const __nv_bfloat16*>(tok));
   if (feat_dtype == 1) {
-    if (accumulate) patchify_fold_kernel<float, true, true><<<grid, 256, 0, stream>>>(reinterpret_cast<float*>(feat), t, B, C, H, W, p, tok_ld);
-    else patchify_fold_kernel<float, true, false><<<grid, 256, 0, stream>>>(reinterpret_cast<float*>(feat), t, B, C, H, W, p, tok_ld);
+    if (accumulate) launch_patchify_fold<float, true, true>(reinterpret_cast<float*>(feat), t, B, C, H, W, p, tok_ld, stream);
+    else launch_patchify_fold<float, true, false>(reinterpret_cast<float*>(feat), t, B, C, H, W, p, tok_ld, stream);
   } else if (feat_dtype == 0) {
-    if (accumulate) patchify_fold_kernel<__nv_bfloat16, true, true><<<grid, 256, 0, stream>>>(reinterpret_cast<__nv_bfloat16*>(feat), t, B, C, H, W, p, tok_ld);
-    else patchify_fold_kernel<__nv_bfloat16, true, false><<<grid, 256, 0, stream>>>(reinterpret_cast<__nv_bfloat16*>(feat), t, B, C, H, W, p, tok_ld);
+    if (accumulate) launch_patchify_fold<__nv_bfloat16, true, true>(reinterpret_cast<__nv_bfloat16*>(feat), t, B, C, H, W, p, tok_ld, stream);
+    else launch_patchify_fold<__nv_bfloat16, true, false>(reinterpret_cast<__nv_bfloat16*>(feat), t, B, C, H, W, p, tok_ld, stream);
   } else return fail(-3, "xf_fold: bad dtype");
   g_launches.fetch_add(1);
   XF_CUDA(cudaGetLastError());
@@ -625,6 +644,15 @@ extern "C" int xf_cast_pad(const float* src, int64_t lds, void* dst, int64_t ldd
                            int cout, xf_stream_t s) {
   if (!src || !dst) return fail(-1, "xf_cast_pad: null pointer");
   if (rows == 0 || cols == 0) return 0;
+  const long long total = static_cast<long long>(rows) * cols;
+  if (rin == 0 && cin == 0 && lds == cols && ldd == cols && total % 8 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    cast_vec8_kernel<<<grid_for(total / 8, 256), 256, 0, reinterpret_cast<cudaStream_t>(s)>>>(
+        reinterpret_cast<const float4*>(src), reinterpret_cast<uint4*>(dst), total / 8);
+    g_launches.fetch_add(1);
+    XF_CUDA(cudaGetLastError());
+    return 0;
+  }
   cast_pad_kernel<<<grid_for(static_cast<long long>(rows) * cols, 256 * 4), 256, 0, reinterpret_cast<cudaStream_t>(s)>>>(
       src, lds, reinterpret_cast<__nv_bfloat16*>(dst), ldd, rows, cols, rin, rout, cin, cout);
   g_launches.fetch_add(1);

@@ -2,8 +2,8 @@
 //
 //   D[M,N] (+)= A(M x K) * B(N x K)^T,  bf16 operands, fp32 accumulation in TMEM.
 //
-// CTA = 192 threads: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2..5 =
-// epilogue (one TMEM lane quadrant each).  Tile = 128 x tile_n x 64; operands are staged by TMA
+// CTA = 320 threads: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2..9 =
+// epilogue (two warps per TMEM lane quadrant, alternating 32-column chunks).  Tile = 128 x tile_n x 64; operands are staged by TMA
 // into a ring of SWIZZLE_128B shared-memory stages; tcgen05.mma (M=128, N=tile_n, K=16) reads them
 // through shared-memory descriptors in either K-major or MN-major form, so forward (x W^T), dgrad
 // (dy W) and wgrad (dy^T x) all run on the same kernel without materialised transposes.  The
@@ -25,7 +25,8 @@ namespace xf {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_EPI_WARPS = 8;   // two warps per TMEM lane quadrant, each takes every other 32-column chunk
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
 constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
 constexpr int GEMM_SMEM_BUDGET = 200 * 1024;         // stage ring budget
 
@@ -203,6 +204,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int m, int n
   }
 }
 
+// CG = 1: one CTA per 128 x tile_n tile.  CG = 2: a CTA pair (cluster of 2) per 256 x tile_n tile with
+// tcgen05.mma.cta_group::2 — each CTA stages its own 128 rows of A and tile_n/2 rows (columns of D) of
+// B, which halves the L2 -> SMEM operand traffic per FLOP (the 1-CTA tile is L2-bandwidth bound).
+template <int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const __grid_constant__ GemmParams p) {
@@ -215,6 +220,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;   // CTA rank inside the pair
+  const bool leader = rank == 0;
   const uint32_t bar_base = smem_u32(bars);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (8 + s); };
@@ -230,62 +237,80 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);
+      mbar_init(tempty_bar(s), GEMM_EPI_WARPS * CG);
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(tmem_ptr_smem), 512);
-    tmem_relinquish();
+    if (CG == 2) { tmem_alloc_cg2(smem_u32(tmem_ptr_smem), 512); tmem_relinquish_cg2(); }
+    else { tmem_alloc(smem_u32(tmem_ptr_smem), 512); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  const int num_items = p.num_m_tiles * p.num_n_tiles * p.split_k;
+  const int num_items = p.num_m_tiles * p.num_n_tiles * p.split_k;   // m-tiles are 128*CG rows tall
+  const int first_item = blockIdx.x / CG, item_stride = gridDim.x / CG;
+  const int cta_b_rows = p.tile_n / CG;                              // B rows (D columns) staged by this CTA
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (every CTA) =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      for (int item = first_item; item < num_items; item += item_stride) {
         int mt, nt, kb0, nkb;
         decode_item(p, item, mt, nt, kb0, nkb);
-        const int m0 = mt * GEMM_BM, n0 = nt * p.tile_n;
+        const int m0 = mt * GEMM_BM * CG + rank * GEMM_BM;
+        const int n0 = nt * p.tile_n + rank * cta_b_rows;
         for (int kb = 0; kb < nkb; ++kb) {
           const int k0 = (kb0 + kb) * GEMM_BK;
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_u32(ring + stage * p.stage_bytes);
           const uint32_t sb = sa + GEMM_A_BYTES;
-          mbar_expect_tx(full_bar(stage), GEMM_A_BYTES + p.b_bytes);
-          if (!p.a_mn) {
-            tma_load_2d(sa, &tmap_a, full_bar(stage), k0, m0);
+          const uint32_t fb = full_bar(stage);
+          if (leader) mbar_expect_tx(fb, CG * (GEMM_A_BYTES + p.b_bytes));
+          if (CG == 2) {
+            if (!p.a_mn) {
+              tma_load_2d_cg2(sa, &tmap_a, fb, k0, m0);
+            } else {
+              tma_load_2d_cg2(sa, &tmap_a, fb, m0, k0);
+              tma_load_2d_cg2(sa + 8192, &tmap_a, fb, m0 + 64, k0);
+            }
+            if (!p.b_mn) {
+              tma_load_2d_cg2(sb, &tmap_b, fb, k0, n0);
+            } else {
+              for (int c = 0; c * 64 < cta_b_rows; ++c) tma_load_2d_cg2(sb + c * 8192, &tmap_b, fb, n0 + c * 64, k0);
+            }
           } else {
-            tma_load_2d(sa, &tmap_a, full_bar(stage), m0, k0);
-            tma_load_2d(sa + 8192, &tmap_a, full_bar(stage), m0 + 64, k0);
-          }
-          if (!p.b_mn) {
-            tma_load_2d(sb, &tmap_b, full_bar(stage), k0, n0);
-          } else {
-            for (int c = 0; c * 64 < p.tile_n; ++c) tma_load_2d(sb + c * 8192, &tmap_b, full_bar(stage), n0 + c * 64, k0);
+            if (!p.a_mn) {
+              tma_load_2d(sa, &tmap_a, fb, k0, m0);
+            } else {
+              tma_load_2d(sa, &tmap_a, fb, m0, k0);
+              tma_load_2d(sa + 8192, &tmap_a, fb, m0 + 64, k0);
+            }
+            if (!p.b_mn) {
+              tma_load_2d(sb, &tmap_b, fb, k0, n0);
+            } else {
+              for (int c = 0; c * 64 < cta_b_rows; ++c) tma_load_2d(sb + c * 8192, &tmap_b, fb, n0 + c * 64, k0);
+            }
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(p.tile_n, p.a_mn, p.b_mn);
+    // ===================== MMA issuer (even CTA of the pair only) =====================
+    if (lane == 0 && leader) {
+      const uint32_t idesc = make_idesc_bf16(p.tile_n, p.a_mn, p.b_mn, 128 * CG);
       const uint32_t a_lbo = p.a_mn ? 8192u : 16u, b_lbo = p.b_mn ? 8192u : 16u;
       const uint32_t a_kstep = p.a_mn ? 2048u : 32u, b_kstep = p.b_mn ? 2048u : 32u;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      for (int item = first_item; item < num_items; item += item_stride) {
         int mt, nt, kb0, nkb;
         decode_item(p, item, mt, nt, kb0, nkb);
         if (nkb == 0) continue;
@@ -301,50 +326,63 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             const uint64_t da = make_smem_desc(sa + k * a_kstep, a_lbo, 1024);
             const uint64_t db = make_smem_desc(sb + k * b_kstep, b_lbo, 1024);
-            umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
+            if (CG == 2) umma_bf16_cg2(d_tmem, da, db, idesc, (kb | k) != 0);
+            else umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
           }
-          umma_commit(empty_bar(stage));
+          if (CG == 2) umma_commit_cg2_mc(empty_bar(stage), 0x3); else umma_commit(empty_bar(stage));
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(tfull_bar(acc));
+        if (CG == 2) umma_commit_cg2_mc(tfull_bar(acc), 0x3); else umma_commit(tfull_bar(acc));
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
-    // ===================== epilogue warps =====================
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    // ===================== epilogue warps (every CTA: its own 128 accumulator rows) =====================
+    const int quad = warp & 3;            // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;     // which of the two warps of the quadrant: takes chunks half, half+2, ...
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+    for (int item = first_item; item < num_items; item += item_stride) {
       int mt, nt, kb0, nkb;
       decode_item(p, item, mt, nt, kb0, nkb);
       if (nkb == 0) continue;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int m = mt * GEMM_BM + quad * 32 + lane;
+      const int m = mt * GEMM_BM * CG + rank * GEMM_BM + quad * 32 + lane;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * p.tile_n;
-      for (int c = 0; c < p.tile_n; c += 32) {
+      bool released = false;
+      for (int c = half * 32; c < p.tile_n; c += 64) {
         uint32_t r[32];
         tmem_ld32(t_row + c, r);
         tmem_ld_wait();
-        if (c + 32 >= p.tile_n) {
-          // whole accumulator is in registers: hand the TMEM stage back to the MMA warp
+        if (c + 64 >= p.tile_n) {
+          // this warp's share of the accumulator is in registers: hand the TMEM stage back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(acc));
+          if (lane == 0) {
+            if (CG == 2) mbar_arrive_even_cta(tempty_bar(acc)); else mbar_arrive(tempty_bar(acc));
+          }
+          released = true;
         }
         const int n0 = nt * p.tile_n + c;
         if (n0 < p.N) epilogue_chunk(p, m, n0, r);
+      }
+      if (!released) {  // tile_n == 32: the second warp of the quadrant has no chunk
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_even_cta(tempty_bar(acc)); else mbar_arrive(tempty_bar(acc));
+        }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (CG == 2) tmem_dealloc_cg2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -377,20 +415,26 @@ extern "C" int xf_gemm(const XfGemm* g, xf_stream_t stream_) {
   if (g->accumulate && g->out_dtype != 1) return fail(-5, "xf_gemm: accumulate needs fp32 output");
   if (g->drop_p < 0.f || g->drop_p >= 1.f) return fail(-6, "xf_gemm: drop_p out of range");
 
+  // CTA pairs (cta_group::2) unless disabled or the problem is a single small tile
+  int cg = g->cta_group == 1 ? 1 : 2;
+  if (g->cta_group == 0 && g->M <= 128) cg = 1;
+  if (cg == 2 && (tile_n % 32 != 0 || (tile_n / 2) % 8 != 0)) cg = 1;
+
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.M = (int)g->M; p.N = (int)g->N; p.K = (int)g->K;
   p.tile_n = tile_n;
   p.a_mn = g->a_mn_major ? 1 : 0;
   p.b_mn = g->b_mn_major ? 1 : 0;
-  p.num_m_tiles = (p.M + GEMM_BM - 1) / GEMM_BM;
+  p.num_m_tiles = (p.M + GEMM_BM * cg - 1) / (GEMM_BM * cg);
   p.num_n_tiles = (p.N + tile_n - 1) / tile_n;
   p.total_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
   if (split_k > p.total_kb) split_k = p.total_kb;
   p.kb_per_split = (p.total_kb + split_k - 1) / split_k;
   split_k = (p.total_kb + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
   p.split_k = split_k;
-  p.b_bytes = p.b_mn ? ((tile_n + 63) / 64) * 8192 : tile_n * 128;
+  const int cta_b_rows = tile_n / cg;
+  p.b_bytes = p.b_mn ? ((cta_b_rows + 63) / 64) * 8192 : cta_b_rows * 128;   // per CTA
   p.stage_bytes = GEMM_A_BYTES + ((p.b_bytes + 1023) / 1024) * 1024;
   p.stages = GEMM_SMEM_BUDGET / p.stage_bytes;
   if (p.stages > 8) p.stages = 8;
@@ -420,26 +464,46 @@ extern "C" int xf_gemm(const XfGemm* g, xf_stream_t stream_) {
   p.drop_thresh = drop_thresh16(g->drop_p);
   if (g->drop_p > 0.f && (g->ldc % 2)) return fail(-7, "xf_gemm: dropout needs an even ldc");
   p.drop_scale = g->drop_p > 0.f ? 1.0f / (1.0f - g->drop_p) : 1.0f;
+  if (split_k > 1 && (g->bias || g->pos_table || g->act || g->dact_in || g->residual || g->drop_p > 0.f))
+    return fail(-8, "xf_gemm: split_k cannot be combined with a non-linear / additive epilogue");
 
   CUtensorMap ta, tb;
   int rc;
   if (!p.a_mn) rc = make_tmap_2d_bf16(&ta, g->a, p.M, p.K, g->a_ld, 64, 128);
   else         rc = make_tmap_2d_bf16(&ta, g->a, p.K, p.M, g->a_ld, 64, 64);
   if (rc) return rc;
-  if (!p.b_mn) rc = make_tmap_2d_bf16(&tb, g->b, p.N, p.K, g->b_ld, 64, tile_n);
+  if (!p.b_mn) rc = make_tmap_2d_bf16(&tb, g->b, p.N, p.K, g->b_ld, 64, cta_b_rows);
   else         rc = make_tmap_2d_bf16(&tb, g->b, p.K, p.N, g->b_ld, 64, 64);
   if (rc) return rc;
 
   const int smem_bytes = 1024 /*align slack*/ + 1024 /*control*/ + p.stages * p.stage_bytes;
   static bool attr_set = false;
   if (!attr_set) {
-    XF_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    XF_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    XF_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   const int items = p.num_m_tiles * p.num_n_tiles * p.split_k;
-  int ctas = g->max_ctas > 0 ? g->max_ctas : sm_count();
-  if (ctas > items) ctas = items;
-  gemm_bf16_tcgen05_kernel<<<ctas, GEMM_THREADS, smem_bytes, stream>>>(ta, tb, p);
+  int sms = g->max_ctas > 0 ? g->max_ctas : sm_count();
+  if (cg == 1) {
+    int ctas = sms < items ? sms : items;
+    gemm_bf16_tcgen05_kernel<1><<<ctas, GEMM_THREADS, smem_bytes, stream>>>(ta, tb, p);
+  } else {
+    int clusters = sms / 2 < items ? sms / 2 : items;
+    if (clusters < 1) clusters = 1;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    XF_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<2>, ta, tb, p));
+  }
   g_launches.fetch_add(1);
   XF_CUDA(cudaGetLastError());
   return 0;

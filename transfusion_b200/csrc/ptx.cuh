@@ -83,6 +83,54 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint
       : "memory");
 }
 
+// ---------------------------------------------------------------- 2-CTA (cta_group::2) variants
+// A CTA pair (cluster of 2 on one TPC) runs one M=256 MMA: each CTA stages its own 128 rows of A and
+// half of the B tile; the even CTA issues the MMA and both CTAs' barriers are signalled by multicast.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> even CTA
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose completion bytes are credited to the EVEN CTA's mbarrier (same smem offset)
+__device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_even_cta(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_cg2() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_cg2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the mbarrier at this smem offset in every CTA of cta_mask once the prior MMAs completed
+__device__ __forceinline__ void umma_commit_cg2_mc(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(cta_mask) : "memory");
+}
+
 // ---------------------------------------------------------------- TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols)
@@ -174,7 +222,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 }
 
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32, M = 128 (cute::UMMA::InstrDescriptor).
-__host__ __device__ __forceinline__ uint32_t make_idesc_bf16(uint32_t n, uint32_t a_mn_major, uint32_t b_mn_major) {
+__host__ __device__ __forceinline__ uint32_t make_idesc_bf16(uint32_t n, uint32_t a_mn_major, uint32_t b_mn_major,
+                                                             uint32_t m = 128) {
   uint32_t d = 0;
   d |= 1u << 4;                  // D format F32
   d |= 1u << 7;                  // A format BF16
@@ -182,7 +231,7 @@ __host__ __device__ __forceinline__ uint32_t make_idesc_bf16(uint32_t n, uint32_
   d |= (a_mn_major & 1u) << 15;  // A major: 0 = K, 1 = MN
   d |= (b_mn_major & 1u) << 16;  // B major
   d |= ((n >> 3) & 0x3F) << 17;  // N >> 3
-  d |= (128u >> 4) << 24;        // M >> 4
+  d |= (m >> 4) << 24;           // M >> 4 (128, or 256 with cta_group::2)
   return d;
 }
 
@@ -194,13 +243,28 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
-__device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-  const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+// erf via Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7, far below bf16 resolution): one ex2 + one rcp
+// instead of the ~30-instruction erff; e = exp(-z^2) is returned for reuse (GELU' needs the same term).
+__device__ __forceinline__ float fast_erf_pos(float z, float& e) {  // z >= 0
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  e = __expf(-z * z);
+  return 1.0f - poly * t * e;
 }
-
+__device__ __forceinline__ float gelu_erf(float x) {
+  float e;
+  const float er = fast_erf_pos(fabsf(x) * 0.70710678118654752f, e);
+  return 0.5f * x * (1.0f + copysignf(er, x));
+}
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  float e;  // e = exp(-x^2/2)
+  const float er = fast_erf_pos(fabsf(x) * 0.70710678118654752f, e);
+  const float cdf = 0.5f * (1.0f + copysignf(er, x));
+  return fmaf(x * 0.39894228040143268f, e, cdf);
+}
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

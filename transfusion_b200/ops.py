@@ -11,6 +11,10 @@ from . import _lib
 from ._lib import XfAttnBwd, XfAttnFwd, XfGemm, XfLayerNorm, XfLayerNormBwd, check, lib
 
 
+# GEMM tiling default: 0 = library default (CTA pairs), 1 = single-CTA tiles (XF_GEMM_CTA_GROUP env var)
+import os as _os
+DEFAULT_CTA_GROUP = int(_os.environ.get("XF_GEMM_CTA_GROUP", "0"))
+
 # When set to a list, every op appends (family, algorithmic flops, algorithmic bytes, start event, end event):
 # bench.py's per-kernel roofline pass (CUDA events on the launching stream).
 PROFILE = None
@@ -59,7 +63,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
          act: int = 0, preact_out: Optional[torch.Tensor] = None, dact_in: Optional[torch.Tensor] = None,
          residual: Optional[torch.Tensor] = None, accumulate: bool = False, split_k: int = 1,
          tile_n: int = 0, drop_p: float = 0.0, drop_seed: int = 0, drop_stream: int = 0,
-         drop_first: bool = False, max_ctas: int = 0) -> torch.Tensor:
+         drop_first: bool = False, max_ctas: int = 0, cta_group: int = 0) -> torch.Tensor:
     """out[M,N] (+)= A(MxK) @ B(NxK)^T with the fused epilogue of include/xfusion.h:XfGemm.
     a / b / out / residual are 2-D row-major (last stride 1); leading dims come from stride(0)."""
     _req(a, torch.bfloat16, "a")
@@ -97,6 +101,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     g.accumulate = int(accumulate)
     g.drop_p, g.drop_seed, g.drop_stream, g.drop_first = drop_p, drop_seed, drop_stream, int(drop_first)
     g.max_ctas = max_ctas
+    g.cta_group = cta_group if cta_group else DEFAULT_CTA_GROUP
     fam = "gemm_wgrad" if a_mn_major else ("gemm_dgrad" if b_mn_major else "gemm_fwd")
     with _Prof(fam, 2.0 * M * N * K):
         check(lib().xf_gemm(C.byref(g), _stream()), "xf_gemm")
@@ -237,8 +242,8 @@ def attn_fwd(q, k, v, out, lse, *, B: int, H: int, Sq: int, Sk: int, dp: int, sc
 
 
 def attn_bwd(q, k, v, d_out, lse, delta, dq, dk, dv, *, B: int, H: int, Sq: int, Sk: int, dp: int, scale: float,
-             key_padding_mask: Optional[torch.Tensor] = None, drop_p: float = 0.0, drop_seed: int = 0,
-             drop_stream: int = 0):
+             key_padding_mask: Optional[torch.Tensor] = None, kpm_start: int = 0, drop_p: float = 0.0,
+             drop_seed: int = 0, drop_stream: int = 0):
     a = XfAttnBwd()
     a.q, a.ldq = q.data_ptr(), q.stride(0)
     a.k, a.ldk = k.data_ptr(), k.stride(0)
@@ -252,6 +257,7 @@ def attn_bwd(q, k, v, d_out, lse, delta, dq, dk, dv, *, B: int, H: int, Sq: int,
     a.dv, a.lddv = dv.data_ptr(), dv.stride(0)
     if key_padding_mask is not None:
         a.key_padding_mask = key_padding_mask.data_ptr()
+    a.kpm_start = kpm_start
     a.B, a.H, a.Sq, a.Sk, a.dp = B, H, Sq, Sk, dp
     a.scale = scale
     a.drop_p, a.drop_seed, a.drop_stream = drop_p, drop_seed, drop_stream
