@@ -186,6 +186,7 @@ typedef struct XfAttnBwd {
   int32_t B, H, Sq, Sk, dp;
   float scale;
   float drop_p; uint32_t drop_seed, drop_stream;   /* must equal the forward's */
+  void* debug_timeline;                            /* dev aid: NULL, or int64[2][2][64][8] device buffer of clock64 stamps */
 } XfAttnBwd;
 int xf_attn_bwd(const XfAttnBwd* a, xf_stream_t stream);
 

@@ -379,6 +379,44 @@ def drop_debug2():
         print("  at", r, c, "out", float(out[r, c]), "ref", float(ref[r, c]), "out2", float(out2[r, c]))
 
 
+def bwd_timeline(drop=0.15):
+    import math
+    B, H, S, d = 13, 4, 3136, 224
+    dev = "cuda"
+    torch.manual_seed(0)
+    qkv = torch.randn(B * S, 3 * H * d, device=dev).bfloat16()
+    D = H * d
+    Sp = (S + 127) // 128 * 128
+    out = torch.empty(B * S, D, device=dev, dtype=torch.bfloat16)
+    lse = torch.empty(B, H, Sp, device=dev)
+    kpm = torch.zeros(B, S, dtype=torch.uint8, device=dev); kpm[:, S - 20:] = 1
+    kw = dict(B=B, H=H, Sq=S, Sk=S, dp=d, scale=1 / math.sqrt(d), drop_p=drop, drop_seed=3, drop_stream=4)
+    ops.attn_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], out, lse, key_padding_mask=kpm, kpm_start=S - 64, **kw)
+    dout = torch.randn(B * S, D, device=dev).bfloat16()
+    delta = torch.empty(B, H, Sp, device=dev)
+    ops.attn_delta(out, dout, delta, B, S, H, d)
+    dqkv = torch.empty(B * S, 3 * D, device=dev, dtype=torch.bfloat16)
+    dbg = torch.zeros(2, 2, 64, 8, dtype=torch.int64, device=dev)
+    for it in range(2):
+        ops.attn_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], dout, lse, delta, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:],
+                     key_padding_mask=kpm, kpm_start=S - 64, debug_timeline=dbg, **kw)
+    torch.cuda.synchronize()
+    t = dbg.cpu()
+    for pi, pname in enumerate(("dQ pass", "dKV pass")):
+        mma, sm = t[pi, 0], t[pi, 1]
+        t0 = int(mma[8, 0])
+        print(f"--- {pname} drop={drop}: iteration period (MMA thread) cycles:", [int(mma[i + 1, 0] - mma[i, 0]) for i in range(8, 24)])
+        print("MMA thread per-iter deltas [T_FULL wait, C_EMPTY wait, issue C, (E_FULL wait), issue acc] (iters 10..17):")
+        for i in range(10, 18):
+            r = mma[i]
+            print("   ", int(r[1] - r[0]), int(r[2] - r[1]), int(r[3] - r[2]), int(r[4] - r[3]), int(r[5] - r[4]))
+        print("softmax warp2 per-iter deltas [C_FULL wait, tmem ld+release, compute, E_EMPTY wait, st+fence+arrive]:")
+        for i in range(10, 18):
+            r = sm[i]
+            print("   ", int(r[1] - r[0]), int(r[2] - r[1]), int(r[3] - r[2]), int(r[4] - r[3]), int(r[5] - r[4]), " period", int(sm[i + 1, 0] - r[0]))
+
+
+CASES["bwd_timeline"] = lambda: (bwd_timeline(0.15), bwd_timeline(0.0))
 CASES["drop_debug2"] = drop_debug2
 CASES["drop_debug"] = drop_debug
 

@@ -46,9 +46,12 @@ struct AttnBwdParams {
   __nv_bfloat16* out1; long long ld1;  // DKV: dv
   float drop_p, drop_scale;
   uint32_t drop_seed, drop_stream, drop_thresh;
+  long long* dbg;  // dev aid: per-iteration clock64() stamps of CTA 0 (null in production)
 };
 
-template <bool DKV>
+#define AB_STAMP(role, i, ev) do { if (p.dbg && blockIdx.x == 0 && (i) < 64) p.dbg[((role) * 64 + (i)) * 8 + (ev)] = clock64(); } while (0)
+
+template <bool DKV, bool DROP>
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_constant__ CUtensorMap tmap_r2,
                         const __grid_constant__ CUtensorMap tmap_t1, const __grid_constant__ CUtensorMap tmap_t2,
@@ -127,60 +130,48 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gri
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // The score MMAs are N = 32 (16 tensor-pipe cycles each), so this thread has to issue one every few
-      // cycles: all shared-memory descriptors are built once (only the low word varies: start address),
-      // the loop body is an add + the MMA.
+      // The score MMAs are N = 32: the tensor pipe retires one every ~46 cycles (measured), so this thread
+      // must issue them with a handful of instructions each: descriptors are built once (only the
+      // start-address word varies) and each 32-column chunk (2 k-steps) is one asm block.
       const uint32_t idesc_c = make_idesc_bf16(AB_BN, 0, 0);
       const uint32_t idesc_acc = make_idesc_bf16(p.dp, 0, 1);
-      const int ksteps = p.dp / 16;
-      const uint32_t r1a = smem_u32(sR1), r2a = smem_u32(sR2), e1a = smem_u32(sE1), e2a = smem_u32(sE2);
+      const int nch = p.nch;
       const uint64_t dk = make_smem_desc(0, 16, 512, SW64);      // K-major template (start = 0)
       const uint64_t dmn = make_smem_desc(0, 2048, 512, SW64);   // MN-major template
-      const uint32_t hi_k = static_cast<uint32_t>(dk >> 32), hi_mn = static_cast<uint32_t>(dmn >> 32);
-      const uint32_t lo_k = static_cast<uint32_t>(dk), lo_mn = static_cast<uint32_t>(dmn);
-      auto mk = [](uint32_t hi, uint32_t lo) { return (static_cast<uint64_t>(hi) << 32) | lo; };
-      constexpr int MAXK = 14;  // dp <= 224
-      uint32_t r1lo[MAXK], r2lo[MAXK];
-#pragma unroll
-      for (int kk = 0; kk < MAXK; ++kk) {
-        const uint32_t off = (kk >> 1) * 8192 + (kk & 1) * 32;
-        r1lo[kk] = lo_k + ((r1a + off) >> 4);
-        r2lo[kk] = lo_k + ((r2a + off) >> 4);
-      }
-      const uint32_t e1lo = lo_k + (e1a >> 4), e2lo = lo_k + (e2a >> 4);
-      const uint32_t t_base = smem_u32(sT);
+      const uint32_t hi_k = desc_hi(dk), hi_mn = desc_hi(dmn), lo_k = desc_lo(dk), lo_mn = desc_lo(dmn);
+      const uint32_t r1lo = lo_k + (smem_u32(sR1) >> 4), r2lo = lo_k + (smem_u32(sR2) >> 4);
+      const uint32_t e1lo = lo_k + (smem_u32(sE1) >> 4), e2lo = lo_k + (smem_u32(sE2) >> 4);
+      const uint32_t t_base = smem_u32(sT) >> 4, t_lo = t_bytes >> 4;
       auto do_acc = [&](int i) {
         const int st = i % AB_STAGES;
-        const uint32_t t1s = (t_base + st * 2 * t_bytes) >> 4, t2s = t1s + (t_bytes >> 4);
+        const uint32_t t1s = t_base + st * 2 * t_lo, t2s = t1s + t_lo;
         mbar_wait(E_FULL, i & 1);
+        AB_STAMP(0, i + 1, 4);
         tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < AB_BN / 16; ++k)
-          umma_bf16(tmem_acc2, mk(hi_k, e2lo + k * 2), mk(hi_mn, lo_mn + t1s + k * 64), idesc_acc, (i | k) != 0);
-        if (DKV) {
-#pragma unroll
-          for (int k = 0; k < AB_BN / 16; ++k)
-            umma_bf16(tmem_acc1, mk(hi_k, e1lo + k * 2), mk(hi_mn, lo_mn + t2s + k * 64), idesc_acc, (i | k) != 0);
-        }
+        umma_k2(tmem_acc2, hi_k, e2lo, 2, hi_mn, lo_mn + t1s, 64, idesc_acc, i != 0);
+        if (DKV) umma_k2(tmem_acc1, hi_k, e1lo, 2, hi_mn, lo_mn + t2s, 64, idesc_acc, i != 0);
         umma_commit(T_EMPTY(st));
         umma_commit(E_EMPTY);
       };
       mbar_wait(R_FULL, 0);
       for (int i = 0; i < n; ++i) {
         const int st = i % AB_STAGES, cb = i % p.ncbuf;
+        AB_STAMP(0, i, 0);
         mbar_wait(T_FULL(st), (i / AB_STAGES) & 1);
+        AB_STAMP(0, i, 1);
         mbar_wait(C_EMPTY(cb), ((i / p.ncbuf) & 1) ^ 1);
+        AB_STAMP(0, i, 2);
         tc_fence_after();
-        const uint32_t t1s = lo_k + ((t_base + st * 2 * t_bytes) >> 4), t2s = t1s + (t_bytes >> 4);
+        const uint32_t t1s = lo_k + t_base + st * 2 * t_lo, t2s = t1s + t_lo;
         const uint32_t c1 = tmem_C + cb * 64, c2 = c1 + 32;
-#pragma unroll
-        for (int kk = 0; kk < MAXK; ++kk)
-          if (kk < ksteps) umma_bf16(c1, mk(hi_k, r1lo[kk]), mk(hi_k, t1s + (kk >> 1) * 128 + (kk & 1) * 2), idesc_c, kk != 0);
-#pragma unroll
-        for (int kk = 0; kk < MAXK; ++kk)
-          if (kk < ksteps) umma_bf16(c2, mk(hi_k, r2lo[kk]), mk(hi_k, t2s + (kk >> 1) * 128 + (kk & 1) * 2), idesc_c, kk != 0);
+        for (int ch = 0; ch < nch; ++ch) {   // resident chunks are 8192 B apart, streamed chunks 2048 B
+          umma_k2(c1, hi_k, r1lo + ch * 512, 2, hi_k, t1s + ch * 128, 2, idesc_c, ch != 0);
+          umma_k2(c2, hi_k, r2lo + ch * 512, 2, hi_k, t2s + ch * 128, 2, idesc_c, ch != 0);
+        }
         umma_commit(C_FULL(cb));
+        AB_STAMP(0, i, 3);
         if (i >= 1) do_acc(i - 1);
+        AB_STAMP(0, i, 5);
       }
       do_acc(n - 1);
       umma_commit(ACC_DONE);
@@ -203,13 +194,20 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gri
     const uint32_t swz = (static_cast<uint32_t>(r) >> 1) & 3u;
     uint8_t* e1row = sE1 + r * 64;
     uint8_t* e2row = sE2 + r * 64;
+    // dropout: decision(row = (b,h,q), col = key).  dQ pass: this thread's row hash is constant, one hash per key
+    // pair.  dK/dV pass: this thread's key is constant (half-word select + pair term), the 32 row hashes of the
+    // streamed queries are computed by the 32 lanes once per iteration and broadcast with shuffles.
+    const uint32_t rh_row = DROP && !DKV ? drop_rowhash(p.drop_seed, bh * p.Sq + row_g) : 0u;
+    const uint32_t colterm = (static_cast<uint32_t>(row_g) >> 1) * 0x9E3779B9U;
+    const uint32_t colshift = (row_g & 1) * 16;
+    const float sc = p.scale;
 
     for (int i = 0; i < n; ++i) {
       const int cb = i % p.ncbuf;
       const int t0 = i * AB_BN;
       // global-memory operands of this iteration are requested BEFORE waiting on the MMA so their
       // latency hides behind it: key-padding bits (dQ pass) / per-query LSE and delta (dK/dV pass)
-      uint32_t badbits = 0;
+      uint32_t badbits = 0, rh_lane = 0;
       float ls[32], ds[32];
       if (!DKV) {
         const int key = t0 + lane;
@@ -226,8 +224,13 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gri
           ls[4 * c4] = L.x; ls[4 * c4 + 1] = L.y; ls[4 * c4 + 2] = L.z; ls[4 * c4 + 3] = L.w;
           ds[4 * c4] = Dl.x; ds[4 * c4 + 1] = Dl.y; ds[4 * c4 + 2] = Dl.z; ds[4 * c4 + 3] = Dl.w;
         }
+        if (DROP) rh_lane = drop_rowhash(p.drop_seed, bh * p.Sq + (t0 + lane));
+        const int qvalid = p.Sq - t0;   // columns >= qvalid are beyond the sequence
+        badbits = (!row_valid) ? 0xffffffffu : (qvalid >= 32 ? 0u : (0xffffffffu << (qvalid < 0 ? 0 : qvalid)));
       }
+      if (warp == 2 && lane == 0) AB_STAMP(1, i, 0);
       mbar_wait(C_FULL(cb), (i / p.ncbuf) & 1);
+      if (warp == 2 && lane == 0) AB_STAMP(1, i, 1);
       tc_fence_after();
       uint32_t c1[32], c2[32];
       tmem_ld32(tmem_C + lane_sel + cb * 64, c1);
@@ -236,45 +239,44 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gri
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(C_EMPTY(cb));
+      if (warp == 2 && lane == 0) AB_STAMP(1, i, 2);
 
       float e1[32], e2[32];
       if (!DKV) {
-        // columns = keys t0 + c
-        const uint64_t drop_row = (bh * p.Sq + row_g) * static_cast<uint64_t>(p.Sk + (p.Sk & 1)) + t0;
+        // columns = keys t0 + c; row statistics are scalars
 #pragma unroll
         for (int c = 0; c < 32; c += 2) {
-          const float pr0 = ((badbits >> c) & 1u) ? 0.f : fast_exp2(__uint_as_float(c1[c]) * p.sl2 - lse_row);
-          const float pr1 = ((badbits >> (c + 1)) & 1u) ? 0.f : fast_exp2(__uint_as_float(c1[c + 1]) * p.sl2 - lse_row);
+          const float pr0 = ((badbits >> c) & 1u) ? 0.f : fast_exp2(fmaf(__uint_as_float(c1[c]), p.sl2, -lse_row));
+          const float pr1 = ((badbits >> (c + 1)) & 1u) ? 0.f : fast_exp2(fmaf(__uint_as_float(c1[c + 1]), p.sl2, -lse_row));
           float dp0 = __uint_as_float(c2[c]), dp1 = __uint_as_float(c2[c + 1]);
-          if (p.drop_p > 0.f) {
-            const uint32_t hsh = drop_pair(p.drop_seed, drop_row + c);
+          if (DROP) {
+            const uint32_t hsh = drop_pairhash(rh_row, static_cast<uint32_t>(t0 + c) >> 1);
             dp0 = drop_keep_lo(hsh, p.drop_thresh) ? dp0 * p.drop_scale : 0.f;
             dp1 = drop_keep_hi(hsh, p.drop_thresh) ? dp1 * p.drop_scale : 0.f;
           }
-          e2[c] = pr0 * (dp0 - delta_row) * p.scale;
-          e2[c + 1] = pr1 * (dp1 - delta_row) * p.scale;
+          e2[c] = pr0 * (dp0 - delta_row) * sc;
+          e2[c + 1] = pr1 * (dp1 - delta_row) * sc;
         }
       } else {
-        // columns = queries t0 + c ; per-column statistics
+        // columns = queries t0 + c; per-column statistics, this thread's key is fixed
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
-          const int qi = t0 + c;
-          const bool ok = row_valid && qi < p.Sq;
-          const float pr = ok ? fast_exp2(__uint_as_float(c1[c]) * p.sl2 - ls[c]) : 0.f;
+          const float pr = ((badbits >> c) & 1u) ? 0.f : fast_exp2(fmaf(__uint_as_float(c1[c]), p.sl2, -ls[c]));
           float dpv = __uint_as_float(c2[c]);
           float pd = pr;
-          if (p.drop_p > 0.f) {
-            const uint64_t eidx = (bh * p.Sq + qi) * static_cast<uint64_t>(p.Sk + (p.Sk & 1)) + row_g;
-            const uint32_t hsh = drop_pair(p.drop_seed, eidx & ~1ull);
-            const bool keep = (eidx & 1) ? drop_keep_hi(hsh, p.drop_thresh) : drop_keep_lo(hsh, p.drop_thresh);
+          if (DROP) {
+            const uint32_t hsh = mix32(__shfl_sync(0xffffffffu, rh_lane, c) + colterm);
+            const bool keep = ((hsh >> colshift) & 0xFFFFu) >= p.drop_thresh;
             dpv = keep ? dpv * p.drop_scale : 0.f;
             pd = keep ? pr * p.drop_scale : 0.f;
           }
           e1[c] = pd;
-          e2[c] = ok ? pr * (dpv - ds[c]) * p.scale : 0.f;
+          e2[c] = pr * (dpv - ds[c]) * sc;
         }
       }
+      if (warp == 2 && lane == 0) AB_STAMP(1, i, 3);
       if (i > 0) mbar_wait(E_EMPTY, (i - 1) & 1);
+      if (warp == 2 && lane == 0) AB_STAMP(1, i, 4);
 #pragma unroll
       for (int sgm = 0; sgm < 4; ++sgm) {
         const uint32_t off = (static_cast<uint32_t>(sgm) ^ swz) << 4;
@@ -289,6 +291,7 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gri
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(E_FULL);
+      if (warp == 2 && lane == 0) AB_STAMP(1, i, 5);
     }
 
     // ---- epilogue: accumulators -> bf16 -> global (token-major, heads merged)
@@ -344,6 +347,7 @@ extern "C" int xf_attn_bwd(const XfAttnBwd* a, xf_stream_t stream_) {
   p.scale = a->scale;
   p.kpm = a->key_padding_mask;
   p.kpm_start = a->kpm_start;
+  p.dbg = reinterpret_cast<long long*>(a->debug_timeline);
   p.lse = a->lse; p.delta = a->delta; p.stat_stride = a->stat_stride;
   p.drop_p = a->drop_p;
   p.drop_scale = a->drop_p > 0.f ? 1.f / (1.f - a->drop_p) : 1.f;
@@ -365,8 +369,10 @@ extern "C" int xf_attn_bwd(const XfAttnBwd* a, xf_stream_t stream_) {
   const int smem_bytes = 1024 + 1024 + 2 * p.nch * 8192 + AB_STAGES * 2 * p.nch * 2048 + 2 * 8192;
   static bool attr_set = false;
   if (!attr_set) {
-    XF_CUDA(cudaFuncSetAttribute(attn_bwd_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    XF_CUDA(cudaFuncSetAttribute(attn_bwd_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    XF_CUDA(cudaFuncSetAttribute(attn_bwd_tcgen05_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    XF_CUDA(cudaFuncSetAttribute(attn_bwd_tcgen05_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    XF_CUDA(cudaFuncSetAttribute(attn_bwd_tcgen05_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    XF_CUDA(cudaFuncSetAttribute(attn_bwd_tcgen05_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   // dQ pass
@@ -376,7 +382,8 @@ extern "C" int xf_attn_bwd(const XfAttnBwd* a, xf_stream_t stream_) {
     pq.n_stream = (a->Sk + AB_BN - 1) / AB_BN;
     pq.ncbuf = (512 - a->dp) / 64 >= 2 ? 2 : 1;
     pq.out2 = reinterpret_cast<__nv_bfloat16*>(a->dq); pq.ld2 = a->lddq;
-    attn_bwd_tcgen05_kernel<false><<<a->B * a->H * pq.r_tiles, AB_THREADS, smem_bytes, stream>>>(q128, do128, k32, v32, pq);
+    if (a->drop_p > 0.f) attn_bwd_tcgen05_kernel<false, true><<<a->B * a->H * pq.r_tiles, AB_THREADS, smem_bytes, stream>>>(q128, do128, k32, v32, pq);
+    else attn_bwd_tcgen05_kernel<false, false><<<a->B * a->H * pq.r_tiles, AB_THREADS, smem_bytes, stream>>>(q128, do128, k32, v32, pq);
     g_launches.fetch_add(1);
     XF_CUDA(cudaGetLastError());
   }
@@ -388,7 +395,9 @@ extern "C" int xf_attn_bwd(const XfAttnBwd* a, xf_stream_t stream_) {
     pk.ncbuf = (512 - 2 * a->dp) / 64 >= 2 ? 2 : 1;
     pk.out2 = reinterpret_cast<__nv_bfloat16*>(a->dk); pk.ld2 = a->lddk;
     pk.out1 = reinterpret_cast<__nv_bfloat16*>(a->dv); pk.ld1 = a->lddv;
-    attn_bwd_tcgen05_kernel<true><<<a->B * a->H * pk.r_tiles, AB_THREADS, smem_bytes, stream>>>(k128, v128, q32, do32, pk);
+    if (pk.dbg) pk.dbg += 2 * 64 * 8;
+    if (a->drop_p > 0.f) attn_bwd_tcgen05_kernel<true, true><<<a->B * a->H * pk.r_tiles, AB_THREADS, smem_bytes, stream>>>(k128, v128, q32, do32, pk);
+    else attn_bwd_tcgen05_kernel<true, false><<<a->B * a->H * pk.r_tiles, AB_THREADS, smem_bytes, stream>>>(k128, v128, q32, do32, pk);
     g_launches.fetch_add(1);
     XF_CUDA(cudaGetLastError());
   }

@@ -124,31 +124,27 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // descriptors are built once; only the start-address word changes per MMA (issue-rate matters
-      // for the N = 64 score MMAs)
+      // descriptors are built once; only the start-address word changes per MMA, and a 64-column chunk's
+      // k-steps are issued from one asm block (issue-rate matters for the N = 64 score MMAs)
       const uint32_t idesc_s = make_idesc_bf16(AF_BN, 0, 0);
       const uint32_t idesc_o = make_idesc_bf16(p.dp, 0, 1);
-      const int ksteps = p.dp / 16;
+      const int npairs = p.dp / 32;                         // pairs of k-steps (32 head-dim columns)
       const uint64_t dk = make_smem_desc(0, 16, 1024);       // K-major SWIZZLE_128B template
       const uint64_t dmn = make_smem_desc(0, 8192, 1024);    // MN-major template (V)
-      const uint32_t hi_k = static_cast<uint32_t>(dk >> 32), hi_mn = static_cast<uint32_t>(dmn >> 32);
-      const uint32_t lo_k = static_cast<uint32_t>(dk), lo_mn = static_cast<uint32_t>(dmn);
-      auto mk = [](uint32_t hi, uint32_t lo) { return (static_cast<uint64_t>(hi) << 32) | lo; };
-      constexpr int MAXK = 16;  // dp <= 256
-      uint32_t qlo[MAXK];
-      const uint32_t qa = smem_u32(sQ);
-#pragma unroll
-      for (int k = 0; k < MAXK; ++k) qlo[k] = lo_k + ((qa + (k >> 2) * 16384 + (k & 3) * 32) >> 4);
-      const uint32_t k_base = smem_u32(sK), v_base = smem_u32(sV), plo = lo_k + (smem_u32(sP) >> 4);
+      const uint32_t hi_k = desc_hi(dk), hi_mn = desc_hi(dmn);
+      const uint32_t q_lo = desc_lo(dk) + (smem_u32(sQ) >> 4), p_lo = desc_lo(dk) + (smem_u32(sP) >> 4);
+      const uint32_t k_base = smem_u32(sK) >> 4, v_base = smem_u32(sV) >> 4, kv_lo = kv_bytes >> 4;
       auto issue_s = [&](int j) {
         const int st = j & 1, sb = j & 1;
         mbar_wait(K_FULL(st), (j >> 1) & 1);
         mbar_wait(S_EMPTY(sb), ((j >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t klo = lo_k + ((k_base + st * kv_bytes) >> 4);
-#pragma unroll
-        for (int k = 0; k < MAXK; ++k)
-          if (k < ksteps) umma_bf16(tmem_S + sb * AF_BN, mk(hi_k, qlo[k]), mk(hi_k, klo + (k >> 2) * 512 + (k & 3) * 2), idesc_s, k != 0);
+        const uint32_t k_lo = desc_lo(dk) + k_base + st * kv_lo;
+        // pair jp covers head-dim columns [32 jp, 32 jp + 32): chunk jp >> 1, half jp & 1
+        for (int jp = 0; jp < npairs; ++jp) {
+          const uint32_t ao = (jp >> 1) * 1024 + (jp & 1) * 4, bo = (jp >> 1) * 512 + (jp & 1) * 4;
+          umma_k2(tmem_S + sb * AF_BN, hi_k, q_lo + ao, 2, hi_k, k_lo + bo, 2, idesc_s, jp != 0);
+        }
         umma_commit(S_FULL(sb));
         umma_commit(K_EMPTY(st));
       };
@@ -160,9 +156,8 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         mbar_wait(P_FULL, j & 1);
         mbar_wait(V_FULL(st), (j >> 1) & 1);
         tc_fence_after();
-        const uint32_t vlo = lo_mn + ((v_base + st * kv_bytes) >> 4);
-#pragma unroll
-        for (int k = 0; k < AF_BN / 16; ++k) umma_bf16(tmem_O, mk(hi_k, plo + k * 2), mk(hi_mn, vlo + k * 128), idesc_o, (j | k) != 0);
+        const uint32_t v_lo = desc_lo(dmn) + v_base + st * kv_lo;
+        umma_k4(tmem_O, hi_k, p_lo, 2, hi_mn, v_lo, 128, idesc_o, j != 0);
         umma_commit(V_EMPTY(st));
         umma_commit(O_READY);
       }
@@ -174,7 +169,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     const int q = q0 + r;
     const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
     float m_used = 0.f, l = 0.f;
-    const uint64_t drop_row = (static_cast<uint64_t>(b * p.H + hd) * p.Sq + q) * static_cast<uint64_t>(p.Sk + (p.Sk & 1));
+    const uint32_t drop_rh = drop_rowhash(p.drop_seed, static_cast<uint64_t>(b * p.H + hd) * p.Sq + q);
     uint8_t* prow = sP + r * 128;
 
     for (int j = 0; j < nkv; ++j) {
@@ -236,7 +231,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       if (p.drop_p > 0.f) {
 #pragma unroll
         for (int c = 0; c < 64; c += 2) {
-          const uint32_t hsh = drop_pair(p.drop_seed, drop_row + static_cast<uint64_t>(k0 + c));
+          const uint32_t hsh = drop_pairhash(drop_rh, static_cast<uint32_t>(k0 + c) >> 1);
           x[c] = drop_keep_lo(hsh, p.drop_thresh) ? x[c] * p.drop_scale : 0.f;
           x[c + 1] = drop_keep_hi(hsh, p.drop_thresh) ? x[c + 1] * p.drop_scale : 0.f;
         }

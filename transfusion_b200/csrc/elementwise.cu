@@ -186,11 +186,11 @@ __device__ __forceinline__ void load8f(const float* p, float (&v)[8]) {
   const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
-// dropout on 8 consecutive elements starting at the even linear index idx0
-__device__ __forceinline__ void drop8(float (&v)[8], uint32_t key, uint64_t idx0, uint32_t t16, float scale) {
+// dropout on 8 consecutive columns col0.. (col0 % 8 == 0) of the row with hash rh
+__device__ __forceinline__ void drop8(float (&v)[8], uint32_t rh, uint32_t col0, uint32_t t16, float scale) {
 #pragma unroll
   for (int k = 0; k < 8; k += 2) {
-    const uint32_t h = drop_pair(key, idx0 + k);
+    const uint32_t h = drop_pairhash(rh, (col0 + k) >> 1);
     v[k] = drop_keep_lo(h, t16) ? v[k] * scale : 0.f;
     v[k + 1] = drop_keep_hi(h, t16) ? v[k + 1] * scale : 0.f;
   }
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const LnParams p) {
         load8f(p.beta + vidx * 8, b);
 #pragma unroll
         for (int k = 0; k < 8; ++k) v[k] = (v[k] - mean) * rstd * g[k] + b[k];
-        if (p.drop_p > 0.f) drop8(v, p.drop_seed, static_cast<uint64_t>(orow * p.ldy + vidx * 8), p.drop_thresh, p.drop_scale);
+        if (p.drop_p > 0.f) drop8(v, drop_rowhash(p.drop_seed, static_cast<uint64_t>(orow)), vidx * 8, p.drop_thresh, p.drop_scale);
         *(reinterpret_cast<uint4*>(yr) + vidx) = pack8(v);
       }
     }
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const LnBwdParams p)
         unpack8(qx[i], xv); unpack8(qd[i], dv);
         load8f(p.gamma + vidx * 8, gm);
         if (p.dy_drop_p > 0.f) {
-          drop8(dv, p.dy_seed, static_cast<uint64_t>(orow * p.lddy + vidx * 8), p.dy_thresh, p.dy_scale);
+          drop8(dv, drop_rowhash(p.dy_seed, static_cast<uint64_t>(orow)), vidx * 8, p.dy_thresh, p.dy_scale);
           qd[i] = pack8(dv);  // keep the masked gradient (exactly representable: scale applied in fp32, re-rounded once)
         }
 #pragma unroll
@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const LnBwdParams p)
         for (int k = 0; k < 8; ++k) o[k] = rstd * (dv[k] * gm[k] - s1 - (xv[k] - mean) * rstd * s2);
         *(reinterpret_cast<uint4*>(dxr) + vidx) = pack8(o);
         if (p.dx2) {
-          if (p.dx2_drop_p > 0.f) drop8(o, p.dx2_seed, static_cast<uint64_t>(irow * p.lddx + vidx * 8), p.dx2_thresh, p.dx2_scale);
+          if (p.dx2_drop_p > 0.f) drop8(o, drop_rowhash(p.dx2_seed, static_cast<uint64_t>(irow)), vidx * 8, p.dx2_thresh, p.dx2_scale);
           *(reinterpret_cast<uint4*>(p.dx2 + irow * p.lddx) + vidx) = pack8(o);
         }
         if (p.dbias) {
@@ -475,7 +475,7 @@ rows_gather_kernel(const __nv_bfloat16* __restrict__ in, long long ldi, __nv_bfl
     const long long ir = remap_row(r, rin, rout, roff);
     const uint4 q = __ldg(reinterpret_cast<const uint4*>(in + ir * ldi) + vc);
     float v[8] = {bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y), bf16_lo(q.z), bf16_hi(q.z), bf16_lo(q.w), bf16_hi(q.w)};
-    if (drop_p > 0.f) drop8(v, seed, static_cast<uint64_t>(ir * ldi + vc * 8), thresh, drop_scale);
+    if (drop_p > 0.f) drop8(v, drop_rowhash(seed, static_cast<uint64_t>(ir)), vc * 8, thresh, drop_scale);
 #pragma unroll
     for (int k = 0; k < 8; ++k) s[k] += v[k];
     *(reinterpret_cast<uint4*>(out + static_cast<long long>(r) * ldo) + vc) =

@@ -107,9 +107,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int m, int n
   }
   const long long orow = static_cast<long long>(m_out) * p.ldc + n0;
   if (p.drop_p > 0.f && p.drop_first) {
+    const uint32_t rh = drop_rowhash(p.drop_seed, static_cast<uint64_t>(m_out));
 #pragma unroll
     for (int i = 0; i < 32; i += 2) {
-      const uint32_t hsh = drop_pair(p.drop_seed, static_cast<uint64_t>(orow + i));
+      const uint32_t hsh = drop_pairhash(rh, static_cast<uint32_t>(n0 + i) >> 1);
       v[i] = drop_keep_lo(hsh, p.drop_thresh) ? v[i] * p.drop_scale : 0.f;
       v[i + 1] = drop_keep_hi(hsh, p.drop_thresh) ? v[i + 1] * p.drop_scale : 0.f;
     }
@@ -151,9 +152,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int m, int n
     }
   }
   if (p.drop_p > 0.f && !p.drop_first) {
+    const uint32_t rh = drop_rowhash(p.drop_seed, static_cast<uint64_t>(m_out));
 #pragma unroll
     for (int i = 0; i < 32; i += 2) {
-      const uint32_t hsh = drop_pair(p.drop_seed, static_cast<uint64_t>(orow + i));
+      const uint32_t hsh = drop_pairhash(rh, static_cast<uint32_t>(n0 + i) >> 1);
       v[i] = drop_keep_lo(hsh, p.drop_thresh) ? v[i] * p.drop_scale : 0.f;
       v[i + 1] = drop_keep_hi(hsh, p.drop_thresh) ? v[i + 1] * p.drop_scale : 0.f;
     }
@@ -304,8 +306,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     // ===================== MMA issuer (even CTA of the pair only) =====================
     if (lane == 0 && leader) {
       const uint32_t idesc = make_idesc_bf16(p.tile_n, p.a_mn, p.b_mn, 128 * CG);
-      const uint32_t a_lbo = p.a_mn ? 8192u : 16u, b_lbo = p.b_mn ? 8192u : 16u;
-      const uint32_t a_kstep = p.a_mn ? 2048u : 32u, b_kstep = p.b_mn ? 2048u : 32u;
+      // descriptor templates: only the start-address word advances (per k-step and per stage)
+      const uint64_t dta = make_smem_desc(0, p.a_mn ? 8192u : 16u, 1024);
+      const uint64_t dtb = make_smem_desc(0, p.b_mn ? 8192u : 16u, 1024);
+      const uint32_t a_hi = desc_hi(dta), b_hi = desc_hi(dtb);
+      const uint32_t a_step = (p.a_mn ? 2048u : 32u) >> 4, b_step = (p.b_mn ? 2048u : 32u) >> 4;
+      const uint32_t ring_lo = smem_u32(ring) >> 4, stage_lo = static_cast<uint32_t>(p.stage_bytes) >> 4;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -320,16 +326,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(ring + stage * p.stage_bytes);
-          const uint32_t sb = sa + GEMM_A_BYTES;
-#pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k) {
-            const uint64_t da = make_smem_desc(sa + k * a_kstep, a_lbo, 1024);
-            const uint64_t db = make_smem_desc(sb + k * b_kstep, b_lbo, 1024);
-            if (CG == 2) umma_bf16_cg2(d_tmem, da, db, idesc, (kb | k) != 0);
-            else umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
+          const uint32_t a_lo = desc_lo(dta) + ring_lo + stage * stage_lo;
+          const uint32_t b_lo = desc_lo(dtb) + ring_lo + stage * stage_lo + (GEMM_A_BYTES >> 4);
+          if (CG == 2) {
+            umma_k4_cg2(d_tmem, a_hi, a_lo, a_step, b_hi, b_lo, b_step, idesc, kb != 0);
+            umma_commit_cg2_mc(empty_bar(stage), 0x3);
+          } else {
+            umma_k4(d_tmem, a_hi, a_lo, a_step, b_hi, b_lo, b_step, idesc, kb != 0);
+            umma_commit(empty_bar(stage));
           }
-          if (CG == 2) umma_commit_cg2_mc(empty_bar(stage), 0x3); else umma_commit(empty_bar(stage));
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         if (CG == 2) umma_commit_cg2_mc(tfull_bar(acc), 0x3); else umma_commit(tfull_bar(acc));
@@ -462,7 +467,6 @@ extern "C" int xf_gemm(const XfGemm* g, xf_stream_t stream_) {
   p.drop_stream = g->drop_stream;
   p.drop_first = g->drop_first;
   p.drop_thresh = drop_thresh16(g->drop_p);
-  if (g->drop_p > 0.f && (g->ldc % 2)) return fail(-7, "xf_gemm: dropout needs an even ldc");
   p.drop_scale = g->drop_p > 0.f ? 1.0f / (1.0f - g->drop_p) : 1.0f;
   if (split_k > 1 && (g->bias || g->pos_table || g->act || g->dact_in || g->residual || g->drop_p > 0.f))
     return fail(-8, "xf_gemm: split_k cannot be combined with a non-linear / additive epilogue");

@@ -153,6 +153,49 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Issue-rate matters: one thread feeds the tensor pipe and a short MMA (N <= 64) retires every ~46 cycles
+// (measured, tools/microbench/mma_bench.cu), so the helpers below issue 2 or 4 MMAs of one K-chain from a
+// single asm block.  Descriptors are passed as (hi, lo) words; only the start-address field (lo) advances.
+#define XF_UMMA_CHAIN_BODY(CG)                                                                   \
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t.reg .b32 al, bl;\n\t"                        \
+      "setp.ne.b32 p, %8, 0;\n\t"                                                                 \
+      "setp.eq.b32 q, 0, 0;\n\t"                                                                  \
+      "mov.b64 da, {%2, %1};\n\tmov.b64 db, {%5, %4};\n\t"                                        \
+      "tcgen05.mma.cta_group::" CG ".kind::f16 [%0], da, db, %7, p;\n\t"                          \
+      "add.u32 al, %2, %3;\n\tadd.u32 bl, %5, %6;\n\t"                                            \
+      "mov.b64 da, {al, %1};\n\tmov.b64 db, {bl, %4};\n\t"                                        \
+      "tcgen05.mma.cta_group::" CG ".kind::f16 [%0], da, db, %7, q;\n\t"
+#define XF_UMMA_CHAIN_MORE(CG)                                                                   \
+      "add.u32 al, al, %3;\n\tadd.u32 bl, bl, %6;\n\t"                                            \
+      "mov.b64 da, {al, %1};\n\tmov.b64 db, {bl, %4};\n\t"                                        \
+      "tcgen05.mma.cta_group::" CG ".kind::f16 [%0], da, db, %7, q;\n\t"
+
+// D (+)= sum_{k<2} A_k B_k
+__device__ __forceinline__ void umma_k2(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t a_step, uint32_t b_hi,
+                                        uint32_t b_lo, uint32_t b_step, uint32_t idesc, uint32_t accumulate_first) {
+  asm volatile(XF_UMMA_CHAIN_BODY("1") "}\n"
+               ::"r"(d_tmem), "r"(a_hi), "r"(a_lo), "r"(a_step), "r"(b_hi), "r"(b_lo), "r"(b_step), "r"(idesc),
+                 "r"(accumulate_first)
+               : "memory");
+}
+// D (+)= sum_{k<4} A_k B_k
+__device__ __forceinline__ void umma_k4(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t a_step, uint32_t b_hi,
+                                        uint32_t b_lo, uint32_t b_step, uint32_t idesc, uint32_t accumulate_first) {
+  asm volatile(XF_UMMA_CHAIN_BODY("1") XF_UMMA_CHAIN_MORE("1") XF_UMMA_CHAIN_MORE("1") "}\n"
+               ::"r"(d_tmem), "r"(a_hi), "r"(a_lo), "r"(a_step), "r"(b_hi), "r"(b_lo), "r"(b_step), "r"(idesc),
+                 "r"(accumulate_first)
+               : "memory");
+}
+__device__ __forceinline__ void umma_k4_cg2(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t a_step, uint32_t b_hi,
+                                            uint32_t b_lo, uint32_t b_step, uint32_t idesc, uint32_t accumulate_first) {
+  asm volatile(XF_UMMA_CHAIN_BODY("2") XF_UMMA_CHAIN_MORE("2") XF_UMMA_CHAIN_MORE("2") "}\n"
+               ::"r"(d_tmem), "r"(a_hi), "r"(a_lo), "r"(a_step), "r"(b_hi), "r"(b_lo), "r"(b_step), "r"(idesc),
+                 "r"(accumulate_first)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t desc_hi(uint64_t d) { return static_cast<uint32_t>(d >> 32); }
+__device__ __forceinline__ uint32_t desc_lo(uint64_t d) { return static_cast<uint32_t>(d); }
+
 // Arrives (once) on the mbarrier when all previously issued tcgen05.mma of this thread completed.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -272,8 +315,7 @@ __device__ __forceinline__ float fast_exp2(float x) {
 }
 
 // Counter-based dropout (no mask storage; the backward recomputes the same bits).  One 32-bit hash
-// (lowbias32 finaliser over the pair counter XOR a per-call key) decides TWO adjacent elements: element
-// 2j keeps iff the low 16 bits >= t16, element 2j+1 iff the high 16 bits >= t16, t16 = round(p * 65536).
+// (lowbias32 finaliser) decides TWO adjacent columns of a row, t16 = round(p * 65536).
 __host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
   x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
   return x;
@@ -284,11 +326,13 @@ __host__ __device__ __forceinline__ uint32_t drop_key(uint32_t seed, uint32_t st
 __host__ __device__ __forceinline__ uint32_t drop_thresh16(float p) {
   return static_cast<uint32_t>(static_cast<double>(p) * 65536.0 + 0.5);
 }
-// even_idx: linear index of the even element of the pair
-__device__ __forceinline__ uint32_t drop_pair(uint32_t key, uint64_t even_idx) {
-  const uint32_t lo = static_cast<uint32_t>(even_idx >> 1);
-  const uint32_t hi = static_cast<uint32_t>(even_idx >> 33);
-  return mix32(lo ^ key ^ (hi * 0x85EBCA6BU));
+// decision(row, col): rowhash is computed once per row (thread), then one hash per column PAIR:
+//   h = mix32(rowhash(row) + (col >> 1) * golden);  even col keeps iff lo16(h) >= t16, odd col iff hi16(h) >= t16
+__device__ __forceinline__ uint32_t drop_rowhash(uint32_t key, uint64_t row) {
+  return mix32(key ^ static_cast<uint32_t>(row) ^ (static_cast<uint32_t>(row >> 32) * 0x85EBCA6BU));
+}
+__device__ __forceinline__ uint32_t drop_pairhash(uint32_t rowhash, uint32_t col_pair) {
+  return mix32(rowhash + col_pair * 0x9E3779B9U);
 }
 __device__ __forceinline__ bool drop_keep_lo(uint32_t h, uint32_t t16) { return (h & 0xFFFFu) >= t16; }
 __device__ __forceinline__ bool drop_keep_hi(uint32_t h, uint32_t t16) { return (h >> 16) >= t16; }

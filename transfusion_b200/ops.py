@@ -243,7 +243,7 @@ def attn_fwd(q, k, v, out, lse, *, B: int, H: int, Sq: int, Sk: int, dp: int, sc
 
 def attn_bwd(q, k, v, d_out, lse, delta, dq, dk, dv, *, B: int, H: int, Sq: int, Sk: int, dp: int, scale: float,
              key_padding_mask: Optional[torch.Tensor] = None, kpm_start: int = 0, drop_p: float = 0.0,
-             drop_seed: int = 0, drop_stream: int = 0):
+             drop_seed: int = 0, drop_stream: int = 0, debug_timeline: Optional[torch.Tensor] = None):
     a = XfAttnBwd()
     a.q, a.ldq = q.data_ptr(), q.stride(0)
     a.k, a.ldk = k.data_ptr(), k.stride(0)
@@ -258,6 +258,7 @@ def attn_bwd(q, k, v, d_out, lse, delta, dq, dk, dv, *, B: int, H: int, Sq: int,
     if key_padding_mask is not None:
         a.key_padding_mask = key_padding_mask.data_ptr()
     a.kpm_start = kpm_start
+    a.debug_timeline = debug_timeline.data_ptr() if debug_timeline is not None else None
     a.B, a.H, a.Sq, a.Sk, a.dp = B, H, Sq, Sk, dp
     a.scale = scale
     a.drop_p, a.drop_seed, a.drop_stream = drop_p, drop_seed, drop_stream
