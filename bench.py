@@ -226,9 +226,31 @@ def run_ours(args):
             with torch.no_grad():
                 net({"image": None, "language_f": (lang_d, mask_d)})
 
+    # end-to-end step: inputs start in pinned HOST memory; the copy of step i+1's inputs is issued on a copy
+    # stream while step i computes (double-buffered device staging), and the scalar loss of every step is read
+    # back to the host.  One H2D of the full input set and one D2H per step are inside the timed region.
+    copy_stream = torch.cuda.Stream(device=dev)
+    stage_bufs = [({k: torch.empty_like(v, device=dev) for k, v in feats_h.items()}, torch.empty_like(lang_h, device=dev),
+                   torch.empty_like(mask_h, device=dev)) for _ in range(2)]
+    stage_ev = [torch.cuda.Event(), torch.cuda.Event()]
+    e2e_state = {"i": 0}
+
+    def prefetch(slot):
+        f, lg, mk = stage_bufs[slot]
+        with torch.cuda.stream(copy_stream):
+            for k in f:
+                f[k].copy_(feats_h[k], non_blocking=True)
+            lg.copy_(lang_h, non_blocking=True)
+            mk.copy_(mask_h, non_blocking=True)
+            stage_ev[slot].record(copy_stream)
+
     def step_e2e():
-        f = {k: v.to(dev, non_blocking=True) for k, v in feats_h.items()}
-        lg, mk = lang_h.to(dev, non_blocking=True), mask_h.to(dev, non_blocking=True)
+        i = e2e_state["i"]
+        e2e_state["i"] = i + 1
+        slot = i & 1
+        prefetch(slot ^ 1)                      # next step's inputs, overlapped with this step's compute
+        torch.cuda.current_stream().wait_event(stage_ev[slot])
+        f, lg, mk = stage_bufs[slot]
         model.rcnn_model.features = f
         if train:
             net.zero_grad(set_to_none=True)
@@ -243,7 +265,7 @@ def run_ours(args):
             with torch.no_grad():
                 out = net({"image": None, "language_f": (lg, mk)})["features"]
                 loss = sum(out[k].float().sum() for k in keys)
-        return float(loss.item())  # device -> host read of the step's result
+        return float(loss.item())  # device -> host read of the step's result (also fences the slot for reuse)
 
     def barrier():
         if world > 1:
@@ -278,6 +300,7 @@ def run_ours(args):
     value = world * B * args.steps / (ms / 1e3)
 
     # ---- end-to-end: host (pinned) inputs in, scalar loss out, every step
+    prefetch(0)
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
