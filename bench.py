@@ -185,7 +185,8 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     w = WORKLOADS[args.workload]
     L = args.lang_len or w["lang_len"]
     B = args.batch or (w["train_batch"] if args.mode == "train" else w["eval_batch"])
@@ -310,11 +311,13 @@ def run_ours(args):
 
     # ---- per-kernel roofline pass: CUDA events around every launch (rank 0, separate from the timed run)
     roofline, kernels = None, None
+    # every rank runs the step (it contains the gradient all-reduce); only rank 0 records the events
+    if rank == 0:
+        ops.PROFILE = []
+    step_resident()
+    torch.cuda.synchronize()
     if rank == 0:
         peaks = load_peaks()
-        ops.PROFILE = []
-        step_resident()
-        torch.cuda.synchronize()
         prof, ops.PROFILE = ops.PROFILE, None
         fam = {}
         for (name, flops, nbytes, e0, e1) in prof:
