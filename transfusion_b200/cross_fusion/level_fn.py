@@ -60,20 +60,29 @@ N_LAYER_PARAMS = 12
 N_TAIL_PARAMS = 4       # final LN weight/bias, back-projection weight/bias
 
 
+N_CLUSTERS = 74  # CTA pairs on a 148-SM B200
+
+
 def _split_k_for(tiles: int, total_kb: int) -> int:
-    """Enough work items to fill ~2 waves of 148 CTAs, at least 4 k-blocks per split."""
-    want = max(1, (2 * 148 + tiles - 1) // tiles)
-    return max(1, min(want, max(1, total_kb // 4)))
+    """Split-K factor for a wgrad GEMM with `tiles` output tiles and `total_kb` 64-token k-blocks: minimise
+    waves x (k-blocks per item + fixed per-item cost) over the persistent grid of CTA pairs."""
+    best, best_cost = 1, None
+    for s in range(1, max(1, min(32, total_kb // 8)) + 1):
+        items = tiles * s
+        waves = -(-items // N_CLUSTERS)
+        cost = waves * (-(-total_kb // s) + 6)
+        if best_cost is None or cost < best_cost:
+            best, best_cost = s, cost
+    return best
 
 
 def _wgrad(dy: torch.Tensor, x: torch.Tensor, out_f32: torch.Tensor, n_out: int, k_in: int, tokens: int):
     """out_f32[n_out, k_in] += dy[tokens, n_out]^T @ x[tokens, k_in]  (both operands MN-major)."""
-    tile_n = 0
-    tn = 256 if k_in % 256 == 0 else (224 if k_in % 224 == 0 else (192 if k_in % 192 == 0 else 128))
-    tiles = ((n_out + 127) // 128) * ((k_in + tn - 1) // tn)
+    tn = next((c for c in (256, 224, 192, 160, 128) if k_in % c == 0), 256)   # mirrors pick_tile_n in gemm.cu
+    tiles = ((n_out + 255) // 256) * ((k_in + tn - 1) // tn)
     split = _split_k_for(tiles, (tokens + 63) // 64)
     ops.gemm(dy, x, out_f32, M=n_out, N=k_in, K=tokens, a_mn_major=True, b_mn_major=True, accumulate=True,
-             split_k=split, tile_n=tile_n)
+             split_k=split)
 
 
 class FusionLevelFunction(torch.autograd.Function):

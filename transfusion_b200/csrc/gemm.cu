@@ -178,9 +178,18 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int m, int n
   if (p.out_f32) {
     float* o = reinterpret_cast<float*>(p.out) + orow;
     if (p.accumulate) {
+      if (full && p.vec_ok) {
+        // 128-bit vector reductions: 8 L2 transactions per 32-column chunk instead of 32
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
-        if (n0 + i < p.N) atomicAdd(o + i, v[i]);
+        for (int i = 0; i < 32; i += 4)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + i), "f"(v[i]), "f"(v[i + 1]), "f"(v[i + 2]),
+                       "f"(v[i + 3])
+                       : "memory");
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (n0 + i < p.N) atomicAdd(o + i, v[i]);
+      }
     } else if (full && p.vec_ok) {
 #pragma unroll
       for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);

@@ -18,6 +18,7 @@ DEFAULT_CTA_GROUP = int(_os.environ.get("XF_GEMM_CTA_GROUP", "0"))
 # When set to a list, every op appends (family, algorithmic flops, algorithmic bytes, start event, end event):
 # bench.py's per-kernel roofline pass (CUDA events on the launching stream).
 PROFILE = None
+PROFILE_DETAIL = bool(int(_os.environ.get("XF_PROFILE_DETAIL", "0")))
 
 
 class _Prof:
@@ -103,6 +104,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     g.max_ctas = max_ctas
     g.cta_group = cta_group if cta_group else DEFAULT_CTA_GROUP
     fam = "gemm_wgrad" if a_mn_major else ("gemm_dgrad" if b_mn_major else "gemm_fwd")
+    if PROFILE_DETAIL:
+        fam += f"[M={M},N={N},K={K},split={split_k},act={act},drop={int(drop_p > 0)},res={int(residual is not None)}]"
     with _Prof(fam, 2.0 * M * N * K):
         check(lib().xf_gemm(C.byref(g), _stream()), "xf_gemm")
     return out
