@@ -166,6 +166,7 @@ typedef struct XfAttnFwd {
   int32_t B, H, Sq, Sk, dp;
   float scale;                       /* 1/sqrt(head_dim) */
   float drop_p; uint32_t drop_seed, drop_stream;   /* dropout on the attention probabilities */
+  void* debug_timeline;              /* dev aid: NULL, or int64[2][64][8] device buffer of clock64 stamps */
 } XfAttnFwd;
 int xf_attn_fwd(const XfAttnFwd* a, xf_stream_t stream);
 

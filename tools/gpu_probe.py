@@ -416,6 +416,37 @@ def bwd_timeline(drop=0.15):
             print("   ", int(r[1] - r[0]), int(r[2] - r[1]), int(r[3] - r[2]), int(r[4] - r[3]), int(r[5] - r[4]), " period", int(sm[i + 1, 0] - r[0]))
 
 
+def fwd_timeline(drop=0.15):
+    import math
+    B, H, S, d = 13, 4, 3136, 224
+    dev = "cuda"
+    torch.manual_seed(0)
+    qkv = torch.randn(B * S, 3 * H * d, device=dev).bfloat16()
+    D = H * d
+    Sp = (S + 127) // 128 * 128
+    out = torch.empty(B * S, D, device=dev, dtype=torch.bfloat16)
+    lse = torch.empty(B, H, Sp, device=dev)
+    kpm = torch.zeros(B, S, dtype=torch.uint8, device=dev); kpm[:, S - 20:] = 1
+    dbg = torch.zeros(2, 64, 8, dtype=torch.int64, device=dev)
+    kw = dict(B=B, H=H, Sq=S, Sk=S, dp=d, scale=1 / math.sqrt(d), drop_p=drop, drop_seed=3, drop_stream=4)
+    for it in range(2):
+        ops.attn_fwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], out, lse, key_padding_mask=kpm, kpm_start=S - 64,
+                     debug_timeline=dbg, **kw)
+    torch.cuda.synchronize()
+    t = dbg.cpu()
+    mma, sm = t[0], t[1]
+    print(f"--- attn fwd drop={drop}: MMA-thread period per KV tile:", [int(mma[i + 1, 0] - mma[i, 0]) for i in range(8, 20)])
+    print("MMA thread [K_FULL wait, S_EMPTY wait, issue S | (gap) P_FULL wait, V_FULL wait, issue PV]:")
+    for i in range(10, 16):
+        r = mma[i]
+        print("   ", int(r[1] - r[0]), int(r[2] - r[1]), int(r[3] - r[2]), "|", int(r[5] - r[4]), int(r[6] - r[5]), int(r[7] - r[6]))
+    print("softmax warp2 [S_FULL wait, ld+release, compute, O_READY wait, rescale+P store+arrive]:")
+    for i in range(10, 16):
+        r = sm[i]
+        print("   ", int(r[1] - r[0]), int(r[2] - r[1]), int(r[3] - r[2]), int(r[4] - r[3]), int(r[5] - r[4]), " period", int(sm[i + 1, 0] - r[0]))
+
+
+CASES["fwd_timeline"] = lambda: (fwd_timeline(0.15), fwd_timeline(0.0))
 CASES["bwd_timeline"] = lambda: (bwd_timeline(0.15), bwd_timeline(0.0))
 CASES["drop_debug2"] = drop_debug2
 CASES["drop_debug"] = drop_debug

@@ -77,6 +77,7 @@ class XfAttnFwd(C.Structure):
         ("B", C.c_int32), ("H", C.c_int32), ("Sq", C.c_int32), ("Sk", C.c_int32), ("dp", C.c_int32),
         ("scale", C.c_float),
         ("drop_p", C.c_float), ("drop_seed", C.c_uint32), ("drop_stream", C.c_uint32),
+        ("debug_timeline", C.c_void_p),
     ]
 
 

@@ -44,8 +44,12 @@ struct AttnFwdParams {
   int lse_stride;
   float drop_p, drop_scale;
   uint32_t drop_seed, drop_stream, drop_thresh;
+  long long* dbg;  // dev aid: clock64 stamps of CTA 0 (null in production)
 };
 
+#define AF_STAMP(role, i, ev) do { if (p.dbg && blockIdx.x == 0 && (i) < 64) p.dbg[((role) * 64 + (i)) * 8 + (ev)] = clock64(); } while (0)
+
+template <bool DROP>
 __global__ void __launch_bounds__(AF_THREADS, 1)
 attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                         const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ AttnFwdParams p) {
@@ -136,8 +140,11 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       const uint32_t k_base = smem_u32(sK) >> 4, v_base = smem_u32(sV) >> 4, kv_lo = kv_bytes >> 4;
       auto issue_s = [&](int j) {
         const int st = j & 1, sb = j & 1;
+        AF_STAMP(0, j, 0);
         mbar_wait(K_FULL(st), (j >> 1) & 1);
+        AF_STAMP(0, j, 1);
         mbar_wait(S_EMPTY(sb), ((j >> 1) & 1) ^ 1);
+        AF_STAMP(0, j, 2);
         tc_fence_after();
         const uint32_t k_lo = desc_lo(dk) + k_base + st * kv_lo;
         // pair jp covers head-dim columns [32 jp, 32 jp + 32): chunk jp >> 1, half jp & 1
@@ -147,19 +154,24 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         }
         umma_commit(S_FULL(sb));
         umma_commit(K_EMPTY(st));
+        AF_STAMP(0, j, 3);
       };
       mbar_wait(Q_FULL, 0);
       issue_s(0);
       for (int j = 0; j < nkv; ++j) {
         if (j + 1 < nkv) issue_s(j + 1);
         const int st = j & 1;
+        AF_STAMP(0, j, 4);
         mbar_wait(P_FULL, j & 1);
+        AF_STAMP(0, j, 5);
         mbar_wait(V_FULL(st), (j >> 1) & 1);
+        AF_STAMP(0, j, 6);
         tc_fence_after();
         const uint32_t v_lo = desc_lo(dmn) + v_base + st * kv_lo;
         umma_k4(tmem_O, hi_k, p_lo, 2, hi_mn, v_lo, 128, idesc_o, j != 0);
         umma_commit(V_EMPTY(st));
         umma_commit(O_READY);
+        AF_STAMP(0, j, 7);
       }
     }
   } else {
@@ -169,13 +181,15 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     const int q = q0 + r;
     const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
     float m_used = 0.f, l = 0.f;
-    const uint32_t drop_rh = drop_rowhash(p.drop_seed, static_cast<uint64_t>(b * p.H + hd) * p.Sq + q);
+    const uint32_t drop_rh = DROP ? drop_rowhash(p.drop_seed, static_cast<uint64_t>(b * p.H + hd) * p.Sq + q) : 0u;
     uint8_t* prow = sP + r * 128;
 
     for (int j = 0; j < nkv; ++j) {
       const int sb = j & 1;
       const int k0 = j * AF_BN;
+      if (warp == 2 && lane == 0) AF_STAMP(1, j, 0);
       mbar_wait(S_FULL(sb), (j >> 1) & 1);
+      if (warp == 2 && lane == 0) AF_STAMP(1, j, 1);
       tc_fence_after();
       uint32_t sr0[32], sr1[32];
       tmem_ld32(tmem_S + lane_sel + sb * AF_BN, sr0);
@@ -184,29 +198,37 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(S_EMPTY(sb));
+      if (warp == 2 && lane == 0) AF_STAMP(1, j, 2);
 
-      // mask bits: bit c set -> key k0+c is ignored (beyond Sk or key-padding)
-      uint32_t mb0 = 0, mb1 = 0;
-      const int kvalid = p.Sk - k0;
-      if (kvalid < 64) {
-        if (kvalid <= 32) { mb1 = 0xffffffffu; mb0 = kvalid >= 32 ? 0u : (0xffffffffu << kvalid); }
-        else mb1 = 0xffffffffu << (kvalid - 32);
-      }
-      if (p.kpm && k0 + AF_BN > p.kpm_start) {
-        const uint8_t* mrow = p.kpm + static_cast<long long>(b) * p.Sk + k0;
-        const bool a0 = (lane < kvalid) && mrow[lane] != 0;
-        const bool a1 = (lane + 32 < kvalid) && mrow[lane + 32] != 0;
-        mb0 |= __ballot_sync(0xffffffffu, a0);
-        mb1 |= __ballot_sync(0xffffffffu, a1);
-      }
+      // mask bits: bit c set -> key k0+c is ignored (beyond Sk or key-padding); only tail / language tiles
+      // take the masked path (warp-uniform branch)
       float x[64];
-      float mt = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        x[c] = ((mb0 >> c) & 1u) ? -INFINITY : __uint_as_float(sr0[c]) * p.sl2;
-        x[32 + c] = ((mb1 >> c) & 1u) ? -INFINITY : __uint_as_float(sr1[c]) * p.sl2;
-        mt = fmaxf(mt, fmaxf(x[c], x[32 + c]));
+      for (int c = 0; c < 32; ++c) { x[c] = __uint_as_float(sr0[c]); x[32 + c] = __uint_as_float(sr1[c]); }
+      const int kvalid = p.Sk - k0;
+      if (kvalid < 64 || (p.kpm && k0 + AF_BN > p.kpm_start)) {
+        uint32_t mb0 = 0, mb1 = 0;
+        if (kvalid < 64) {
+          if (kvalid <= 32) { mb1 = 0xffffffffu; mb0 = kvalid >= 32 ? 0u : (0xffffffffu << kvalid); }
+          else mb1 = 0xffffffffu << (kvalid - 32);
+        }
+        if (p.kpm && k0 + AF_BN > p.kpm_start) {
+          const uint8_t* mrow = p.kpm + static_cast<long long>(b) * p.Sk + k0;
+          const bool a0 = (lane < kvalid) && mrow[lane] != 0;
+          const bool a1 = (lane + 32 < kvalid) && mrow[lane + 32] != 0;
+          mb0 |= __ballot_sync(0xffffffffu, a0);
+          mb1 |= __ballot_sync(0xffffffffu, a1);
+        }
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          if ((mb0 >> c) & 1u) x[c] = -INFINITY;
+          if ((mb1 >> c) & 1u) x[32 + c] = -INFINITY;
+        }
       }
+      float mt = x[0];
+#pragma unroll
+      for (int c = 1; c < 64; ++c) mt = fmaxf(mt, x[c]);
+      mt *= p.sl2;   // log2 domain (sl2 > 0)
       bool need = false;
       float alpha = 1.f;
       if (j == 0) {
@@ -222,22 +244,25 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         m_used = m_new;
       }
       float psum = 0.f;
+      const float neg_m = -m_used;
 #pragma unroll
       for (int c = 0; c < 64; ++c) {
-        x[c] = fast_exp2(x[c] - m_used);
+        x[c] = fast_exp2(fmaf(x[c], p.sl2, neg_m));
         psum += x[c];
       }
       l += psum;
-      if (p.drop_p > 0.f) {
+      if (DROP) {   // the 1/(1-p) scale is applied once to O in the epilogue
 #pragma unroll
         for (int c = 0; c < 64; c += 2) {
           const uint32_t hsh = drop_pairhash(drop_rh, static_cast<uint32_t>(k0 + c) >> 1);
-          x[c] = drop_keep_lo(hsh, p.drop_thresh) ? x[c] * p.drop_scale : 0.f;
-          x[c + 1] = drop_keep_hi(hsh, p.drop_thresh) ? x[c + 1] * p.drop_scale : 0.f;
+          x[c] = drop_keep_lo(hsh, p.drop_thresh) ? x[c] : 0.f;
+          x[c + 1] = drop_keep_hi(hsh, p.drop_thresh) ? x[c + 1] : 0.f;
         }
       }
+      if (warp == 2 && lane == 0) AF_STAMP(1, j, 3);
       if (j > 0) {
         mbar_wait(O_READY, (j - 1) & 1);  // PV_{j-1} retired: P buffer free, O stable
+        if (warp == 2 && lane == 0) AF_STAMP(1, j, 4);
         tc_fence_after();
         if (any_need) {
           int c = 0;
@@ -271,12 +296,13 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(P_FULL);
+      if (warp == 2 && lane == 0) AF_STAMP(1, j, 5);
     }
 
     // ---- epilogue: O / l -> bf16, heads merged; LSE (log2 domain)
     mbar_wait(O_READY, (nkv - 1) & 1);
     tc_fence_after();
-    const float inv = l > 0.f ? 1.f / l : 0.f;
+    const float inv = l > 0.f ? (DROP ? p.drop_scale : 1.f) / l : 0.f;
     const bool row_ok = q < p.Sq;
     __nv_bfloat16* orow = p.out + (static_cast<long long>(b) * p.Sq + q) * p.ldo + hd * p.dp;
     int c = 0;
@@ -342,6 +368,7 @@ extern "C" int xf_attn_fwd(const XfAttnFwd* a, xf_stream_t stream_) {
   p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
   p.ldo = a->ldo;
   p.lse = a->lse;
+  p.dbg = reinterpret_cast<long long*>(a->debug_timeline);
   p.lse_stride = a->lse_stride > 0 ? a->lse_stride : a->Sq;
   p.drop_p = a->drop_p;
   p.drop_scale = a->drop_p > 0.f ? 1.f / (1.f - a->drop_p) : 1.f;
@@ -358,11 +385,13 @@ extern "C" int xf_attn_fwd(const XfAttnFwd* a, xf_stream_t stream_) {
   const int smem_bytes = 1024 + 1024 + p.nchunk * 16384 + 4 * p.nchunk * 8192 + 16384;
   static bool attr_set = false;
   if (!attr_set) {
-    XF_CUDA(cudaFuncSetAttribute(attn_fwd_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    XF_CUDA(cudaFuncSetAttribute(attn_fwd_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    XF_CUDA(cudaFuncSetAttribute(attn_fwd_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   const int grid = a->B * a->H * p.q_tiles;
-  attn_fwd_tcgen05_kernel<<<grid, AF_THREADS, smem_bytes, stream>>>(tq, tk, tv, p);
+  if (a->drop_p > 0.f) attn_fwd_tcgen05_kernel<true><<<grid, AF_THREADS, smem_bytes, stream>>>(tq, tk, tv, p);
+  else attn_fwd_tcgen05_kernel<false><<<grid, AF_THREADS, smem_bytes, stream>>>(tq, tk, tv, p);
   g_launches.fetch_add(1);
   XF_CUDA(cudaGetLastError());
   return 0;

@@ -222,7 +222,7 @@ def attn_delta(o: torch.Tensor, d_o: torch.Tensor, delta: torch.Tensor, B: int, 
 
 def attn_fwd(q, k, v, out, lse, *, B: int, H: int, Sq: int, Sk: int, dp: int, scale: float,
              key_padding_mask: Optional[torch.Tensor] = None, kpm_start: int = 0,
-             drop_p: float = 0.0, drop_seed: int = 0, drop_stream: int = 0):
+             drop_p: float = 0.0, drop_seed: int = 0, drop_stream: int = 0, debug_timeline: Optional[torch.Tensor] = None):
     """q/k/v/out: bf16 2-D views [B*S, >=H*dp] (may be column slices of one fused qkv buffer)."""
     a = XfAttnFwd()
     a.q, a.ldq = q.data_ptr(), q.stride(0)
@@ -236,6 +236,7 @@ def attn_fwd(q, k, v, out, lse, *, B: int, H: int, Sq: int, Sk: int, dp: int, sc
             raise _lib.XfError("key_padding_mask must be uint8/bool")
         a.key_padding_mask = key_padding_mask.data_ptr()
     a.kpm_start = kpm_start
+    a.debug_timeline = debug_timeline.data_ptr() if debug_timeline is not None else None
     a.B, a.H, a.Sq, a.Sk, a.dp = B, H, Sq, Sk, dp
     a.scale = scale
     a.drop_p, a.drop_seed, a.drop_stream = drop_p, drop_seed, drop_stream
