@@ -275,7 +275,7 @@ struct LnBwdParams {
 constexpr int LNB_ROWS = 32;  // rows per CTA pass
 
 template <int NV>
-__global__ void __launch_bounds__(256, 3) layernorm_bwd_kernel(const LnBwdParams p) {
+__global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const LnBwdParams p) {
   const int warps_per_cta = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -353,33 +353,44 @@ __global__ void __launch_bounds__(256, 3) layernorm_bwd_kernel(const LnBwdParams
       if (col < p.D) {
         float4 gm = make_float4(0.f, 0.f, 0.f, 0.f);
         (void)gm;
-        for (int r = base; r < rend; ++r) {
-          const long long irow = remap_row(r, p.in_rows_in, p.in_rows_out, p.in_row_off);
-          const long long orow = remap_row(r, p.out_rows_in, p.out_rows_out, p.out_row_off);
-          const float mean = p.mean[r], rstd = p.rstd[r];
-          const uint2 qx = *reinterpret_cast<const uint2*>(p.x + irow * p.ldx + col);
-          const uint2 qd = *reinterpret_cast<const uint2*>(p.dy + orow * p.lddy + col);
-          float xv[4] = {bf16_lo(qx.x), bf16_hi(qx.x), bf16_lo(qx.y), bf16_hi(qx.y)};
-          float dv[4] = {bf16_lo(qd.x), bf16_hi(qd.x), bf16_lo(qd.y), bf16_hi(qd.y)};
-          if (p.dy_drop_p > 0.f) {
-            const uint32_t rh = drop_rowhash(p.dy_seed, static_cast<uint64_t>(orow));
+        for (int rb = base; rb < rend; rb += 4) {   // 4 rows (12 independent 64-bit loads) in flight per thread
+          uint2 qx[4], qd[4], qo[4];
+          float mean[4], rstd[4];
+          long long orow[4];
 #pragma unroll
-            for (int k = 0; k < 4; k += 2) {
-              const uint32_t h = drop_pairhash(rh, static_cast<uint32_t>(col + k) >> 1);
-              dv[k] = drop_keep_lo(h, p.dy_thresh) ? dv[k] * p.dy_scale : 0.f;
-              dv[k + 1] = drop_keep_hi(h, p.dy_thresh) ? dv[k + 1] * p.dy_scale : 0.f;
+          for (int u = 0; u < 4; ++u) {
+            const int r = min(rb + u, rend - 1);
+            const long long irow = remap_row(r, p.in_rows_in, p.in_rows_out, p.in_row_off);
+            orow[u] = remap_row(r, p.out_rows_in, p.out_rows_out, p.out_row_off);
+            mean[u] = p.mean[r]; rstd[u] = p.rstd[r];
+            qx[u] = *reinterpret_cast<const uint2*>(p.x + irow * p.ldx + col);
+            qd[u] = *reinterpret_cast<const uint2*>(p.dy + orow[u] * p.lddy + col);
+            if (p.dbias) qo[u] = *reinterpret_cast<const uint2*>((p.dx2 ? p.dx2 : p.dx) + irow * p.lddx + col);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (rb + u < rend) {
+              float xv[4] = {bf16_lo(qx[u].x), bf16_hi(qx[u].x), bf16_lo(qx[u].y), bf16_hi(qx[u].y)};
+              float dv[4] = {bf16_lo(qd[u].x), bf16_hi(qd[u].x), bf16_lo(qd[u].y), bf16_hi(qd[u].y)};
+              if (p.dy_drop_p > 0.f) {
+                const uint32_t rh = drop_rowhash(p.dy_seed, static_cast<uint64_t>(orow[u]));
+#pragma unroll
+                for (int k = 0; k < 4; k += 2) {
+                  const uint32_t h = drop_pairhash(rh, static_cast<uint32_t>(col + k) >> 1);
+                  dv[k] = drop_keep_lo(h, p.dy_thresh) ? dv[k] * p.dy_scale : 0.f;
+                  dv[k + 1] = drop_keep_hi(h, p.dy_thresh) ? dv[k + 1] * p.dy_scale : 0.f;
+                }
+              }
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                cg[j][k] += dv[k] * (xv[k] - mean[u]) * rstd[u];
+                cb[j][k] += dv[k];
+              }
+              if (p.dbias) {
+                cbias[j][0] += bf16_lo(qo[u].x); cbias[j][1] += bf16_hi(qo[u].x);
+                cbias[j][2] += bf16_lo(qo[u].y); cbias[j][3] += bf16_hi(qo[u].y);
+              }
             }
-          }
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            cg[j][k] += dv[k] * (xv[k] - mean) * rstd;
-            cb[j][k] += dv[k];
-          }
-          if (p.dbias) {
-            const __nv_bfloat16* src = (p.dx2 ? p.dx2 : p.dx) + irow * p.lddx + col;
-            const uint2 qo = *reinterpret_cast<const uint2*>(src);
-            cbias[j][0] += bf16_lo(qo.x); cbias[j][1] += bf16_hi(qo.x);
-            cbias[j][2] += bf16_lo(qo.y); cbias[j][3] += bf16_hi(qo.y);
           }
         }
       }
@@ -403,32 +414,42 @@ __global__ void __launch_bounds__(256, 3) layernorm_bwd_kernel(const LnBwdParams
 // ------------------------------------------------------------------------------------------
 // column sums: out[n] += sum_m x[m, n]  (bias gradients of in_proj and linear1)
 // ------------------------------------------------------------------------------------------
+// CTA = 64 column-vectors (512 columns) x 4 row lanes; each thread keeps 4 independent 128-bit loads in
+// flight; the 4 row lanes are combined through shared memory, then one atomic per column per CTA.
 __global__ void __launch_bounds__(256)
 colsum_kernel(const __nv_bfloat16* __restrict__ x, long long ld, int rows, int cols, int rows_per_cta, float* __restrict__ out) {
-  const int vc = blockIdx.x * blockDim.x + threadIdx.x;  // 8-column vector index
-  if (vc * 8 >= cols) return;
+  __shared__ float red[4][64 * 8 + 8];
+  const int vl = threadIdx.x & 63, rl = threadIdx.x >> 6;
+  const int vc = blockIdx.x * 64 + vl;  // 8-column vector index
+  const bool active = vc * 8 < cols;
   const int r0 = blockIdx.y * rows_per_cta;
   const int r1 = min(rows, r0 + rows_per_cta);
   float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  int r = r0;
-  for (; r + 4 <= r1; r += 4) {   // 4 independent 128-bit loads in flight per thread
-    uint4 q[4];
+  if (active) {
+    int r = r0 + rl;
+    for (; r + 12 < r1; r += 16) {
+      uint4 q[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) q[u] = __ldg(reinterpret_cast<const uint4*>(x + static_cast<long long>(r + u) * ld) + vc);
+      for (int u = 0; u < 4; ++u) q[u] = __ldg(reinterpret_cast<const uint4*>(x + static_cast<long long>(r + 4 * u) * ld) + vc);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      s[0] += bf16_lo(q[u].x); s[1] += bf16_hi(q[u].x); s[2] += bf16_lo(q[u].y); s[3] += bf16_hi(q[u].y);
-      s[4] += bf16_lo(q[u].z); s[5] += bf16_hi(q[u].z); s[6] += bf16_lo(q[u].w); s[7] += bf16_hi(q[u].w);
+      for (int u = 0; u < 4; ++u) {
+        s[0] += bf16_lo(q[u].x); s[1] += bf16_hi(q[u].x); s[2] += bf16_lo(q[u].y); s[3] += bf16_hi(q[u].y);
+        s[4] += bf16_lo(q[u].z); s[5] += bf16_hi(q[u].z); s[6] += bf16_lo(q[u].w); s[7] += bf16_hi(q[u].w);
+      }
+    }
+    for (; r < r1; r += 4) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(x + static_cast<long long>(r) * ld) + vc);
+      s[0] += bf16_lo(q.x); s[1] += bf16_hi(q.x); s[2] += bf16_lo(q.y); s[3] += bf16_hi(q.y);
+      s[4] += bf16_lo(q.z); s[5] += bf16_hi(q.z); s[6] += bf16_lo(q.w); s[7] += bf16_hi(q.w);
     }
   }
-  for (; r < r1; ++r) {
-    const uint4 q = __ldg(reinterpret_cast<const uint4*>(x + static_cast<long long>(r) * ld) + vc);
-    s[0] += bf16_lo(q.x); s[1] += bf16_hi(q.x); s[2] += bf16_lo(q.y); s[3] += bf16_hi(q.y);
-    s[4] += bf16_lo(q.z); s[5] += bf16_hi(q.z); s[6] += bf16_lo(q.w); s[7] += bf16_hi(q.w);
-  }
 #pragma unroll
-  for (int k = 0; k < 8; ++k)
-    if (vc * 8 + k < cols) atomicAdd(out + vc * 8 + k, s[k]);
+  for (int k = 0; k < 8; ++k) red[rl][vl * 8 + k] = s[k];
+  __syncthreads();
+  for (int c = threadIdx.x; c < 512; c += 256) {
+    const int col = blockIdx.x * 512 + c;
+    if (col < cols) atomicAdd(out + col, red[0][c] + red[1][c] + red[2][c] + red[3][c]);
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -650,7 +671,7 @@ extern "C" int xf_layernorm_bwd(const XfLayerNormBwd* a, xf_stream_t s) {
   p.dx2_thresh = drop_thresh16(a->dx2_drop_p);
   p.dx2_scale = a->dx2_drop_p > 0.f ? 1.f / (1.f - a->dx2_drop_p) : 1.f;
   int ctas = (a->rows + LNB_ROWS - 1) / LNB_ROWS;
-  if (ctas > 3 * sm_count()) ctas = 3 * sm_count();
+  if (ctas > 4 * sm_count()) ctas = 4 * sm_count();
   if (ctas < 1) ctas = 1;
   const int nv = (a->D / 8 + 31) / 32;
   const size_t sh = 0;
@@ -670,9 +691,10 @@ extern "C" int xf_colsum(const void* x, int64_t ld, int rows, int cols, float* o
   if (cols % 8 || ld % 8) return fail(-2, "xf_colsum: cols and ld must be multiples of 8");
   if (rows == 0) return 0;
   const int vcols = cols / 8;
-  const int gx = (vcols + 255) / 256;
-  int gy = (2 * sm_count() + gx - 1) / gx;
-  if (gy > rows) gy = rows;
+  const int gx = (vcols + 63) / 64;
+  int gy = (4 * sm_count() + gx - 1) / gx;
+  if (gy * 16 > rows) gy = (rows + 15) / 16;
+  if (gy < 1) gy = 1;
   const int rows_per_cta = (rows + gy - 1) / gy;
   gy = (rows + rows_per_cta - 1) / rows_per_cta;
   colsum_kernel<<<dim3(gx, gy), 256, 0, reinterpret_cast<cudaStream_t>(s)>>>(reinterpret_cast<const __nv_bfloat16*>(x), ld, rows, cols,
