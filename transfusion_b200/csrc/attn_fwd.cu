@@ -10,10 +10,13 @@
 //                           O  += P_j V_j  (tcgen05, M=128, N=dp,  K=64)  -> TMEM O
 //   warps 2-5 softmax     : one thread per query row (TMEM lane): tcgen05.ld the S row, key-padding /
 //                           tail mask, running max / sum in registers (log2 domain, lazy rescale of
-//                           O in TMEM only when the max grows by > 2^8), dropout on P, P -> bf16 ->
-//                           SWIZZLE_128B shared memory as the A operand of the PV MMA; final
-//                           O / l -> bf16 -> global (heads merged), LSE saved for backward.
+//                           O in TMEM only when the max grows by > 2^8), dropout on P, P -> packed bf16 ->
+//                           tcgen05.st back into the S buffer's TMEM columns; final O / l -> bf16 ->
+//                           global (heads merged), LSE saved for backward.
 // S is double-buffered in TMEM so QK^T of tile j+1 overlaps the softmax of tile j.
+// Both A operands live in TENSOR MEMORY (".ts" MMAs): Q is copied once from shared memory with tcgen05.cp
+// (dp/2 columns) and P never touches shared memory.  A 64-key tile then moves 112 KB through shared memory
+// (TMA writes + K and V operand reads) instead of 200 KB — the SS form was shared-memory-bandwidth bound.
 //
 // Shared memory (1024-byte aligned atoms, SWIZZLE_128B, 64-column chunks written by TMA):
 //   Q : nchunk x [128 rows x 128 B]      K-major A operand of S
@@ -61,7 +64,6 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
   uint8_t* sQ = smem + 1024;
   uint8_t* sK = sQ + q_bytes;
   uint8_t* sV = sK + 2 * kv_bytes;
-  uint8_t* sP = sV + 2 * kv_bytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(bars);
@@ -107,6 +109,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
   const uint32_t tmem_base = *tmem_ptr_smem;
   const uint32_t tmem_S = tmem_base;         // 2 x 64 columns
   const uint32_t tmem_O = tmem_base + 128;   // dp columns
+  const uint32_t tmem_Q = tmem_base + 384;   // dp/2 columns: Q as packed bf16 (A operand of the score MMA)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -136,31 +139,35 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       const uint64_t dk = make_smem_desc(0, 16, 1024);       // K-major SWIZZLE_128B template
       const uint64_t dmn = make_smem_desc(0, 8192, 1024);    // MN-major template (V)
       const uint32_t hi_k = desc_hi(dk), hi_mn = desc_hi(dmn);
-      const uint32_t q_lo = desc_lo(dk) + (smem_u32(sQ) >> 4), p_lo = desc_lo(dk) + (smem_u32(sP) >> 4);
       const uint32_t k_base = smem_u32(sK) >> 4, v_base = smem_u32(sV) >> 4, kv_lo = kv_bytes >> 4;
       auto issue_s = [&](int j) {
         const int st = j & 1, sb = j & 1;
         AF_STAMP(0, j, 0);
         mbar_wait(K_FULL(st), (j >> 1) & 1);
         AF_STAMP(0, j, 1);
-        mbar_wait(S_EMPTY(sb), ((j >> 1) & 1) ^ 1);
+        // S buffer sb last held P_{j-2}, consumed by PV_{j-2}: already issued by this thread, and the tensor pipe
+        // runs in issue order, so no barrier is needed before overwriting it
         AF_STAMP(0, j, 2);
         tc_fence_after();
         const uint32_t k_lo = desc_lo(dk) + k_base + st * kv_lo;
-        // pair jp covers head-dim columns [32 jp, 32 jp + 32): chunk jp >> 1, half jp & 1
-        for (int jp = 0; jp < npairs; ++jp) {
-          const uint32_t ao = (jp >> 1) * 1024 + (jp & 1) * 4, bo = (jp >> 1) * 512 + (jp & 1) * 4;
-          umma_k2(tmem_S + sb * AF_BN, hi_k, q_lo + ao, 2, hi_k, k_lo + bo, 2, idesc_s, jp != 0);
-        }
+        // pair jp covers head-dim columns [32 jp, 32 jp + 32): K chunk jp >> 1, half jp & 1; Q slice columns 16 jp
+        for (int jp = 0; jp < npairs; ++jp)
+          umma_ts_k2(tmem_S + sb * AF_BN, tmem_Q + 16 * jp, hi_k, k_lo + (jp >> 1) * 512 + (jp & 1) * 4, 2, idesc_s, jp != 0);
         umma_commit(S_FULL(sb));
         umma_commit(K_EMPTY(st));
         AF_STAMP(0, j, 3);
       };
       mbar_wait(Q_FULL, 0);
+      tc_fence_after();
+      {  // Q: shared memory -> TMEM, one 128 x 32 B slice per k-step
+        const uint32_t qa = smem_u32(sQ);
+        for (int kk = 0; kk < p.dp / 16; ++kk)
+          tmem_cp_128x256b(tmem_Q + 8 * kk, make_smem_desc(qa + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024));
+      }
       issue_s(0);
       for (int j = 0; j < nkv; ++j) {
         if (j + 1 < nkv) issue_s(j + 1);
-        const int st = j & 1;
+        const int st = j & 1, sb = j & 1;
         AF_STAMP(0, j, 4);
         mbar_wait(P_FULL, j & 1);
         AF_STAMP(0, j, 5);
@@ -168,7 +175,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         AF_STAMP(0, j, 6);
         tc_fence_after();
         const uint32_t v_lo = desc_lo(dmn) + v_base + st * kv_lo;
-        umma_k4(tmem_O, hi_k, p_lo, 2, hi_mn, v_lo, 128, idesc_o, j != 0);
+        umma_ts_k4(tmem_O, tmem_S + sb * AF_BN, hi_mn, v_lo, 128, idesc_o, j != 0);   // A = P_j (TMEM, 32 columns)
         umma_commit(V_EMPTY(st));
         umma_commit(O_READY);
         AF_STAMP(0, j, 7);
@@ -182,7 +189,6 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
     float m_used = 0.f, l = 0.f;
     const uint32_t drop_rh = DROP ? drop_rowhash(p.drop_seed, static_cast<uint64_t>(b * p.H + hd) * p.Sq + q) : 0u;
-    uint8_t* prow = sP + r * 128;
 
     for (int j = 0; j < nkv; ++j) {
       const int sb = j & 1;
@@ -195,9 +201,6 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       tmem_ld32(tmem_S + lane_sel + sb * AF_BN, sr0);
       tmem_ld32(tmem_S + lane_sel + sb * AF_BN + 32, sr1);
       tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(S_EMPTY(sb));
       if (warp == 2 && lane == 0) AF_STAMP(1, j, 2);
 
       // mask bits: bit c set -> key k0+c is ignored (beyond Sk or key-padding); only tail / language tiles
@@ -260,11 +263,13 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         }
       }
       if (warp == 2 && lane == 0) AF_STAMP(1, j, 3);
-      if (j > 0) {
-        mbar_wait(O_READY, (j - 1) & 1);  // PV_{j-1} retired: P buffer free, O stable
+      if (j > 0 && any_need) {
+        // O may only be rescaled once PV_{j-1} has retired.  (Waiting only in this case is safe: the barrier can be
+        // at most one phase ahead of j-1, because PV_j needs this warp's P_FULL arrival.)
+        mbar_wait(O_READY, (j - 1) & 1);
         if (warp == 2 && lane == 0) AF_STAMP(1, j, 4);
         tc_fence_after();
-        if (any_need) {
+        {
           int c = 0;
           for (; c + 32 <= p.dp; c += 32) {
             uint32_t o[32];
@@ -285,14 +290,14 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
           tmem_st_wait();
         }
       }
-      // P row -> shared memory, K-major SWIZZLE_128B: 16-byte segment s of row r lands at s ^ (r & 7)
+      // P row -> TMEM (packed bf16, key 2c in the low half of column c) over the first 32 columns of this S buffer
+      {
+        uint32_t pk[32];
 #pragma unroll
-      for (int sgm = 0; sgm < 8; ++sgm) {
-        const uint4 v = make_uint4(pack_bf16(x[8 * sgm], x[8 * sgm + 1]), pack_bf16(x[8 * sgm + 2], x[8 * sgm + 3]),
-                                   pack_bf16(x[8 * sgm + 4], x[8 * sgm + 5]), pack_bf16(x[8 * sgm + 6], x[8 * sgm + 7]));
-        *reinterpret_cast<uint4*>(prow + ((sgm ^ (r & 7)) << 4)) = v;
+        for (int c = 0; c < 32; ++c) pk[c] = pack_bf16(x[2 * c], x[2 * c + 1]);
+        tmem_st32(tmem_S + lane_sel + sb * AF_BN, pk);
+        tmem_st_wait();
       }
-      fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(P_FULL);
@@ -382,7 +387,7 @@ extern "C" int xf_attn_fwd(const XfAttnFwd* a, xf_stream_t stream_) {
   if ((rc = make_tmap_3d_bf16(&tk, a->k, a->B, a->Sk, cols, a->ldk, 64, AF_BN))) return rc;
   if ((rc = make_tmap_3d_bf16(&tv, a->v, a->B, a->Sk, cols, a->ldv, 64, AF_BN))) return rc;
 
-  const int smem_bytes = 1024 + 1024 + p.nchunk * 16384 + 4 * p.nchunk * 8192 + 16384;
+  const int smem_bytes = 1024 + 1024 + p.nchunk * 16384 + 4 * p.nchunk * 8192;
   static bool attr_set = false;
   if (!attr_set) {
     XF_CUDA(cudaFuncSetAttribute(attn_fwd_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

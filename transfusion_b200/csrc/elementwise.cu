@@ -121,19 +121,25 @@ __global__ void lang_rows_fwd_kernel(const float* __restrict__ lang, const float
   }
 }
 
-__global__ void lang_rows_bwd_kernel(const __nv_bfloat16* __restrict__ dz, float* __restrict__ dlang,
-                                     float* __restrict__ dkind, int B, int L, int D, int n, int S) {
-  // one thread per column pair; loops over all (b, j) rows (B*L is small)
+// grid.x: blocks of 128 column pairs, grid.y: chunks of rows; every (row, column pair) has one owner thread, the
+// kind-embedding gradient is reduced per thread over its row chunk, then one atomic pair per thread.
+__global__ void __launch_bounds__(128)
+lang_rows_bwd_kernel(const __nv_bfloat16* __restrict__ dz, float* __restrict__ dlang, float* __restrict__ dkind, int B, int L,
+                     int D, int n, int S, int rows_per_cta) {
   const int e2 = blockIdx.x * blockDim.x + threadIdx.x;
   if (e2 >= D / 2) return;
+  const int r0 = blockIdx.y * rows_per_cta;
+  const int r1 = min(B * L, r0 + rows_per_cta);
   float s0 = 0.f, s1 = 0.f;
-  for (int r = blockIdx.y; r < B * L; r += gridDim.y) {
+  for (int r = r0; r < r1; ++r) {
     const int j = r % L, b = r / L;
     const uint32_t q = *reinterpret_cast<const uint32_t*>(dz + (static_cast<long long>(b) * S + n + j) * D + 2 * e2);
     const float g0 = bf16_lo(q), g1 = bf16_hi(q);
     if (dlang) {
-      float* d = dlang + static_cast<long long>(r) * D + 2 * e2;
-      d[0] += g0; d[1] += g1;
+      float2* d = reinterpret_cast<float2*>(dlang + static_cast<long long>(r) * D + 2 * e2);
+      float2 cur = *d;
+      cur.x += g0; cur.y += g1;
+      *d = cur;
     }
     s0 += g0; s1 += g1;
   }
@@ -610,9 +616,14 @@ extern "C" int xf_lang_rows_bwd(const void* dz, float* dlang, float* dkind, int 
   if (!dz || !dkind) return fail(-1, "xf_lang_rows_bwd: null pointer");
   if (D % 2) return fail(-2, "xf_lang_rows_bwd: D must be even");
   if (B * L == 0) return 0;
-  // gridDim.y = 1 when dlang is written (each (row, col) must be owned by exactly one thread)
-  dim3 grid((D / 2 + 127) / 128, 1);
-  lang_rows_bwd_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(s)>>>(reinterpret_cast<const __nv_bfloat16*>(dz), dlang, dkind, B, L, D, n, S);
+  const int rows = B * L;
+  const int gx = (D / 2 + 127) / 128;
+  int gy = (2 * sm_count() + gx - 1) / gx;
+  if (gy > rows) gy = rows;
+  const int rows_per_cta = (rows + gy - 1) / gy;
+  gy = (rows + rows_per_cta - 1) / rows_per_cta;
+  lang_rows_bwd_kernel<<<dim3(gx, gy), 128, 0, reinterpret_cast<cudaStream_t>(s)>>>(reinterpret_cast<const __nv_bfloat16*>(dz), dlang, dkind,
+                                                                                B, L, D, n, S, rows_per_cta);
   g_launches.fetch_add(1);
   XF_CUDA(cudaGetLastError());
   return 0;

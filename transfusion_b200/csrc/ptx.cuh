@@ -193,6 +193,34 @@ __device__ __forceinline__ void umma_k4_cg2(uint32_t d_tmem, uint32_t a_hi, uint
                  "r"(accumulate_first)
                : "memory");
 }
+// A operand from TMEM (".ts" form): 128 lanes x 8 columns per K = 16 slice (bf16 packed two per column, element
+// 2c in the low half; verified by tools/microbench/ts_mma_test.cu).  Saves the 4 KB shared-memory read of A per MMA.
+#define XF_UMMA_TS_BODY                                                                           \
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 db;\n\t.reg .b32 at, bl;\n\t"                             \
+      "setp.ne.b32 p, %6, 0;\n\t"                                                                 \
+      "setp.eq.b32 q, 0, 0;\n\t"                                                                  \
+      "mov.b64 db, {%3, %2};\n\t"                                                                 \
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %5, p;\n\t"                             \
+      "add.u32 at, %1, 8;\n\tadd.u32 bl, %3, %4;\n\tmov.b64 db, {bl, %2};\n\t"                    \
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [at], db, %5, q;\n\t"
+#define XF_UMMA_TS_MORE                                                                           \
+      "add.u32 at, at, 8;\n\tadd.u32 bl, bl, %4;\n\tmov.b64 db, {bl, %2};\n\t"                    \
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [at], db, %5, q;\n\t"
+__device__ __forceinline__ void umma_ts_k2(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_hi, uint32_t b_lo, uint32_t b_step,
+                                           uint32_t idesc, uint32_t accumulate_first) {
+  asm volatile(XF_UMMA_TS_BODY "}\n" ::"r"(d_tmem), "r"(a_tmem), "r"(b_hi), "r"(b_lo), "r"(b_step), "r"(idesc),
+               "r"(accumulate_first) : "memory");
+}
+__device__ __forceinline__ void umma_ts_k4(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_hi, uint32_t b_lo, uint32_t b_step,
+                                           uint32_t idesc, uint32_t accumulate_first) {
+  asm volatile(XF_UMMA_TS_BODY XF_UMMA_TS_MORE XF_UMMA_TS_MORE "}\n" ::"r"(d_tmem), "r"(a_tmem), "r"(b_hi), "r"(b_lo),
+               "r"(b_step), "r"(idesc), "r"(accumulate_first) : "memory");
+}
+// shared memory (UMMA descriptor, 128 rows x 32 B) -> TMEM (128 lanes x 8 columns); ordered with later tcgen05.mma
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+}
+
 __device__ __forceinline__ uint32_t desc_hi(uint64_t d) { return static_cast<uint32_t>(d >> 32); }
 __device__ __forceinline__ uint32_t desc_lo(uint64_t d) { return static_cast<uint32_t>(d); }
 

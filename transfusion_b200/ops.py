@@ -147,13 +147,15 @@ def lang_rows_fwd(lang: torch.Tensor, kind: torch.Tensor, z: torch.Tensor, n: in
     B, L, D = lang.shape
     S = z.shape[1]
     _req(lang, torch.float32, "lang"); _req(kind, torch.float32, "kind"); _req(z, torch.bfloat16, "z")
-    check(lib().xf_lang_rows_fwd(_ptr(lang), _ptr(kind), _ptr(z), B, L, D, n, S, _stream()), "xf_lang_rows_fwd")
+    with _Prof("lang_rows", 0.0, 6.0 * B * L * D):
+        check(lib().xf_lang_rows_fwd(_ptr(lang), _ptr(kind), _ptr(z), B, L, D, n, S, _stream()), "xf_lang_rows_fwd")
 
 
 def lang_rows_bwd(dz: torch.Tensor, dlang: Optional[torch.Tensor], dkind: torch.Tensor, B: int, L: int, n: int):
     S, D = dz.shape[1], dz.shape[2]
     _req(dz, torch.bfloat16, "dz"); _req(dkind, torch.float32, "dkind")
-    check(lib().xf_lang_rows_bwd(_ptr(dz), _ptr(dlang), _ptr(dkind), B, L, D, n, S, _stream()), "xf_lang_rows_bwd")
+    with _Prof("lang_rows", 0.0, 10.0 * B * L * D):
+        check(lib().xf_lang_rows_bwd(_ptr(dz), _ptr(dlang), _ptr(dkind), B, L, D, n, S, _stream()), "xf_lang_rows_bwd")
 
 
 def layernorm_fwd(x, y, gamma, beta, mean, rstd, rows: int, D: int, *, in_map=(0, 0, 0), out_map=(0, 0, 0),
@@ -208,7 +210,8 @@ def cast_pad(src: torch.Tensor, dst: torch.Tensor, rows: int, cols: int, rin=0, 
 
 def unpad_add(src: torch.Tensor, dst: torch.Tensor, rows: int, cols: int, rin=0, rout=0, cin=0, cout=0):
     _req(src, torch.float32, "src"); _req(dst, torch.float32, "dst")
-    check(lib().xf_unpad_add(_ptr(src), C.c_int64(src.stride(0) if src.dim() > 1 else cols), _ptr(dst),
+    with _Prof("cast", 0.0, 12.0 * rows * cols):
+      check(lib().xf_unpad_add(_ptr(src), C.c_int64(src.stride(0) if src.dim() > 1 else cols), _ptr(dst),
                              C.c_int64(dst.stride(0) if dst.dim() > 1 else cols), rows, cols, rin, rout, cin, cout, _stream()),
           "xf_unpad_add")
 
