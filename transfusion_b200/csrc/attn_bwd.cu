@@ -19,7 +19,7 @@
 // 3-stage ring of streamed tiles.  All tiles use 32-column (64-byte) chunks with SWIZZLE_64B so a
 // 224-wide head needs exactly 7 chunks (no padding to 256), which is what lets the 3-stage ring fit.
 //
-// CTA = 192 threads: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 element-wise + epilogue.
+// CTA = 192 threads: warps 0-3 element-wise + epilogue, warp 4 TMA producer, warp 5 MMA issuer.
 #include <string.h>
 
 #include "../../include/xfusion.h"
@@ -97,7 +97,7 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gri
     mbar_init(ACC_DONE, 1);
     fence_mbar_init();
   }
-  if (warp == 1) {
+  if (warp == 5) {
     tmem_alloc(smem_u32(tmem_ptr_smem), 512);
     tmem_relinquish();
   }
@@ -109,7 +109,9 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gri
   const uint32_t tmem_acc1 = tmem_base + p.dp;                       // DKV only
   const uint32_t tmem_C = tmem_base + (DKV ? 2 : 1) * p.dp;          // ncbuf x (C1: 32 | C2: 32)
 
-  if (warp == 0) {
+  // warps 0-3: element-wise stage (TMEM lane quadrant = warp id); warp 4: TMA producer; warp 5: MMA issuer
+  // (highest ids: the scheduler favours them over the ALU-heavy element-wise warps)
+  if (warp == 4) {
     if (lane == 0) {
       const int col0 = hd * p.dp;
       mbar_expect_tx(R_FULL, 2 * r_bytes);
@@ -128,7 +130,7 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gri
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 5) {
     if (lane == 0) {
       // The score MMAs are N = 32: the tensor pipe retires one every ~46 cycles (measured), so this thread
       // must issue them with a handful of instructions each: descriptors are built once (only the
@@ -228,9 +230,9 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gri
         const int qvalid = p.Sq - t0;   // columns >= qvalid are beyond the sequence
         badbits = (!row_valid) ? 0xffffffffu : (qvalid >= 32 ? 0u : (0xffffffffu << (qvalid < 0 ? 0 : qvalid)));
       }
-      if (warp == 2 && lane == 0) AB_STAMP(1, i, 0);
+      if (warp == 0 && lane == 0) AB_STAMP(1, i, 0);
       mbar_wait(C_FULL(cb), (i / p.ncbuf) & 1);
-      if (warp == 2 && lane == 0) AB_STAMP(1, i, 1);
+      if (warp == 0 && lane == 0) AB_STAMP(1, i, 1);
       tc_fence_after();
       uint32_t c1[32], c2[32];
       tmem_ld32(tmem_C + lane_sel + cb * 64, c1);
@@ -239,7 +241,7 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gri
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(C_EMPTY(cb));
-      if (warp == 2 && lane == 0) AB_STAMP(1, i, 2);
+      if (warp == 0 && lane == 0) AB_STAMP(1, i, 2);
 
       float e1[32], e2[32];
       if (!DKV) {
@@ -274,9 +276,9 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gri
           e2[c] = pr * (dpv - ds[c]) * sc;
         }
       }
-      if (warp == 2 && lane == 0) AB_STAMP(1, i, 3);
+      if (warp == 0 && lane == 0) AB_STAMP(1, i, 3);
       if (i > 0) mbar_wait(E_EMPTY, (i - 1) & 1);
-      if (warp == 2 && lane == 0) AB_STAMP(1, i, 4);
+      if (warp == 0 && lane == 0) AB_STAMP(1, i, 4);
 #pragma unroll
       for (int sgm = 0; sgm < 4; ++sgm) {
         const uint32_t off = (static_cast<uint32_t>(sgm) ^ swz) << 4;
@@ -291,7 +293,7 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gri
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(E_FULL);
-      if (warp == 2 && lane == 0) AB_STAMP(1, i, 5);
+      if (warp == 0 && lane == 0) AB_STAMP(1, i, 5);
     }
 
     // ---- epilogue: accumulators -> bf16 -> global (token-major, heads merged)
@@ -321,7 +323,7 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gri
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 5) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }

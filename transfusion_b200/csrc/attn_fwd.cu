@@ -5,10 +5,10 @@
 // General Lq != Lk (the QKVEncoder-style cross-attention of cross_qkv_layers.py:70-77 is the same op).
 //
 // One CTA per (batch, head, 128-query tile); 192 threads:
-//   warp 0    TMA producer: Q tile once, then K_j / V_j tiles (64 keys) into 2-stage rings
-//   warp 1    MMA issuer  : S_j = Q K_j^T  (tcgen05, M=128, N=64,  K=dp)  -> TMEM S[j&1]
+//   warp 4    TMA producer: Q tile once, then K_j / V_j tiles (64 keys) into 2-stage rings
+//   warp 5    MMA issuer  : S_j = Q K_j^T  (tcgen05, M=128, N=64,  K=dp)  -> TMEM S[j&1]
 //                           O  += P_j V_j  (tcgen05, M=128, N=dp,  K=64)  -> TMEM O
-//   warps 2-5 softmax     : one thread per query row (TMEM lane): tcgen05.ld the S row, key-padding /
+//   warps 0-3 softmax     : one thread per query row (TMEM lane): tcgen05.ld the S row, key-padding /
 //                           tail mask, running max / sum in registers (log2 domain, lazy rescale of
 //                           O in TMEM only when the max grows by > 2^8), dropout on P, P -> packed bf16 ->
 //                           tcgen05.st back into the S buffer's TMEM columns; final O / l -> bf16 ->
@@ -99,7 +99,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     mbar_init(O_READY, 1);
     fence_mbar_init();
   }
-  if (warp == 1) {
+  if (warp == 5) {
     tmem_alloc(smem_u32(tmem_ptr_smem), 512);
     tmem_relinquish();
   }
@@ -111,7 +111,9 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
   const uint32_t tmem_O = tmem_base + 128;   // dp columns
   const uint32_t tmem_Q = tmem_base + 384;   // dp/2 columns: Q as packed bf16 (A operand of the score MMA)
 
-  if (warp == 0) {
+  // warps 0-3: softmax (TMEM lane quadrant = warp id); warp 4: TMA producer; warp 5: MMA issuer.  The scheduler
+  // favours higher warp ids, so the single-thread roles must not sit below the ALU-heavy softmax warps.
+  if (warp == 4) {
     if (lane == 0) {
       const int col0 = hd * p.dp;
       mbar_expect_tx(Q_FULL, q_bytes);
@@ -129,7 +131,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
           tma_load_3d(smem_u32(sV + st * kv_bytes + c * 8192), &tmap_v, V_FULL(st), col0 + 64 * c, j * AF_BN, b);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 5) {
     if (lane == 0) {
       // descriptors are built once; only the start-address word changes per MMA, and a 64-column chunk's
       // k-steps are issued from one asm block (issue-rate matters for the N = 64 score MMAs)
@@ -193,15 +195,15 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
     for (int j = 0; j < nkv; ++j) {
       const int sb = j & 1;
       const int k0 = j * AF_BN;
-      if (warp == 2 && lane == 0) AF_STAMP(1, j, 0);
+      if (warp == 0 && lane == 0) AF_STAMP(1, j, 0);
       mbar_wait(S_FULL(sb), (j >> 1) & 1);
-      if (warp == 2 && lane == 0) AF_STAMP(1, j, 1);
+      if (warp == 0 && lane == 0) AF_STAMP(1, j, 1);
       tc_fence_after();
       uint32_t sr0[32], sr1[32];
       tmem_ld32(tmem_S + lane_sel + sb * AF_BN, sr0);
       tmem_ld32(tmem_S + lane_sel + sb * AF_BN + 32, sr1);
       tmem_ld_wait();
-      if (warp == 2 && lane == 0) AF_STAMP(1, j, 2);
+      if (warp == 0 && lane == 0) AF_STAMP(1, j, 2);
 
       // mask bits: bit c set -> key k0+c is ignored (beyond Sk or key-padding); only tail / language tiles
       // take the masked path (warp-uniform branch)
@@ -262,12 +264,12 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
           x[c + 1] = drop_keep_hi(hsh, p.drop_thresh) ? x[c + 1] : 0.f;
         }
       }
-      if (warp == 2 && lane == 0) AF_STAMP(1, j, 3);
+      if (warp == 0 && lane == 0) AF_STAMP(1, j, 3);
       if (j > 0 && any_need) {
         // O may only be rescaled once PV_{j-1} has retired.  (Waiting only in this case is safe: the barrier can be
         // at most one phase ahead of j-1, because PV_j needs this warp's P_FULL arrival.)
         mbar_wait(O_READY, (j - 1) & 1);
-        if (warp == 2 && lane == 0) AF_STAMP(1, j, 4);
+        if (warp == 0 && lane == 0) AF_STAMP(1, j, 4);
         tc_fence_after();
         {
           int c = 0;
@@ -301,7 +303,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(P_FULL);
-      if (warp == 2 && lane == 0) AF_STAMP(1, j, 5);
+      if (warp == 0 && lane == 0) AF_STAMP(1, j, 5);
     }
 
     // ---- epilogue: O / l -> bf16, heads merged; LSE (log2 domain)
@@ -346,7 +348,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 5) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
