@@ -396,13 +396,13 @@ def bwd_timeline(drop=0.15):
     delta = torch.empty(B, H, Sp, device=dev)
     ops.attn_delta(out, dout, delta, B, S, H, d)
     dqkv = torch.empty(B * S, 3 * D, device=dev, dtype=torch.bfloat16)
-    dbg = torch.zeros(2, 2, 64, 8, dtype=torch.int64, device=dev)
+    dbg = torch.zeros(3, 2, 64, 8, dtype=torch.int64, device=dev)
     for it in range(2):
         ops.attn_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], dout, lse, delta, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:],
                      key_padding_mask=kpm, kpm_start=S - 64, debug_timeline=dbg, **kw)
     torch.cuda.synchronize()
     t = dbg.cpu()
-    for pi, pname in enumerate(("dQ pass", "dKV pass")):
+    for pi, pname in enumerate(("dQ pass", "dK pass", "dV pass")):
         mma, sm = t[pi, 0], t[pi, 1]
         t0 = int(mma[8, 0])
         print(f"--- {pname} drop={drop}: iteration period (MMA thread) cycles:", [int(mma[i + 1, 0] - mma[i, 0]) for i in range(8, 24)])
@@ -410,10 +410,10 @@ def bwd_timeline(drop=0.15):
         for i in range(10, 18):
             r = mma[i]
             print("   ", int(r[1] - r[0]), int(r[2] - r[1]), int(r[3] - r[2]), int(r[4] - r[3]), int(r[5] - r[4]))
-        print("softmax warp2 per-iter deltas [C_FULL wait, tmem ld+release, compute, E_EMPTY wait, st+fence+arrive]:")
+        print("element-wise warp0 per-iter deltas [C_FULL wait, ld+compute, E_EMPTY wait, st+arrive]:")
         for i in range(10, 18):
             r = sm[i]
-            print("   ", int(r[1] - r[0]), int(r[2] - r[1]), int(r[3] - r[2]), int(r[4] - r[3]), int(r[5] - r[4]), " period", int(sm[i + 1, 0] - r[0]))
+            print("   ", int(r[1] - r[0]), int(r[3] - r[1]), int(r[4] - r[3]), int(r[5] - r[4]), " period", int(sm[i + 1, 0] - r[0]))
 
 
 def fwd_timeline(drop=0.15):

@@ -1,103 +1,118 @@
-// xf_attn_bwd: fused attention backward for sm_100a (recomputes S from Q, K and the saved LSE; no
-// S x S tensor).  autograd backward of torch18_adapters.py:789-798 (+ head split/merge :544-555,607).
+// xf_attn_bwd: fused attention backward for sm_100a (recomputes the probabilities from Q, K and the saved
+// LSE; no S x S tensor).  autograd backward of torch18_adapters.py:789-798 (+ head split/merge :544-555,607).
 //
-// Two launches of one templated kernel (5 GEMMs of the textbook backward become 3 + 4 because S and
-// dP are recomputed in both; the accumulators of dQ, dK and dV (3 x dp fp32 columns) do not fit the
-// 512 TMEM columns together with the score tiles when dp = 224):
+// Measured on B200 (tools/microbench/mma_bench.cu): one tcgen05.mma (M=128, K=16) costs max(N/2, ~46) cycles
+// whatever the operand source, so score tiles must be >= 64 wide, and with a 224-wide head the three
+// accumulators dQ, dK, dV (3 x 224 fp32 columns) cannot share the 512 TMEM columns with them.  The backward
+// is therefore three launches of one templated kernel, each owning ONE accumulator:
 //
-//   DKV = false ("dQ pass", query-stationary):  resident R1 = Q, R2 = dO tiles [128 x dp];
-//        stream T1 = K_j, T2 = V_j (32 keys):  C1 = Q K_j^T, C2 = dO V_j^T,  dS = P o (C2 - delta) * scale,
-//        dQ += dS K_j.
-//   DKV = true  ("dK/dV pass", key-stationary): resident R1 = K, R2 = V tiles [128 x dp];
-//        stream T1 = Q_i, T2 = dO_i (32 queries): C1 = K Q_i^T (= S^T), C2 = V dO_i^T (= dP^T),
-//        dV += P^T dO_i,  dK += dS^T Q_i.
+//   MODE_DQ (query-stationary): C1 = Q K_j^T, C2 = dO V_j^T,  E = dS   = P o (C2 - delta) * scale,  dQ += E K_j
+//   MODE_DK (key-stationary)  : C1 = K Q_i^T, C2 = V dO_i^T,  E = dS^T,                             dK += E Q_i
+//   MODE_DV (key-stationary)  : C1 = K Q_i^T,                 E = P^T (dropout applied),            dV += E dO_i
 //
-// In both: C1/C2 are tcgen05 MMAs (M=128, N=32, K=dp) into TMEM, the element-wise stage runs one
-// thread per resident row (TMEM lane) out of registers, writes the bf16 tiles E1 (= P^T, DKV only) and
-// E2 (= dS or dS^T) into SWIZZLE_64B shared memory as K-major A operands, and the accumulating MMAs
-// (M=128, N=dp, K=32) read the streamed tile a second time as an MN-major B operand.  TMA feeds a
-// 3-stage ring of streamed tiles.  All tiles use 32-column (64-byte) chunks with SWIZZLE_64B so a
-// 224-wide head needs exactly 7 chunks (no padding to 256), which is what lets the 3-stage ring fit.
-//
-// CTA = 192 threads: warps 0-3 element-wise + epilogue, warp 4 TMA producer, warp 5 MMA issuer.
+// Per CTA (128 resident rows, one (batch, head)); 320 threads = warps 0-7 element-wise (TMEM lane quadrant w & 3,
+// 32 of the 64 streamed columns each), warp 8 TMA producer, warp 9 MMA issuer:
+//   * the first resident operand R1 (Q or K) is staged once through shared memory and copied into TENSOR
+//     MEMORY with tcgen05.cp (dp/2 columns); C1 is a ".ts" MMA (A from TMEM), so R1 costs no shared memory
+//     and no shared-memory bandwidth while streaming;
+//   * the second resident operand R2 (dO or V) stays in shared memory (SWIZZLE_64B, 32-column chunks);
+//   * streamed 64-row tiles T1/T2 arrive by TMA: the tile that is also the B operand of the accumulate MMA
+//     (read a second time MN-major) lives in a 3-stage ring, the tile that only feeds a score MMA in a
+//     2-stage ring;
+//   * the element-wise stage reads C1/C2 from TMEM (tcgen05.ld), and writes E as packed bf16 straight back to
+//     TMEM (tcgen05.st): the accumulate MMA is ".ts" too, E never touches shared memory.
+// TMEM columns (dp = 224): accumulator 224 | R1 112 | C1,C2 2 x 64 | E 32 = 496.
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/xfusion.h"
 #include "host_common.cuh"
 #include "ptx.cuh"
 
+extern "C" int xf_attn_bwd_v1(const XfAttnBwd* a, xf_stream_t stream_);
+
 namespace xf {
 
-constexpr int AB_BM = 128;      // resident rows per CTA
-constexpr int AB_BN = 32;       // streamed rows per iteration
-constexpr int AB_STAGES = 3;
-constexpr int AB_THREADS = 192;
-constexpr uint32_t SW64 = 4;    // UMMA layout code for SWIZZLE_64B
+constexpr int NB_BM = 128;   // resident rows per CTA
+constexpr int NB_BN = 64;    // streamed rows per iteration
+constexpr int NB_LONG = 3, NB_SHORT = 2;
+constexpr int NB_EW_WARPS = 8;   // element-wise warps: two per TMEM lane quadrant, each owns 32 of the 64 streamed columns
+constexpr int NB_THREADS = 32 * (NB_EW_WARPS + 2);
+constexpr uint32_t NB_SW64 = 4;
+enum { MODE_DQ = 0, MODE_DK = 1, MODE_DV = 2 };
 
-struct AttnBwdParams {
-  int B, H, Sq, Sk, dp, nch, r_tiles, n_stream, ncbuf;
+struct AttnBwd2Params {
+  int B, H, Sq, Sk, dp, nch, r_tiles, n_stream;
   float sl2, scale;
-  const uint8_t* kpm;      // [B, Sk] 1 = ignore, or null
-  int kpm_start;           // keys < kpm_start are never masked
-  const float* lse;        // [B, H, stat_stride] log2 domain
-  const float* delta;      // [B, H, stat_stride]
+  const uint8_t* kpm;
+  int kpm_start;
+  const float* lse;
+  const float* delta;
   int stat_stride;
-  __nv_bfloat16* out2; long long ld2;  // DQ: dq ; DKV: dk
-  __nv_bfloat16* out1; long long ld1;  // DKV: dv
+  __nv_bfloat16* out;
+  long long ldo;
   float drop_p, drop_scale;
-  uint32_t drop_seed, drop_stream, drop_thresh;
-  long long* dbg;  // dev aid: per-iteration clock64() stamps of CTA 0 (null in production)
+  uint32_t drop_key, drop_thresh;
+  long long* dbg;  // dev aid: clock64 stamps of CTA 0 (null in production)
 };
 
-#define AB_STAMP(role, i, ev) do { if (p.dbg && blockIdx.x == 0 && (i) < 64) p.dbg[((role) * 64 + (i)) * 8 + (ev)] = clock64(); } while (0)
+#define NB_STAMP(role, i, ev) do { if (p.dbg && blockIdx.x == 0 && (i) < 64) p.dbg[((role) * 64 + (i)) * 8 + (ev)] = clock64(); } while (0)
 
-template <bool DKV, bool DROP>
-__global__ void __launch_bounds__(AB_THREADS, 1)
-attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_constant__ CUtensorMap tmap_r2,
-                        const __grid_constant__ CUtensorMap tmap_t1, const __grid_constant__ CUtensorMap tmap_t2,
-                        const __grid_constant__ AttnBwdParams p) {
+template <int MODE, bool DROP>
+__global__ void __launch_bounds__(NB_THREADS, 1)
+attn_bwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_constant__ CUtensorMap tmap_r2,
+                         const __grid_constant__ CUtensorMap tmap_t1, const __grid_constant__ CUtensorMap tmap_t2,
+                         const __grid_constant__ AttnBwd2Params p) {
+  constexpr bool ROWQ = MODE == MODE_DQ;   // resident rows are queries (else keys)
+  constexpr bool HAS2 = MODE != MODE_DV;   // second score product C2 = R2 T2^T
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + 256);
-  const uint32_t r_bytes = p.nch * 8192u;   // [128 rows x 64 B] per chunk
-  const uint32_t t_bytes = p.nch * 2048u;   // [32 rows x 64 B] per chunk
-  uint8_t* sR1 = smem + 1024;
-  uint8_t* sR2 = sR1 + r_bytes;
-  uint8_t* sT = sR2 + r_bytes;              // ring: stage s -> T1 at sT + s*2*t_bytes, T2 right after
-  uint8_t* sE1 = sT + AB_STAGES * 2 * t_bytes;
-  uint8_t* sE2 = sE1 + 8192;
+  float* s_stat = reinterpret_cast<float*>(smem + 512);   // [4 warps][128]: per-warp copy of the 64 lse + 64 delta of a tile
+  const uint32_t r2_bytes = HAS2 ? p.nch * 8192u : 0u;    // [128 rows x 64 B] per 32-column chunk
+  const uint32_t t_bytes = p.nch * 4096u;                 // [64 rows x 64 B] per chunk
+  uint8_t* sR2 = smem + 2560;                              // 1024-aligned: 2560 = control (512) + stats (2048)
+  sR2 = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sR2) + 1023) & ~uintptr_t(1023));
+  uint8_t* sL = sR2 + r2_bytes;                            // long ring (tile also read MN-major by the accumulate MMA)
+  uint8_t* sS = sL + NB_LONG * t_bytes;                    // short ring (tile only feeds a score MMA)
+  uint8_t* sStage = sL;                                    // R1 staging (SWIZZLE_128B, 64-column chunks) aliases the rings
+  const int nck = (p.dp + 63) / 64;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(bars);
-  const uint32_t R_FULL = bar0;
-  auto T_FULL = [&](int s) { return bar0 + 8u * (1 + s); };
-  auto T_EMPTY = [&](int s) { return bar0 + 8u * (4 + s); };
-  auto C_FULL = [&](int s) { return bar0 + 8u * (7 + s); };
-  auto C_EMPTY = [&](int s) { return bar0 + 8u * (9 + s); };
-  const uint32_t E_FULL = bar0 + 8u * 11;
-  const uint32_t E_EMPTY = bar0 + 8u * 12;
-  const uint32_t ACC_DONE = bar0 + 8u * 13;
+  const uint32_t R_FULL = bar0, R1_COPIED = bar0 + 8;
+  auto L_FULL = [&](int s) { return bar0 + 8u * (2 + s); };
+  auto L_EMPTY = [&](int s) { return bar0 + 8u * (5 + s); };
+  auto S_FULL = [&](int s) { return bar0 + 8u * (8 + s); };
+  auto S_EMPTY = [&](int s) { return bar0 + 8u * (10 + s); };
+  auto C_FULL = [&](int s) { return bar0 + 8u * (12 + s); };
+  auto C_EMPTY = [&](int s) { return bar0 + 8u * (14 + s); };
+  const uint32_t E_FULL = bar0 + 8u * 16, E_EMPTY = bar0 + 8u * 17, ACC_DONE = bar0 + 8u * 18;
 
   int bid = blockIdx.x;
   const int rt = bid % p.r_tiles; bid /= p.r_tiles;
   const int hd = bid % p.H;
   const int b = bid / p.H;
-  const int r0 = rt * AB_BM;
+  const int r0 = rt * NB_BM;
   const int n = p.n_stream;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_r1); tma_prefetch_desc(&tmap_r2);
     tma_prefetch_desc(&tmap_t1); tma_prefetch_desc(&tmap_t2);
     mbar_init(R_FULL, 1);
-    for (int s = 0; s < AB_STAGES; ++s) { mbar_init(T_FULL(s), 1); mbar_init(T_EMPTY(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(C_FULL(s), 1); mbar_init(C_EMPTY(s), 4); }
-    mbar_init(E_FULL, 4);
+    mbar_init(R1_COPIED, 1);
+    for (int s = 0; s < NB_LONG; ++s) { mbar_init(L_FULL(s), 1); mbar_init(L_EMPTY(s), 1); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(S_FULL(s), 1); mbar_init(S_EMPTY(s), 1);
+      mbar_init(C_FULL(s), 1); mbar_init(C_EMPTY(s), NB_EW_WARPS);
+    }
+    mbar_init(E_FULL, NB_EW_WARPS);
     mbar_init(E_EMPTY, 1);
     mbar_init(ACC_DONE, 1);
     fence_mbar_init();
   }
-  if (warp == 5) {
+  if (warp == NB_EW_WARPS + 1) {
     tmem_alloc(smem_u32(tmem_ptr_smem), 512);
     tmem_relinquish();
   }
@@ -105,303 +120,318 @@ attn_bwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  const uint32_t tmem_acc2 = tmem_base;
-  const uint32_t tmem_acc1 = tmem_base + p.dp;                       // DKV only
-  const uint32_t tmem_C = tmem_base + (DKV ? 2 : 1) * p.dp;          // ncbuf x (C1: 32 | C2: 32)
+  const uint32_t tm_acc = tmem_base;
+  const uint32_t tm_r1 = tmem_base + p.dp;                    // dp/2 columns
+  const uint32_t tm_c = tmem_base + p.dp + p.dp / 2;          // DQ/DK: one buffer C1|C2 ; DV: two buffers of C1
+  const uint32_t tm_e = tm_c + 128;                           // 32 columns: E as packed bf16 (A of the accumulate MMA)
 
-  // warps 0-3: element-wise stage (TMEM lane quadrant = warp id); warp 4: TMA producer; warp 5: MMA issuer
-  // (highest ids: the scheduler favours them over the ALU-heavy element-wise warps)
-  if (warp == 4) {
+  if (warp == NB_EW_WARPS) {
+    // ===================== TMA producer =====================
     if (lane == 0) {
       const int col0 = hd * p.dp;
-      mbar_expect_tx(R_FULL, 2 * r_bytes);
-      for (int c = 0; c < p.nch; ++c) {
-        tma_load_3d(smem_u32(sR1 + c * 8192), &tmap_r1, R_FULL, col0 + 32 * c, r0, b);
-        tma_load_3d(smem_u32(sR2 + c * 8192), &tmap_r2, R_FULL, col0 + 32 * c, r0, b);
-      }
+      mbar_expect_tx(R_FULL, nck * 16384u + r2_bytes);
+      for (int c = 0; c < nck; ++c) tma_load_3d(smem_u32(sStage + c * 16384), &tmap_r1, R_FULL, col0 + 64 * c, r0, b);
+      if (HAS2)
+        for (int c = 0; c < p.nch; ++c) tma_load_3d(smem_u32(sR2 + c * 8192), &tmap_r2, R_FULL, col0 + 32 * c, r0, b);
+      mbar_wait(R1_COPIED, 0);   // the staging area is now free for the rings
       for (int i = 0; i < n; ++i) {
-        const int st = i % AB_STAGES;
-        mbar_wait(T_EMPTY(st), ((i / AB_STAGES) & 1) ^ 1);
-        mbar_expect_tx(T_FULL(st), 2 * t_bytes);
-        const uint32_t t1 = smem_u32(sT + st * 2 * t_bytes), t2 = t1 + t_bytes;
-        for (int c = 0; c < p.nch; ++c) {
-          tma_load_3d(t1 + c * 2048, &tmap_t1, T_FULL(st), col0 + 32 * c, i * AB_BN, b);
-          tma_load_3d(t2 + c * 2048, &tmap_t2, T_FULL(st), col0 + 32 * c, i * AB_BN, b);
+        const int ls = i % NB_LONG, ss = i % NB_SHORT;
+        const uint32_t lpar = ((i / NB_LONG) & 1) ^ 1, spar = ((i / NB_SHORT) & 1) ^ 1;
+        const uint32_t la = smem_u32(sL + ls * t_bytes), sa = smem_u32(sS + ss * t_bytes);
+        if (MODE != MODE_DV) {   // T1 -> long ring (score + accumulate), T2 -> short ring (score only)
+          mbar_wait(L_EMPTY(ls), lpar);
+          mbar_expect_tx(L_FULL(ls), t_bytes);
+          for (int c = 0; c < p.nch; ++c) tma_load_3d(la + c * 4096, &tmap_t1, L_FULL(ls), col0 + 32 * c, i * NB_BN, b);
+          mbar_wait(S_EMPTY(ss), spar);
+          mbar_expect_tx(S_FULL(ss), t_bytes);
+          for (int c = 0; c < p.nch; ++c) tma_load_3d(sa + c * 4096, &tmap_t2, S_FULL(ss), col0 + 32 * c, i * NB_BN, b);
+        } else {                 // T1 -> short ring (score only), T2 -> long ring (accumulate only)
+          mbar_wait(S_EMPTY(ss), spar);
+          mbar_expect_tx(S_FULL(ss), t_bytes);
+          for (int c = 0; c < p.nch; ++c) tma_load_3d(sa + c * 4096, &tmap_t1, S_FULL(ss), col0 + 32 * c, i * NB_BN, b);
+          mbar_wait(L_EMPTY(ls), lpar);
+          mbar_expect_tx(L_FULL(ls), t_bytes);
+          for (int c = 0; c < p.nch; ++c) tma_load_3d(la + c * 4096, &tmap_t2, L_FULL(ls), col0 + 32 * c, i * NB_BN, b);
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == NB_EW_WARPS + 1) {
+    // ===================== MMA issuer =====================
     if (lane == 0) {
-      // The score MMAs are N = 32: the tensor pipe retires one every ~46 cycles (measured), so this thread
-      // must issue them with a handful of instructions each: descriptors are built once (only the
-      // start-address word varies) and each 32-column chunk (2 k-steps) is one asm block.
-      const uint32_t idesc_c = make_idesc_bf16(AB_BN, 0, 0);
+      const uint32_t idesc_c = make_idesc_bf16(NB_BN, 0, 0);
       const uint32_t idesc_acc = make_idesc_bf16(p.dp, 0, 1);
-      const int nch = p.nch;
-      const uint64_t dk = make_smem_desc(0, 16, 512, SW64);      // K-major template (start = 0)
-      const uint64_t dmn = make_smem_desc(0, 2048, 512, SW64);   // MN-major template
+      const uint64_t dk = make_smem_desc(0, 16, 512, NB_SW64);      // K-major template
+      const uint64_t dmn = make_smem_desc(0, 4096, 512, NB_SW64);   // MN-major template: 32-column chunks 4096 B apart
       const uint32_t hi_k = desc_hi(dk), hi_mn = desc_hi(dmn), lo_k = desc_lo(dk), lo_mn = desc_lo(dmn);
-      const uint32_t r1lo = lo_k + (smem_u32(sR1) >> 4), r2lo = lo_k + (smem_u32(sR2) >> 4);
-      const uint32_t e1lo = lo_k + (smem_u32(sE1) >> 4), e2lo = lo_k + (smem_u32(sE2) >> 4);
-      const uint32_t t_base = smem_u32(sT) >> 4, t_lo = t_bytes >> 4;
+      const uint32_t r2lo = lo_k + (smem_u32(sR2) >> 4);
+      const uint32_t l_base = smem_u32(sL) >> 4, s_base = smem_u32(sS) >> 4, t_lo = t_bytes >> 4;
+
+      mbar_wait(R_FULL, 0);
+      tc_fence_after();
+      {  // R1: shared memory (SWIZZLE_128B staging) -> TMEM, one 128 x 32 B slice per k-step
+        const uint32_t st = smem_u32(sStage);
+        for (int kk = 0; kk < p.dp / 16; ++kk)
+          tmem_cp_128x256b(tm_r1 + 8 * kk, make_smem_desc(st + (kk >> 2) * 16384 + (kk & 3) * 32, 16, 1024));
+        umma_commit(R1_COPIED);
+      }
       auto do_acc = [&](int i) {
-        const int st = i % AB_STAGES;
-        const uint32_t t1s = t_base + st * 2 * t_lo, t2s = t1s + t_lo;
+        const int ls = i % NB_LONG;
         mbar_wait(E_FULL, i & 1);
-        AB_STAMP(0, i + 1, 4);
+        if (MODE == MODE_DV) mbar_wait(L_FULL(ls), (i / NB_LONG) & 1);
+        NB_STAMP(0, i + 1, 4);
         tc_fence_after();
-        umma_k2(tmem_acc2, hi_k, e2lo, 2, hi_mn, lo_mn + t1s, 64, idesc_acc, i != 0);
-        if (DKV) umma_k2(tmem_acc1, hi_k, e1lo, 2, hi_mn, lo_mn + t2s, 64, idesc_acc, i != 0);
-        umma_commit(T_EMPTY(st));
+        umma_ts_k4(tm_acc, tm_e, hi_mn, lo_mn + l_base + ls * t_lo, 64, idesc_acc, i != 0);   // K = 64 streamed rows
+        umma_commit(L_EMPTY(ls));
         umma_commit(E_EMPTY);
       };
-      mbar_wait(R_FULL, 0);
       for (int i = 0; i < n; ++i) {
-        const int st = i % AB_STAGES, cb = i % p.ncbuf;
-        AB_STAMP(0, i, 0);
-        mbar_wait(T_FULL(st), (i / AB_STAGES) & 1);
-        AB_STAMP(0, i, 1);
-        mbar_wait(C_EMPTY(cb), ((i / p.ncbuf) & 1) ^ 1);
-        AB_STAMP(0, i, 2);
+        const int ls = i % NB_LONG, ss = i % NB_SHORT;
+        const int cb = HAS2 ? 0 : (i & 1);
+        const int cuse = HAS2 ? i : (i >> 1);
+        NB_STAMP(0, i, 0);
+        if (MODE != MODE_DV) mbar_wait(L_FULL(ls), (i / NB_LONG) & 1);
+        mbar_wait(S_FULL(ss), (i / NB_SHORT) & 1);
+        NB_STAMP(0, i, 1);
+        mbar_wait(C_EMPTY(cb), (cuse & 1) ^ 1);
+        NB_STAMP(0, i, 2);
         tc_fence_after();
-        const uint32_t t1s = lo_k + t_base + st * 2 * t_lo, t2s = t1s + t_lo;
-        const uint32_t c1 = tmem_C + cb * 64, c2 = c1 + 32;
-        for (int ch = 0; ch < nch; ++ch) {   // resident chunks are 8192 B apart, streamed chunks 2048 B
-          umma_k2(c1, hi_k, r1lo + ch * 512, 2, hi_k, t1s + ch * 128, 2, idesc_c, ch != 0);
-          umma_k2(c2, hi_k, r2lo + ch * 512, 2, hi_k, t2s + ch * 128, 2, idesc_c, ch != 0);
+        const uint32_t c1 = tm_c + (HAS2 ? 0 : cb * 64), c2 = tm_c + 64;
+        const uint32_t t1lo = lo_k + (MODE != MODE_DV ? l_base + ls * t_lo : s_base + ss * t_lo);
+        const uint32_t t2lo = lo_k + s_base + ss * t_lo;
+        for (int ch = 0; ch < p.nch; ++ch) {   // 32 head-dim columns (2 k-steps) per asm block
+          umma_ts_k2(c1, tm_r1 + 16 * ch, hi_k, t1lo + ch * 256, 2, idesc_c, ch != 0);
+          if (HAS2) umma_k2(c2, hi_k, r2lo + ch * 512, 2, hi_k, t2lo + ch * 256, 2, idesc_c, ch != 0);
         }
         umma_commit(C_FULL(cb));
-        AB_STAMP(0, i, 3);
+        umma_commit(S_EMPTY(ss));
+        NB_STAMP(0, i, 3);
         if (i >= 1) do_acc(i - 1);
-        AB_STAMP(0, i, 5);
+        NB_STAMP(0, i, 5);
       }
       do_acc(n - 1);
       umma_commit(ACC_DONE);
     }
   } else {
-    // ===================== element-wise stage + epilogue =====================
-    const int quad = warp & 3;
+    // ===================== element-wise stage + epilogue (warps 0-7) =====================
+    // warp w: TMEM lane quadrant w & 3 (rows), column half w >> 2 (32 of the 64 streamed columns).  Two warps per
+    // scheduler double the element-wise throughput, which otherwise paces the key-stationary passes.
+    const int quad = warp & 3, half = warp >> 2;
     const int r = quad * 32 + lane;
-    const int row_g = r0 + r;  // query index (DQ) or key index (DKV) within the batch element
+    const int row_g = r0 + r;   // query (DQ) or key (DK/DV) index inside the batch element
     const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
     const long long stat_base = (static_cast<long long>(b) * p.H + hd) * p.stat_stride;
+    const uint64_t bh = static_cast<uint64_t>(b * p.H + hd);
     float lse_row = 0.f, delta_row = 0.f;
     bool row_valid = true;
-    if (!DKV) {
+    if (ROWQ) {
       if (row_g < p.Sq) { lse_row = p.lse[stat_base + row_g]; delta_row = p.delta[stat_base + row_g]; }
     } else {
       row_valid = row_g < p.Sk && !(p.kpm && p.kpm[static_cast<long long>(b) * p.Sk + row_g] != 0);
     }
-    const uint64_t bh = static_cast<uint64_t>(b * p.H + hd);
-    const uint32_t swz = (static_cast<uint32_t>(r) >> 1) & 3u;
-    uint8_t* e1row = sE1 + r * 64;
-    uint8_t* e2row = sE2 + r * 64;
-    // dropout: decision(row = (b,h,q), col = key).  dQ pass: this thread's row hash is constant, one hash per key
-    // pair.  dK/dV pass: this thread's key is constant (half-word select + pair term), the 32 row hashes of the
-    // streamed queries are computed by the 32 lanes once per iteration and broadcast with shuffles.
-    const uint32_t rh_row = DROP && !DKV ? drop_rowhash(p.drop_seed, bh * p.Sq + row_g) : 0u;
-    const uint32_t colterm = (static_cast<uint32_t>(row_g) >> 1) * 0x9E3779B9U;
+    const uint32_t rh_row = DROP && ROWQ ? drop_rowhash(p.drop_key, bh * p.Sq + row_g) : 0u;
+    const uint32_t colterm = (static_cast<uint32_t>(row_g) >> 1) * 0x9E3779B9U;   // key-stationary: this thread's key
     const uint32_t colshift = (row_g & 1) * 16;
     const float sc = p.scale;
+    float* my_stat = s_stat + warp * 64;   // [32 lse | 32 delta] of this warp's column half
 
     for (int i = 0; i < n; ++i) {
-      const int cb = i % p.ncbuf;
-      const int t0 = i * AB_BN;
-      // global-memory operands of this iteration are requested BEFORE waiting on the MMA so their
-      // latency hides behind it: key-padding bits (dQ pass) / per-query LSE and delta (dK/dV pass)
-      uint32_t badbits = 0, rh_lane = 0;
-      float ls[32], ds[32];
-      if (!DKV) {
+      const int cb = HAS2 ? 0 : (i & 1);
+      const int cuse = HAS2 ? i : (i >> 1);
+      const int t0 = i * NB_BN + 32 * half;   // first streamed row of this warp's columns
+      // operands from global memory are requested before waiting on the MMA (latency hidden behind it)
+      uint32_t bad = 0, rhl = 0;
+      float g_l = 0.f, g_d = 0.f;
+      if (ROWQ) {
         const int key = t0 + lane;
-        bool bad = key >= p.Sk;
-        if (!bad && p.kpm && t0 + AB_BN > p.kpm_start) bad = p.kpm[static_cast<long long>(b) * p.Sk + key] != 0;
-        badbits = __ballot_sync(0xffffffffu, bad);
+        bool bk = key >= p.Sk;
+        if (!bk && p.kpm && t0 + 32 > p.kpm_start) bk = p.kpm[static_cast<long long>(b) * p.Sk + key] != 0;
+        bad = __ballot_sync(0xffffffffu, bk);
       } else {
-        const float4* lp = reinterpret_cast<const float4*>(p.lse + stat_base + t0);
-        const float4* dl = reinterpret_cast<const float4*>(p.delta + stat_base + t0);
-#pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
-          const float4 L = __ldg(lp + c4);
-          const float4 Dl = __ldg(dl + c4);
-          ls[4 * c4] = L.x; ls[4 * c4 + 1] = L.y; ls[4 * c4 + 2] = L.z; ls[4 * c4 + 3] = L.w;
-          ds[4 * c4] = Dl.x; ds[4 * c4 + 1] = Dl.y; ds[4 * c4 + 2] = Dl.z; ds[4 * c4 + 3] = Dl.w;
-        }
-        if (DROP) rh_lane = drop_rowhash(p.drop_seed, bh * p.Sq + (t0 + lane));
+        g_l = __ldg(p.lse + stat_base + t0 + lane);
+        if (HAS2) g_d = __ldg(p.delta + stat_base + t0 + lane);
+        if (DROP) rhl = drop_rowhash(p.drop_key, bh * p.Sq + (t0 + lane));
         const int qvalid = p.Sq - t0;   // columns >= qvalid are beyond the sequence
-        badbits = (!row_valid) ? 0xffffffffu : (qvalid >= 32 ? 0u : (0xffffffffu << (qvalid < 0 ? 0 : qvalid)));
+        bad = !row_valid ? 0xffffffffu : (qvalid >= 32 ? 0u : (qvalid <= 0 ? 0xffffffffu : (0xffffffffu << qvalid)));
       }
-      if (warp == 0 && lane == 0) AB_STAMP(1, i, 0);
-      mbar_wait(C_FULL(cb), (i / p.ncbuf) & 1);
-      if (warp == 0 && lane == 0) AB_STAMP(1, i, 1);
+      if (warp == 0 && lane == 0) NB_STAMP(1, i, 0);
+      mbar_wait(C_FULL(cb), cuse & 1);
+      if (warp == 0 && lane == 0) NB_STAMP(1, i, 1);
       tc_fence_after();
       uint32_t c1[32], c2[32];
-      tmem_ld32(tmem_C + lane_sel + cb * 64, c1);
-      tmem_ld32(tmem_C + lane_sel + cb * 64 + 32, c2);
+      tmem_ld32(tm_c + (HAS2 ? 0 : cb * 64) + lane_sel + 32 * half, c1);
+      if (HAS2) tmem_ld32(tm_c + 64 + lane_sel + 32 * half, c2);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(C_EMPTY(cb));
-      if (warp == 0 && lane == 0) AB_STAMP(1, i, 2);
-
-      float e1[32], e2[32];
-      if (!DKV) {
-        // columns = keys t0 + c; row statistics are scalars
+      if (lane == 0) mbar_arrive(C_EMPTY(cb));   // this warp's share of the score tile is in registers
+      float e[32];
+      if (ROWQ) {
 #pragma unroll
         for (int c = 0; c < 32; c += 2) {
-          const float pr0 = ((badbits >> c) & 1u) ? 0.f : fast_exp2(fmaf(__uint_as_float(c1[c]), p.sl2, -lse_row));
-          const float pr1 = ((badbits >> (c + 1)) & 1u) ? 0.f : fast_exp2(fmaf(__uint_as_float(c1[c + 1]), p.sl2, -lse_row));
+          const float pr0 = ((bad >> c) & 1u) ? 0.f : fast_exp2(fmaf(__uint_as_float(c1[c]), p.sl2, -lse_row));
+          const float pr1 = ((bad >> (c + 1)) & 1u) ? 0.f : fast_exp2(fmaf(__uint_as_float(c1[c + 1]), p.sl2, -lse_row));
           float dp0 = __uint_as_float(c2[c]), dp1 = __uint_as_float(c2[c + 1]);
           if (DROP) {
             const uint32_t hsh = drop_pairhash(rh_row, static_cast<uint32_t>(t0 + c) >> 1);
             dp0 = drop_keep_lo(hsh, p.drop_thresh) ? dp0 * p.drop_scale : 0.f;
             dp1 = drop_keep_hi(hsh, p.drop_thresh) ? dp1 * p.drop_scale : 0.f;
           }
-          e2[c] = pr0 * (dp0 - delta_row) * sc;
-          e2[c + 1] = pr1 * (dp1 - delta_row) * sc;
+          e[c] = pr0 * (dp0 - delta_row) * sc;
+          e[c + 1] = pr1 * (dp1 - delta_row) * sc;
         }
       } else {
-        // columns = queries t0 + c; per-column statistics, this thread's key is fixed
+        // per-warp shared copy of the 32 lse / delta values of this warp's columns, read back as 128-bit broadcasts
+        __syncwarp();
+        my_stat[lane] = g_l;
+        if (HAS2) my_stat[32 + lane] = g_d;
+        __syncwarp();
+        const uint32_t st_addr = smem_u32(my_stat);
+        float st_l[32], st_d[32];
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(st_l[c]), "=f"(st_l[c + 1]), "=f"(st_l[c + 2]), "=f"(st_l[c + 3]) : "r"(st_addr + 4 * c));
+          if (HAS2)
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(st_d[c]), "=f"(st_d[c + 1]), "=f"(st_d[c + 2]), "=f"(st_d[c + 3]) : "r"(st_addr + 128 + 4 * c));
+        }
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
-          const float pr = ((badbits >> c) & 1u) ? 0.f : fast_exp2(fmaf(__uint_as_float(c1[c]), p.sl2, -ls[c]));
-          float dpv = __uint_as_float(c2[c]);
-          float pd = pr;
+          const float pr = ((bad >> c) & 1u) ? 0.f : fast_exp2(fmaf(__uint_as_float(c1[c]), p.sl2, -st_l[c]));
+          bool keep = true;
           if (DROP) {
-            const uint32_t hsh = mix32(__shfl_sync(0xffffffffu, rh_lane, c) + colterm);
-            const bool keep = ((hsh >> colshift) & 0xFFFFu) >= p.drop_thresh;
-            dpv = keep ? dpv * p.drop_scale : 0.f;
-            pd = keep ? pr * p.drop_scale : 0.f;
+            const uint32_t hsh = mix32(__shfl_sync(0xffffffffu, rhl, c) + colterm);
+            keep = ((hsh >> colshift) & 0xFFFFu) >= p.drop_thresh;
           }
-          e1[c] = pd;
-          e2[c] = pr * (dpv - ds[c]) * sc;
+          if (MODE == MODE_DV) {
+            e[c] = DROP ? (keep ? pr * p.drop_scale : 0.f) : pr;
+          } else {
+            float dpv = __uint_as_float(c2[c]);
+            if (DROP) dpv = keep ? dpv * p.drop_scale : 0.f;
+            e[c] = ((bad >> c) & 1u) ? 0.f : pr * (dpv - st_d[c]) * sc;   // no 0 * NaN from padding
+          }
         }
       }
-      if (warp == 0 && lane == 0) AB_STAMP(1, i, 3);
-      if (i > 0) mbar_wait(E_EMPTY, (i - 1) & 1);
-      if (warp == 0 && lane == 0) AB_STAMP(1, i, 4);
+      uint32_t pk[16];
 #pragma unroll
-      for (int sgm = 0; sgm < 4; ++sgm) {
-        const uint32_t off = (static_cast<uint32_t>(sgm) ^ swz) << 4;
-        *reinterpret_cast<uint4*>(e2row + off) =
-            make_uint4(pack_bf16(e2[8 * sgm], e2[8 * sgm + 1]), pack_bf16(e2[8 * sgm + 2], e2[8 * sgm + 3]),
-                       pack_bf16(e2[8 * sgm + 4], e2[8 * sgm + 5]), pack_bf16(e2[8 * sgm + 6], e2[8 * sgm + 7]));
-        if (DKV)
-          *reinterpret_cast<uint4*>(e1row + off) =
-              make_uint4(pack_bf16(e1[8 * sgm], e1[8 * sgm + 1]), pack_bf16(e1[8 * sgm + 2], e1[8 * sgm + 3]),
-                         pack_bf16(e1[8 * sgm + 4], e1[8 * sgm + 5]), pack_bf16(e1[8 * sgm + 6], e1[8 * sgm + 7]));
-      }
-      fence_proxy_async_smem();
+      for (int c = 0; c < 16; ++c) pk[c] = pack_bf16(e[2 * c], e[2 * c + 1]);
+      if (warp == 0 && lane == 0) NB_STAMP(1, i, 3);
+      // acc_{i-1} has consumed the previous E (for i = 0 the wait on the fresh barrier's opposite parity passes at
+      // once; written without an `i > 0` test so the compiler does not peel a second copy of the loop body)
+      mbar_wait(E_EMPTY, (i + 1) & 1);
+      tc_fence_after();
+      if (warp == 0 && lane == 0) NB_STAMP(1, i, 4);
+      tmem_st16(tm_e + lane_sel + 16 * half, pk);
+      tmem_st_wait();
+      tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(E_FULL);
-      if (warp == 0 && lane == 0) AB_STAMP(1, i, 5);
+      if (warp == 0 && lane == 0) NB_STAMP(1, i, 5);
     }
 
-    // ---- epilogue: accumulators -> bf16 -> global (token-major, heads merged)
+    // ---- epilogue: accumulator -> bf16 -> global (token-major, heads merged); the two warps of a quadrant
+    //      alternate 32-column chunks
     mbar_wait(ACC_DONE, 0);
     tc_fence_after();
-    const int limit = DKV ? p.Sk : p.Sq;
+    const int limit = ROWQ ? p.Sq : p.Sk;
     const bool ok = row_g < limit;
-    const long long tok = static_cast<long long>(b) * limit + row_g;
-#pragma unroll 1
-    for (int which = 0; which < (DKV ? 2 : 1); ++which) {
-      const uint32_t tacc = which == 0 ? tmem_acc2 : tmem_acc1;
-      __nv_bfloat16* orow = which == 0 ? p.out2 + tok * p.ld2 + hd * p.dp : p.out1 + tok * p.ld1 + hd * p.dp;
-      for (int c = 0; c < p.dp; c += 32) {
-        uint32_t o[32];
-        tmem_ld32(tacc + lane_sel + c, o);
-        tmem_ld_wait();
-        if (ok) {
+    __nv_bfloat16* orow = p.out + (static_cast<long long>(b) * limit + row_g) * p.ldo + hd * p.dp;
+    for (int c = 32 * half; c < p.dp; c += 64) {
+      uint32_t o[32];
+      tmem_ld32(tm_acc + lane_sel + c, o);
+      tmem_ld_wait();
+      if (ok) {
 #pragma unroll
-          for (int k = 0; k < 32; k += 8)
-            *reinterpret_cast<uint4*>(orow + c + k) =
-                make_uint4(pack_bf16(__uint_as_float(o[k]), __uint_as_float(o[k + 1])), pack_bf16(__uint_as_float(o[k + 2]), __uint_as_float(o[k + 3])),
-                           pack_bf16(__uint_as_float(o[k + 4]), __uint_as_float(o[k + 5])), pack_bf16(__uint_as_float(o[k + 6]), __uint_as_float(o[k + 7])));
-        }
+        for (int k = 0; k < 32; k += 8)
+          *reinterpret_cast<uint4*>(orow + c + k) =
+              make_uint4(pack_bf16(__uint_as_float(o[k]), __uint_as_float(o[k + 1])), pack_bf16(__uint_as_float(o[k + 2]), __uint_as_float(o[k + 3])),
+                         pack_bf16(__uint_as_float(o[k + 4]), __uint_as_float(o[k + 5])), pack_bf16(__uint_as_float(o[k + 6]), __uint_as_float(o[k + 7])));
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == NB_EW_WARPS + 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+}
+
+template <int MODE>
+static int launch_bwd2(bool drop, int grid, int smem_bytes, cudaStream_t stream, const CUtensorMap& r1, const CUtensorMap& r2,
+                       const CUtensorMap& t1, const CUtensorMap& t2, const AttnBwd2Params& p) {
+  if (drop) {
+    XF_CUDA(cudaFuncSetAttribute(attn_bwd2_tcgen05_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attn_bwd2_tcgen05_kernel<MODE, true><<<grid, NB_THREADS, smem_bytes, stream>>>(r1, r2, t1, t2, p);
+  } else {
+    XF_CUDA(cudaFuncSetAttribute(attn_bwd2_tcgen05_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attn_bwd2_tcgen05_kernel<MODE, false><<<grid, NB_THREADS, smem_bytes, stream>>>(r1, r2, t1, t2, p);
+  }
+  g_launches.fetch_add(1);
+  XF_CUDA(cudaGetLastError());
+  return 0;
 }
 
 }  // namespace xf
 
 extern "C" int xf_attn_bwd(const XfAttnBwd* a, xf_stream_t stream_) {
   using namespace xf;
+  static const bool use_v1 = getenv("XF_ATTN_BWD_V1") != nullptr;
+  if (use_v1) return xf_attn_bwd_v1(a, stream_);
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!a || !a->q || !a->k || !a->v || !a->d_out || !a->lse || !a->delta || !a->dq || !a->dk || !a->dv)
     return fail(-1, "xf_attn_bwd: null pointer");
   if (a->dp % 32 || a->dp < 32 || a->dp > 224) return fail(-2, "xf_attn_bwd: padded head dim %d must be a multiple of 32 in [32,224]", a->dp);
   if (a->B <= 0 || a->H <= 0 || a->Sq <= 0 || a->Sk <= 0) return fail(-3, "xf_attn_bwd: bad shape");
-  if (a->stat_stride % 32 || a->stat_stride < ((a->Sq + 31) / 32) * 32) return fail(-4, "xf_attn_bwd: stat_stride must be a multiple of 32 >= Sq rounded up to 32");
+  if (a->stat_stride % 64 || a->stat_stride < ((a->Sq + 63) / 64) * 64) return fail(-4, "xf_attn_bwd: stat_stride must be a multiple of 64 >= Sq rounded up to 64");
   if ((a->lddq % 8) || (a->lddk % 8) || (a->lddv % 8)) return fail(-5, "xf_attn_bwd: gradient leading dims must be multiples of 8");
   if (a->drop_p < 0.f || a->drop_p >= 1.f) return fail(-6, "xf_attn_bwd: drop_p out of range");
 
-  AttnBwdParams p;
+  AttnBwd2Params p;
   memset(&p, 0, sizeof(p));
   p.B = a->B; p.H = a->H; p.Sq = a->Sq; p.Sk = a->Sk; p.dp = a->dp; p.nch = a->dp / 32;
   p.sl2 = a->scale * 1.4426950408889634f;
   p.scale = a->scale;
   p.kpm = a->key_padding_mask;
   p.kpm_start = a->kpm_start;
-  p.dbg = reinterpret_cast<long long*>(a->debug_timeline);
   p.lse = a->lse; p.delta = a->delta; p.stat_stride = a->stat_stride;
   p.drop_p = a->drop_p;
   p.drop_scale = a->drop_p > 0.f ? 1.f / (1.f - a->drop_p) : 1.f;
-  p.drop_seed = drop_key(a->drop_seed, a->drop_stream); p.drop_stream = a->drop_stream;
+  p.drop_key = drop_key(a->drop_seed, a->drop_stream);
   p.drop_thresh = drop_thresh16(a->drop_p);
+  p.dbg = reinterpret_cast<long long*>(a->debug_timeline);
+  const bool drop = a->drop_p > 0.f;
 
   const uint64_t cols = static_cast<uint64_t>(a->H) * a->dp;
-  CUtensorMap q128, do128, k32, v32, k128, v128, q32, do32;
+  CUtensorMap q_stage, k_stage, do_res, v_res, k64, v64, q64, do64;
   int rc;
-  if ((rc = make_tmap_3d_bf16(&q128, a->q, a->B, a->Sq, cols, a->ldq, 32, AB_BM, 64))) return rc;
-  if ((rc = make_tmap_3d_bf16(&do128, a->d_out, a->B, a->Sq, cols, a->lddo, 32, AB_BM, 64))) return rc;
-  if ((rc = make_tmap_3d_bf16(&k32, a->k, a->B, a->Sk, cols, a->ldk, 32, AB_BN, 64))) return rc;
-  if ((rc = make_tmap_3d_bf16(&v32, a->v, a->B, a->Sk, cols, a->ldv, 32, AB_BN, 64))) return rc;
-  if ((rc = make_tmap_3d_bf16(&k128, a->k, a->B, a->Sk, cols, a->ldk, 32, AB_BM, 64))) return rc;
-  if ((rc = make_tmap_3d_bf16(&v128, a->v, a->B, a->Sk, cols, a->ldv, 32, AB_BM, 64))) return rc;
-  if ((rc = make_tmap_3d_bf16(&q32, a->q, a->B, a->Sq, cols, a->ldq, 32, AB_BN, 64))) return rc;
-  if ((rc = make_tmap_3d_bf16(&do32, a->d_out, a->B, a->Sq, cols, a->lddo, 32, AB_BN, 64))) return rc;
+  if ((rc = make_tmap_3d_bf16(&q_stage, a->q, a->B, a->Sq, cols, a->ldq, 64, NB_BM, 128))) return rc;
+  if ((rc = make_tmap_3d_bf16(&k_stage, a->k, a->B, a->Sk, cols, a->ldk, 64, NB_BM, 128))) return rc;
+  if ((rc = make_tmap_3d_bf16(&do_res, a->d_out, a->B, a->Sq, cols, a->lddo, 32, NB_BM, 64))) return rc;
+  if ((rc = make_tmap_3d_bf16(&v_res, a->v, a->B, a->Sk, cols, a->ldv, 32, NB_BM, 64))) return rc;
+  if ((rc = make_tmap_3d_bf16(&k64, a->k, a->B, a->Sk, cols, a->ldk, 32, NB_BN, 64))) return rc;
+  if ((rc = make_tmap_3d_bf16(&v64, a->v, a->B, a->Sk, cols, a->ldv, 32, NB_BN, 64))) return rc;
+  if ((rc = make_tmap_3d_bf16(&q64, a->q, a->B, a->Sq, cols, a->ldq, 32, NB_BN, 64))) return rc;
+  if ((rc = make_tmap_3d_bf16(&do64, a->d_out, a->B, a->Sq, cols, a->lddo, 32, NB_BN, 64))) return rc;
 
-  const int smem_bytes = 1024 + 1024 + 2 * p.nch * 8192 + AB_STAGES * 2 * p.nch * 2048 + 2 * 8192;
-  static bool attr_set = false;
-  if (!attr_set) {
-    XF_CUDA(cudaFuncSetAttribute(attn_bwd_tcgen05_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    XF_CUDA(cudaFuncSetAttribute(attn_bwd_tcgen05_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    XF_CUDA(cudaFuncSetAttribute(attn_bwd_tcgen05_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    XF_CUDA(cudaFuncSetAttribute(attn_bwd_tcgen05_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
-  // dQ pass
+  const int ring = (NB_LONG + NB_SHORT) * p.nch * 4096;
+  const int smem2 = 1024 + 4096 + p.nch * 8192 + ring;   // align slack + control/stats + R2 + rings
+  const int smem1 = 1024 + 4096 + ring;
+  const int q_tiles = (a->Sq + NB_BM - 1) / NB_BM, k_tiles = (a->Sk + NB_BM - 1) / NB_BM;
   {
-    AttnBwdParams pq = p;
-    pq.r_tiles = (a->Sq + AB_BM - 1) / AB_BM;
-    pq.n_stream = (a->Sk + AB_BN - 1) / AB_BN;
-    pq.ncbuf = (512 - a->dp) / 64 >= 2 ? 2 : 1;
-    pq.out2 = reinterpret_cast<__nv_bfloat16*>(a->dq); pq.ld2 = a->lddq;
-    if (a->drop_p > 0.f) attn_bwd_tcgen05_kernel<false, true><<<a->B * a->H * pq.r_tiles, AB_THREADS, smem_bytes, stream>>>(q128, do128, k32, v32, pq);
-    else attn_bwd_tcgen05_kernel<false, false><<<a->B * a->H * pq.r_tiles, AB_THREADS, smem_bytes, stream>>>(q128, do128, k32, v32, pq);
-    g_launches.fetch_add(1);
-    XF_CUDA(cudaGetLastError());
+    AttnBwd2Params pq = p;
+    pq.r_tiles = q_tiles; pq.n_stream = (a->Sk + NB_BN - 1) / NB_BN;
+    pq.out = reinterpret_cast<__nv_bfloat16*>(a->dq); pq.ldo = a->lddq;
+    if ((rc = launch_bwd2<MODE_DQ>(drop, a->B * a->H * q_tiles, smem2, stream, q_stage, do_res, k64, v64, pq))) return rc;
   }
-  // dK / dV pass
   {
-    AttnBwdParams pk = p;
-    pk.r_tiles = (a->Sk + AB_BM - 1) / AB_BM;
-    pk.n_stream = (a->Sq + AB_BN - 1) / AB_BN;
-    pk.ncbuf = (512 - 2 * a->dp) / 64 >= 2 ? 2 : 1;
-    pk.out2 = reinterpret_cast<__nv_bfloat16*>(a->dk); pk.ld2 = a->lddk;
-    pk.out1 = reinterpret_cast<__nv_bfloat16*>(a->dv); pk.ld1 = a->lddv;
+    AttnBwd2Params pk = p;
+    pk.r_tiles = k_tiles; pk.n_stream = (a->Sq + NB_BN - 1) / NB_BN;
+    pk.out = reinterpret_cast<__nv_bfloat16*>(a->dk); pk.ldo = a->lddk;
     if (pk.dbg) pk.dbg += 2 * 64 * 8;
-    if (a->drop_p > 0.f) attn_bwd_tcgen05_kernel<true, true><<<a->B * a->H * pk.r_tiles, AB_THREADS, smem_bytes, stream>>>(k128, v128, q32, do32, pk);
-    else attn_bwd_tcgen05_kernel<true, false><<<a->B * a->H * pk.r_tiles, AB_THREADS, smem_bytes, stream>>>(k128, v128, q32, do32, pk);
-    g_launches.fetch_add(1);
-    XF_CUDA(cudaGetLastError());
+    if ((rc = launch_bwd2<MODE_DK>(drop, a->B * a->H * k_tiles, smem2, stream, k_stage, v_res, q64, do64, pk))) return rc;
+    pk.out = reinterpret_cast<__nv_bfloat16*>(a->dv); pk.ldo = a->lddv;
+    if (pk.dbg) pk.dbg += 2 * 64 * 8;
+    if ((rc = launch_bwd2<MODE_DV>(drop, a->B * a->H * k_tiles, smem1, stream, k_stage, v_res, q64, do64, pk))) return rc;
   }
   return 0;
 }

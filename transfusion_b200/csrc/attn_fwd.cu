@@ -236,7 +236,9 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       mt *= p.sl2;   // log2 domain (sl2 > 0)
       bool need = false;
       float alpha = 1.f;
-      if (j == 0) {
+      int jv = j;
+      asm volatile("" : "+r"(jv));   // opaque: no peeled copy of the loop body for the first tile
+      if (jv == 0) {
         m_used = (mt == -INFINITY) ? 0.f : mt;
       } else {
         need = mt > m_used + AF_RESCALE_THRESHOLD;
@@ -265,7 +267,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         }
       }
       if (warp == 0 && lane == 0) AF_STAMP(1, j, 3);
-      if (j > 0 && any_need) {
+      if (jv > 0 && any_need) {
         // O may only be rescaled once PV_{j-1} has retired.  (Waiting only in this case is safe: the barrier can be
         // at most one phase ahead of j-1, because PV_j needs this warp's P_FULL arrival.)
         mbar_wait(O_READY, (j - 1) & 1);
