@@ -29,8 +29,6 @@
 #include "host_common.cuh"
 #include "ptx.cuh"
 
-extern "C" int xf_attn_bwd_v1(const XfAttnBwd* a, xf_stream_t stream_);
-
 namespace xf {
 
 constexpr int NB_BM = 128;   // resident rows per CTA
@@ -229,9 +227,10 @@ attn_bwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gr
       row_valid = row_g < p.Sk && !(p.kpm && p.kpm[static_cast<long long>(b) * p.Sk + row_g] != 0);
     }
     const uint32_t rh_row = DROP && ROWQ ? drop_rowhash(p.drop_key, bh * p.Sq + row_g) : 0u;
-    const uint32_t colterm = (static_cast<uint32_t>(row_g) >> 1) * 0x9E3779B9U;   // key-stationary: this thread's key
-    const uint32_t colshift = (row_g & 1) * 16;
-    const float sc = p.scale;
+    const uint32_t ch_row = DROP && !ROWQ ? drop_colhash(p.drop_key, static_cast<uint32_t>(row_g)) : 0u;   // this thread's key
+    // key-stationary passes: an invalid (padded / out-of-range) key row contributes nothing
+    const float sc = (ROWQ || row_valid) ? p.scale : 0.f;
+    const float keep_scale = (ROWQ || row_valid) ? p.drop_scale : 0.f;
     float* my_stat = s_stat + warp * 64;   // [32 lse | 32 delta] of this warp's column half
 
     for (int i = 0; i < n; ++i) {
@@ -246,12 +245,13 @@ attn_bwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gr
         bool bk = key >= p.Sk;
         if (!bk && p.kpm && t0 + 32 > p.kpm_start) bk = p.kpm[static_cast<long long>(b) * p.Sk + key] != 0;
         bad = __ballot_sync(0xffffffffu, bk);
+        if (DROP) rhl = drop_colhash(p.drop_key, static_cast<uint32_t>(key));   // this lane's key hash, broadcast below
       } else {
         g_l = __ldg(p.lse + stat_base + t0 + lane);
         if (HAS2) g_d = __ldg(p.delta + stat_base + t0 + lane);
         if (DROP) rhl = drop_rowhash(p.drop_key, bh * p.Sq + (t0 + lane));
-        const int qvalid = p.Sq - t0;   // columns >= qvalid are beyond the sequence
-        bad = !row_valid ? 0xffffffffu : (qvalid >= 32 ? 0u : (qvalid <= 0 ? 0xffffffffu : (0xffffffffu << qvalid)));
+        // columns beyond the sequence: lse := +inf makes their probability exactly 0, delta := 0 keeps it finite
+        if (t0 + lane >= p.Sq) { g_l = INFINITY; g_d = 0.f; }
       }
       if (warp == 0 && lane == 0) NB_STAMP(1, i, 0);
       mbar_wait(C_FULL(cb), cuse & 1);
@@ -272,9 +272,8 @@ attn_bwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gr
           const float pr1 = ((bad >> (c + 1)) & 1u) ? 0.f : fast_exp2(fmaf(__uint_as_float(c1[c + 1]), p.sl2, -lse_row));
           float dp0 = __uint_as_float(c2[c]), dp1 = __uint_as_float(c2[c + 1]);
           if (DROP) {
-            const uint32_t hsh = drop_pairhash(rh_row, static_cast<uint32_t>(t0 + c) >> 1);
-            dp0 = drop_keep_lo(hsh, p.drop_thresh) ? dp0 * p.drop_scale : 0.f;
-            dp1 = drop_keep_hi(hsh, p.drop_thresh) ? dp1 * p.drop_scale : 0.f;
+            dp0 = drop_keep_rc(rh_row, __shfl_sync(0xffffffffu, rhl, c), p.drop_thresh) ? dp0 * p.drop_scale : 0.f;
+            dp1 = drop_keep_rc(rh_row, __shfl_sync(0xffffffffu, rhl, c + 1), p.drop_thresh) ? dp1 * p.drop_scale : 0.f;
           }
           e[c] = pr0 * (dp0 - delta_row) * sc;
           e[c + 1] = pr1 * (dp1 - delta_row) * sc;
@@ -295,18 +294,15 @@ attn_bwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gr
         }
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
-          const float pr = ((bad >> c) & 1u) ? 0.f : fast_exp2(fmaf(__uint_as_float(c1[c]), p.sl2, -st_l[c]));
+          const float pr = fast_exp2(fmaf(__uint_as_float(c1[c]), p.sl2, -st_l[c]));   // 0 for padded queries (lse = +inf)
           bool keep = true;
-          if (DROP) {
-            const uint32_t hsh = mix32(__shfl_sync(0xffffffffu, rhl, c) + colterm);
-            keep = ((hsh >> colshift) & 0xFFFFu) >= p.drop_thresh;
-          }
+          if (DROP) keep = drop_keep_rc(__shfl_sync(0xffffffffu, rhl, c), ch_row, p.drop_thresh);
           if (MODE == MODE_DV) {
-            e[c] = DROP ? (keep ? pr * p.drop_scale : 0.f) : pr;
+            e[c] = keep ? pr * keep_scale : 0.f;
           } else {
             float dpv = __uint_as_float(c2[c]);
             if (DROP) dpv = keep ? dpv * p.drop_scale : 0.f;
-            e[c] = ((bad >> c) & 1u) ? 0.f : pr * (dpv - st_d[c]) * sc;   // no 0 * NaN from padding
+            e[c] = pr * (dpv - st_d[c]) * sc;
           }
         }
       }
@@ -375,8 +371,6 @@ static int launch_bwd2(bool drop, int grid, int smem_bytes, cudaStream_t stream,
 
 extern "C" int xf_attn_bwd(const XfAttnBwd* a, xf_stream_t stream_) {
   using namespace xf;
-  static const bool use_v1 = getenv("XF_ATTN_BWD_V1") != nullptr;
-  if (use_v1) return xf_attn_bwd_v1(a, stream_);
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (!a || !a->q || !a->k || !a->v || !a->d_out || !a->lse || !a->delta || !a->dq || !a->dk || !a->dv)
     return fail(-1, "xf_attn_bwd: null pointer");

@@ -259,11 +259,12 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       }
       l += psum;
       if (DROP) {   // the 1/(1-p) scale is applied once to O in the epilogue
+        const uint32_t ch0 = drop_colhash(p.drop_seed, static_cast<uint32_t>(k0 + lane));
+        const uint32_t ch1 = drop_colhash(p.drop_seed, static_cast<uint32_t>(k0 + 32 + lane));
 #pragma unroll
-        for (int c = 0; c < 64; c += 2) {
-          const uint32_t hsh = drop_pairhash(drop_rh, static_cast<uint32_t>(k0 + c) >> 1);
-          x[c] = drop_keep_lo(hsh, p.drop_thresh) ? x[c] : 0.f;
-          x[c + 1] = drop_keep_hi(hsh, p.drop_thresh) ? x[c + 1] : 0.f;
+        for (int c = 0; c < 32; ++c) {
+          x[c] = drop_keep_rc(drop_rh, __shfl_sync(0xffffffffu, ch0, c), p.drop_thresh) ? x[c] : 0.f;
+          x[32 + c] = drop_keep_rc(drop_rh, __shfl_sync(0xffffffffu, ch1, c), p.drop_thresh) ? x[32 + c] : 0.f;
         }
       }
       if (warp == 0 && lane == 0) AF_STAMP(1, j, 3);

@@ -362,6 +362,15 @@ __device__ __forceinline__ uint32_t drop_rowhash(uint32_t key, uint64_t row) {
 __device__ __forceinline__ uint32_t drop_pairhash(uint32_t rowhash, uint32_t col_pair) {
   return mix32(rowhash + col_pair * 0x9E3779B9U);
 }
+// Attention-probability dropout, symmetric in (query, key) so either orientation hoists the expensive hash:
+//   keep(q, k) = top16((rowhash(q) ^ colhash(k)) * odd) >= t16.  Threads that own a query row compute the tile's
+//   key hashes once per warp (one per lane) and broadcast them with shuffles; key-owning threads do the converse.
+__device__ __forceinline__ uint32_t drop_colhash(uint32_t key, uint32_t col) {
+  return mix32(key ^ 0xA511E9B3U ^ (col * 0x85EBCA6BU));
+}
+__device__ __forceinline__ bool drop_keep_rc(uint32_t rowhash, uint32_t colhash, uint32_t t16) {
+  return (((rowhash ^ colhash) * 0x9E3779B1U) >> 16) >= t16;
+}
 __device__ __forceinline__ bool drop_keep_lo(uint32_t h, uint32_t t16) { return (h & 0xFFFFu) >= t16; }
 __device__ __forceinline__ bool drop_keep_hi(uint32_t h, uint32_t t16) { return (h >> 16) >= t16; }
 
