@@ -334,14 +334,20 @@ def run_ours(args):
         top = next(iter(kernels))
         kname = {"gemm_fwd": "gemm_bf16_tcgen05_kernel (forward x W^T)", "gemm_dgrad": "gemm_bf16_tcgen05_kernel (dgrad)",
                  "gemm_wgrad": "gemm_bf16_tcgen05_kernel (wgrad, split-K)", "attn_fwd": "attn_fwd_tcgen05_kernel",
-                 "attn_bwd": "attn_bwd_tcgen05_kernel<DKV>"}.get(top, top)
+                 "attn_bwd": "attn_bwd2_tcgen05_kernel<MODE_DQ|MODE_DK|MODE_DV> (one xf_attn_bwd call = 3 passes)"}.get(top, top)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")
+        if os.path.isfile(tpath):   # DRAM bytes of the dominant kernel from the committed ncu --set full capture (level-0 launch)
+            with open(tpath) as tf:
+                tfam = json.load(tf)["families"].get(top.split("_")[0] if top.startswith("gemm") else top, {})
+            traffic = tfam.get("traffic_bytes_per_call", tfam.get("traffic_bytes_per_launch"))
         if "tflops" in kernels[top]:
             roofline = {"bound": "tensor", "kernel": kname, "achieved": kernels[top]["tflops"], "peak": peaks["tflops"],
-                        "unit": "TFLOP/s", "frac": round(kernels[top]["tflops"] / peaks["tflops"], 4), "traffic": None,
+                        "unit": "TFLOP/s", "frac": round(kernels[top]["tflops"] / peaks["tflops"], 4), "traffic": traffic,
                         "share_of_step": kernels[top]["share"], "peak_source": peaks["source"]}
         else:
             roofline = {"bound": "hbm", "kernel": kname, "achieved": kernels[top].get("gbs"), "peak": peaks["hbm_gbs"],
-                        "unit": "GB/s", "frac": round((kernels[top].get("gbs") or 0.0) / peaks["hbm_gbs"], 4), "traffic": None,
+                        "unit": "GB/s", "frac": round((kernels[top].get("gbs") or 0.0) / peaks["hbm_gbs"], 4), "traffic": traffic,
                         "share_of_step": kernels[top]["share"], "peak_source": peaks["source"]}
         f_fwd = algorithmic_flops_fwd(w, L)
         from transfusion_b200.configs import level_shapes
