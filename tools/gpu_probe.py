@@ -379,6 +379,10 @@ def drop_debug2():
         print("  at", r, c, "out", float(out[r, c]), "ref", float(ref[r, c]), "out2", float(out2[r, c]))
 
 
+def t0b(mma):
+    return int(mma[10, 0])
+
+
 def bwd_timeline(drop=0.15):
     import math
     B, H, S, d = 13, 4, 3136, 224
@@ -414,6 +418,17 @@ def bwd_timeline(drop=0.15):
         for i in range(10, 18):
             r = sm[i]
             print("   ", int(r[1] - r[0]), int(r[3] - r[1]), int(r[4] - r[3]), int(r[5] - r[4]), " period", int(sm[i + 1, 0] - r[0]))
+        # absolute timeline (same SM clock) of iterations 10..12, relative to the MMA thread's start of iteration 10
+        ev = []
+        names_m = {0: "M loop top", 1: "M tiles full", 2: "M C_EMPTY passed -> issue C", 3: "M C issued+committed", 4: "M E_FULL(i-1) passed -> issue acc(i-1)", 5: "M acc issued"}
+        names_e = {0: "E loop top (stats requested)", 1: "E C_FULL passed", 2: "E w0 C_EMPTY arrived", 6: "E w7 C_EMPTY arrived", 3: "E compute done", 4: "E E_EMPTY passed", 5: "E E stored+arrived"}
+        for i in range(10, 13):
+            for k, nm in names_m.items():
+                ev.append((int(mma[i, k]) - t0b(mma), f"i={i} {nm}"))
+            for k, nm in names_e.items():
+                ev.append((int(sm[i, k]) - t0b(mma), f"i={i} {nm}"))
+        for tt, nm in sorted(ev):
+            print(f"      {tt:7d}  {nm}")
 
 
 def fwd_timeline(drop=0.15):

@@ -106,7 +106,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);   // warp-uniform for the compiler
   const uint32_t tmem_S = tmem_base;         // 2 x 64 columns
   const uint32_t tmem_O = tmem_base + 128;   // dp columns
   const uint32_t tmem_Q = tmem_base + 384;   // dp/2 columns: Q as packed bf16 (A operand of the score MMA)
@@ -114,7 +114,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
   // warps 0-3: softmax (TMEM lane quadrant = warp id); warp 4: TMA producer; warp 5: MMA issuer.  The scheduler
   // favours higher warp ids, so the single-thread roles must not sit below the ALU-heavy softmax warps.
   if (warp == 4) {
-    if (lane == 0) {
+    if (elect_one()) {   // elect.sync, not `lane == 0`: bare UTMALDG / UTCHMMA sequences, no per-instruction ELECT loop
       const int col0 = hd * p.dp;
       mbar_expect_tx(Q_FULL, q_bytes);
       for (int c = 0; c < p.nchunk; ++c) tma_load_3d(smem_u32(sQ + c * 16384), &tmap_q, Q_FULL, col0 + 64 * c, q0, b);
@@ -132,7 +132,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       }
     }
   } else if (warp == 5) {
-    if (lane == 0) {
+    if (elect_one()) {
       // descriptors are built once; only the start-address word changes per MMA, and a 64-column chunk's
       // k-steps are issued from one asm block (issue-rate matters for the N = 64 score MMAs)
       const uint32_t idesc_s = make_idesc_bf16(AF_BN, 0, 0);

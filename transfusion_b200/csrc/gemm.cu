@@ -259,7 +259,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);   // warp-uniform for the compiler
 
   const int num_items = p.num_m_tiles * p.num_n_tiles * p.split_k;   // m-tiles are 128*CG rows tall
   const int first_item = blockIdx.x / CG, item_stride = gridDim.x / CG;
@@ -269,7 +269,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   // roles (TMA producer, MMA issuer) take the two highest warps and the epilogue warps the low ones.
   if (warp == GEMM_EPI_WARPS) {
     // ===================== TMA producer (every CTA) =====================
-    if (lane == 0) {
+    // elect.sync rather than `lane == 0`: the compiler then knows one thread is active and emits bare
+    // UTMALDG / UTCHMMA sequences instead of an ELECT + BRA.U.ANY loop around each of them
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int item = first_item; item < num_items; item += item_stride) {
@@ -315,7 +317,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
   } else if (warp == GEMM_EPI_WARPS + 1) {
     // ===================== MMA issuer (even CTA of the pair only) =====================
-    if (lane == 0 && leader) {
+    if (leader && elect_one()) {
       const uint32_t idesc = make_idesc_bf16(p.tile_n, p.a_mn, p.b_mn, 128 * CG);
       // descriptor templates: only the start-address word advances (per k-step and per stage)
       const uint64_t dta = make_smem_desc(0, p.a_mn ? 8192u : 16u, 1024);
