@@ -410,17 +410,17 @@ def bwd_timeline(drop=0.15):
         mma, sm = t[pi, 0], t[pi, 1]
         t0 = int(mma[8, 0])
         print(f"--- {pname} drop={drop}: iteration period (MMA thread) cycles:", [int(mma[i + 1, 0] - mma[i, 0]) for i in range(8, 24)])
-        print("MMA thread per-iter deltas [T_FULL wait, C_EMPTY wait, issue C, (E_FULL wait), issue acc] (iters 10..17):")
+        print("MMA thread per-iter deltas [L_FULL wait, S_FULL wait, C_EMPTY wait, issue C, (E_FULL wait), issue acc] (iters 10..17):")
         for i in range(10, 18):
             r = mma[i]
-            print("   ", int(r[1] - r[0]), int(r[2] - r[1]), int(r[3] - r[2]), int(r[4] - r[3]), int(r[5] - r[4]))
+            print("   ", int(r[6] - r[0]), int(r[1] - r[6]), int(r[2] - r[1]), int(r[3] - r[2]), int(r[4] - r[3]), int(r[5] - r[4]))
         print("element-wise warp0 per-iter deltas [C_FULL wait, ld+compute, E_EMPTY wait, st+arrive]:")
         for i in range(10, 18):
             r = sm[i]
             print("   ", int(r[1] - r[0]), int(r[3] - r[1]), int(r[4] - r[3]), int(r[5] - r[4]), " period", int(sm[i + 1, 0] - r[0]))
         # absolute timeline (same SM clock) of iterations 10..12, relative to the MMA thread's start of iteration 10
         ev = []
-        names_m = {0: "M loop top", 1: "M tiles full", 2: "M C_EMPTY passed -> issue C", 3: "M C issued+committed", 4: "M E_FULL(i-1) passed -> issue acc(i-1)", 5: "M acc issued"}
+        names_m = {0: "M loop top", 6: "M long-ring tile full", 1: "M tiles full", 2: "M C_EMPTY passed -> issue C", 3: "M C issued+committed", 4: "M E_FULL(i-1) passed -> issue acc(i-1)", 5: "M acc issued"}
         names_e = {0: "E loop top (stats requested)", 1: "E C_FULL passed", 2: "E w0 C_EMPTY arrived", 6: "E w7 C_EMPTY arrived", 3: "E compute done", 4: "E E_EMPTY passed", 5: "E E stored+arrived"}
         for i in range(10, 13):
             for k, nm in names_m.items():

@@ -67,10 +67,10 @@ attn_bwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gr
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + 256);
-  float* s_stat = reinterpret_cast<float*>(smem + 512);   // [4 warps][128]: per-warp copy of the 64 lse + 64 delta of a tile
+  float* s_stat = reinterpret_cast<float*>(smem + 512);   // [8 warps][96]: per-warp lse / delta / hashes of its 32 streamed columns
   const uint32_t r2_bytes = HAS2 ? p.nch * 8192u : 0u;    // [128 rows x 64 B] per 32-column chunk
   const uint32_t t_bytes = p.nch * 4096u;                 // [64 rows x 64 B] per chunk
-  uint8_t* sR2 = smem + 2560;                              // 1024-aligned: 2560 = control (512) + stats (2048)
+  uint8_t* sR2 = smem + 3584;                              // control (512) + stats (3072), rounded up to 1024 below
   sR2 = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sR2) + 1023) & ~uintptr_t(1023));
   uint8_t* sL = sR2 + r2_bytes;                            // long ring (tile also read MN-major by the accumulate MMA)
   uint8_t* sS = sL + NB_LONG * t_bytes;                    // short ring (tile only feeds a score MMA)
@@ -190,6 +190,7 @@ attn_bwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gr
         const int cuse = HAS2 ? i : (i >> 1);
         NB_STAMP(0, i, 0);
         if (MODE != MODE_DV) mbar_wait(L_FULL(ls), (i / NB_LONG) & 1);
+        NB_STAMP(0, i, 6);
         mbar_wait(S_FULL(ss), (i / NB_SHORT) & 1);
         NB_STAMP(0, i, 1);
         mbar_wait(C_EMPTY(cb), (cuse & 1) ^ 1);
@@ -221,40 +222,58 @@ attn_bwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gr
     const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
     const long long stat_base = (static_cast<long long>(b) * p.H + hd) * p.stat_stride;
     const uint64_t bh = static_cast<uint64_t>(b * p.H + hd);
+    // The element-wise stage paces all three passes, so it is written for instruction count: packed fp32 math
+    // (fma/mul .f32x2), every scale folded into the exponent (P * scale = exp2(s * sl2 - (lse - log2 scale))),
+    // per-tile column operands re-read as 128-bit shared-memory broadcasts, key-padding fixed up after the loop
+    // on the (rare) tiles that need it, invalid key rows zeroed once in the epilogue.
+    const float fold = ROWQ || HAS2 ? __log2f(p.scale) : __log2f(p.drop_scale);   // DQ/DK: dS carries `scale`; DV: P_d carries 1/(1-p)
     float lse_row = 0.f, delta_row = 0.f;
     bool row_valid = true;
     if (ROWQ) {
-      if (row_g < p.Sq) { lse_row = p.lse[stat_base + row_g]; delta_row = p.delta[stat_base + row_g]; }
+      if (row_g < p.Sq) { lse_row = p.lse[stat_base + row_g] - fold; delta_row = p.delta[stat_base + row_g]; }
     } else {
       row_valid = row_g < p.Sk && !(p.kpm && p.kpm[static_cast<long long>(b) * p.Sk + row_g] != 0);
     }
-    const uint32_t rh_row = DROP && ROWQ ? drop_rowhash(p.drop_key, bh * p.Sq + row_g) : 0u;
-    const uint32_t ch_row = DROP && !ROWQ ? drop_colhash(p.drop_key, static_cast<uint32_t>(row_g)) : 0u;   // this thread's key
-    // key-stationary passes: an invalid (padded / out-of-range) key row contributes nothing
-    const float sc = (ROWQ || row_valid) ? p.scale : 0.f;
-    const float keep_scale = (ROWQ || row_valid) ? p.drop_scale : 0.f;
-    float* my_stat = s_stat + warp * 64;   // [32 lse | 32 delta] of this warp's column half
+    // this thread's own hash: query hash (DQ) or (odd) key hash (DK/DV); the tile's column hashes come from shared memory
+    const uint32_t h_row = !DROP ? 0u : ROWQ ? drop_rowhash(p.drop_key, bh * p.Sq + row_g) : drop_colhash(p.drop_key, static_cast<uint32_t>(row_g));
+    const float2 sl2_2 = make_float2(p.sl2, p.sl2);
+    const float2 ds_2 = make_float2(p.drop_scale, p.drop_scale);
+    const float2 nlse_2 = make_float2(-lse_row, -lse_row), ndelta_2 = make_float2(-delta_row, -delta_row);
+    const uint32_t t32 = p.drop_thresh;
+    float* my_stat = s_stat + warp * 96;   // per warp: [32 lse | 32 delta | 32 hashes] of this warp's 32 streamed columns
+    const uint32_t st_addr = smem_u32(my_stat);
+
+    // key-stationary passes: the per-column statistics of tile i + 1 are requested one iteration ahead and only
+    // touched (fold, shared-memory staging) an iteration later: warps issue in order, so an instruction that
+    // consumes a load stalls everything behind it for the full memory latency
+    float g_l = 0.f, g_d = 0.f;
+    auto load_stats = [&](int i) {
+      const int col = i * NB_BN + 32 * half + lane;
+      const bool in = col < p.Sq;   // beyond the sequence: lse := +inf makes the probability exactly 0, delta := 0 keeps dS finite
+      g_l = in ? __ldg(p.lse + stat_base + col) : INFINITY;
+      if (HAS2) g_d = in ? __ldg(p.delta + stat_base + col) : 0.f;
+    };
+    if (!ROWQ) load_stats(0);
 
     for (int i = 0; i < n; ++i) {
       const int cb = HAS2 ? 0 : (i & 1);
       const int cuse = HAS2 ? i : (i >> 1);
       const int t0 = i * NB_BN + 32 * half;   // first streamed row of this warp's columns
-      // operands from global memory are requested before waiting on the MMA (latency hidden behind it)
-      uint32_t bad = 0, rhl = 0;
-      float g_l = 0.f, g_d = 0.f;
+      uint32_t bad = 0;
+      __syncwarp();   // the previous iteration's shared-memory reads are done
       if (ROWQ) {
         const int key = t0 + lane;
         bool bk = key >= p.Sk;
         if (!bk && p.kpm && t0 + 32 > p.kpm_start) bk = p.kpm[static_cast<long long>(b) * p.Sk + key] != 0;
         bad = __ballot_sync(0xffffffffu, bk);
-        if (DROP) rhl = drop_colhash(p.drop_key, static_cast<uint32_t>(key));   // this lane's key hash, broadcast below
+        if (DROP) my_stat[64 + lane] = __uint_as_float(drop_colhash(p.drop_key, static_cast<uint32_t>(key)));
       } else {
-        g_l = __ldg(p.lse + stat_base + t0 + lane);
-        if (HAS2) g_d = __ldg(p.delta + stat_base + t0 + lane);
-        if (DROP) rhl = drop_rowhash(p.drop_key, bh * p.Sq + (t0 + lane));
-        // columns beyond the sequence: lse := +inf makes their probability exactly 0, delta := 0 keeps it finite
-        if (t0 + lane >= p.Sq) { g_l = INFINITY; g_d = 0.f; }
+        my_stat[lane] = g_l - fold;
+        if (HAS2) my_stat[32 + lane] = g_d;
+        if (DROP) my_stat[64 + lane] = __uint_as_float(drop_rowhash(p.drop_key, bh * p.Sq + (t0 + lane)));
+        if (i + 1 < n) load_stats(i + 1);
       }
+      __syncwarp();
       if (warp == 0 && lane == 0) NB_STAMP(1, i, 0);
       mbar_wait(C_FULL(cb), cuse & 1);
       if (warp == 0 && lane == 0) NB_STAMP(1, i, 1);
@@ -267,52 +286,41 @@ attn_bwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gr
       __syncwarp();
       if (lane == 0) mbar_arrive(C_EMPTY(cb));   // this warp's share of the score tile is in registers
       if (warp == 0 && lane == 0) NB_STAMP(1, i, 2);
-      if (warp == 7 && lane == 0) NB_STAMP(1, i, 6);
-      float e[32];
-      if (ROWQ) {
-#pragma unroll
-        for (int c = 0; c < 32; c += 2) {
-          const float pr0 = ((bad >> c) & 1u) ? 0.f : fast_exp2(fmaf(__uint_as_float(c1[c]), p.sl2, -lse_row));
-          const float pr1 = ((bad >> (c + 1)) & 1u) ? 0.f : fast_exp2(fmaf(__uint_as_float(c1[c + 1]), p.sl2, -lse_row));
-          float dp0 = __uint_as_float(c2[c]), dp1 = __uint_as_float(c2[c + 1]);
-          if (DROP) {
-            dp0 = drop_keep_rc(rh_row, __shfl_sync(0xffffffffu, rhl, c), p.drop_thresh) ? dp0 * p.drop_scale : 0.f;
-            dp1 = drop_keep_rc(rh_row, __shfl_sync(0xffffffffu, rhl, c + 1), p.drop_thresh) ? dp1 * p.drop_scale : 0.f;
-          }
-          e[c] = pr0 * (dp0 - delta_row) * sc;
-          e[c + 1] = pr1 * (dp1 - delta_row) * sc;
-        }
-      } else {
-        // per-warp shared copy of the 32 lse / delta values of this warp's columns, read back as 128-bit broadcasts
-        __syncwarp();
-        my_stat[lane] = g_l;
-        if (HAS2) my_stat[32 + lane] = g_d;
-        __syncwarp();
-        const uint32_t st_addr = smem_u32(my_stat);
-        float st_l[32], st_d[32];
-#pragma unroll
-        for (int c = 0; c < 32; c += 4) {
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(st_l[c]), "=f"(st_l[c + 1]), "=f"(st_l[c + 2]), "=f"(st_l[c + 3]) : "r"(st_addr + 4 * c));
-          if (HAS2)
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(st_d[c]), "=f"(st_d[c + 1]), "=f"(st_d[c + 2]), "=f"(st_d[c + 3]) : "r"(st_addr + 128 + 4 * c));
-        }
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const float pr = fast_exp2(fmaf(__uint_as_float(c1[c]), p.sl2, -st_l[c]));   // 0 for padded queries (lse = +inf)
-          bool keep = true;
-          if (DROP) keep = drop_keep_rc(__shfl_sync(0xffffffffu, rhl, c), ch_row, p.drop_thresh);
-          if (MODE == MODE_DV) {
-            e[c] = keep ? pr * keep_scale : 0.f;
-          } else {
-            float dpv = __uint_as_float(c2[c]);
-            if (DROP) dpv = keep ? dpv * p.drop_scale : 0.f;
-            e[c] = pr * (dpv - st_d[c]) * sc;
-          }
-        }
-      }
       uint32_t pk[16];
 #pragma unroll
-      for (int c = 0; c < 16; ++c) pk[c] = pack_bf16(e[2 * c], e[2 * c + 1]);
+      for (int c = 0; c < 32; c += 4) {
+        float4 st_l, st_d;
+        uint4 hs;
+        if (!ROWQ) asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(st_l.x), "=f"(st_l.y), "=f"(st_l.z), "=f"(st_l.w) : "r"(st_addr + 4 * c));
+        if (!ROWQ && HAS2) asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(st_d.x), "=f"(st_d.y), "=f"(st_d.z), "=f"(st_d.w) : "r"(st_addr + 128 + 4 * c));
+        if (DROP) asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(hs.x), "=r"(hs.y), "=r"(hs.z), "=r"(hs.w) : "r"(st_addr + 256 + 4 * c));
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {   // two column pairs per 128-bit broadcast
+          const int cc = c + 2 * h2;
+          const float2 nl = ROWQ ? nlse_2 : (h2 ? make_float2(-st_l.z, -st_l.w) : make_float2(-st_l.x, -st_l.y));
+          const float2 x = __ffma2_rn(make_float2(__uint_as_float(c1[cc]), __uint_as_float(c1[cc + 1])), sl2_2, nl);
+          float2 pr = make_float2(fast_exp2(x.x), fast_exp2(x.y));   // P * scale (DQ/DK) or P / (1 - p) (DV)
+          bool k0 = true, k1 = true;
+          if (DROP) {
+            k0 = drop_keep_rc(h2 ? hs.z : hs.x, h_row, t32);   // (query hash) * (odd key hash), either orientation
+            k1 = drop_keep_rc(h2 ? hs.w : hs.y, h_row, t32);
+          }
+          float2 e2;
+          if (MODE == MODE_DV) {
+            e2 = make_float2(k0 ? pr.x : 0.f, k1 ? pr.y : 0.f);
+          } else {
+            const float2 dpv = make_float2(k0 ? __uint_as_float(c2[cc]) : 0.f, k1 ? __uint_as_float(c2[cc + 1]) : 0.f);
+            const float2 nd = ROWQ ? ndelta_2 : (h2 ? make_float2(-st_d.z, -st_d.w) : make_float2(-st_d.x, -st_d.y));
+            e2 = __fmul2_rn(pr, __ffma2_rn(dpv, ds_2, nd));   // P * scale * (dP_dropped / (1 - p) - delta)
+          }
+          pk[cc >> 1] = pack_bf16(e2.x, e2.y);
+        }
+      }
+      if (ROWQ && bad != 0) {   // masked / out-of-range keys (last tiles only): their dS is exactly 0
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          pk[j] &= (((bad >> (2 * j)) & 1u) ? 0u : 0x0000FFFFu) | (((bad >> (2 * j + 1)) & 1u) ? 0u : 0xFFFF0000u);
+      }
       if (warp == 0 && lane == 0) NB_STAMP(1, i, 3);
       // acc_{i-1} has consumed the previous E (for i = 0 the wait on the fresh barrier's opposite parity passes at
       // once; written without an `i > 0` test so the compiler does not peel a second copy of the loop body)
@@ -338,6 +346,10 @@ attn_bwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gr
       uint32_t o[32];
       tmem_ld32(tm_acc + lane_sel + c, o);
       tmem_ld_wait();
+      if (!row_valid) {   // padded key: its dK / dV row is exactly 0 (the loop above does not mask rows)
+#pragma unroll
+        for (int k = 0; k < 32; ++k) o[k] = 0u;
+      }
       if (ok) {
 #pragma unroll
         for (int k = 0; k < 32; k += 8)
@@ -395,7 +407,7 @@ extern "C" int xf_attn_bwd(const XfAttnBwd* a, xf_stream_t stream_) {
   p.drop_p = a->drop_p;
   p.drop_scale = a->drop_p > 0.f ? 1.f / (1.f - a->drop_p) : 1.f;
   p.drop_key = drop_key(a->drop_seed, a->drop_stream);
-  p.drop_thresh = drop_thresh16(a->drop_p);
+  { const uint32_t t16 = drop_thresh16(a->drop_p); p.drop_thresh = (t16 > 65535u ? 65535u : t16) << 16; }   // compared against the full hash word
   p.dbg = reinterpret_cast<long long*>(a->debug_timeline);
   const bool drop = a->drop_p > 0.f;
 

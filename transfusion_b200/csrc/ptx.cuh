@@ -362,14 +362,16 @@ __device__ __forceinline__ uint32_t drop_rowhash(uint32_t key, uint64_t row) {
 __device__ __forceinline__ uint32_t drop_pairhash(uint32_t rowhash, uint32_t col_pair) {
   return mix32(rowhash + col_pair * 0x9E3779B9U);
 }
-// Attention-probability dropout, symmetric in (query, key) so either orientation hoists the expensive hash:
-//   keep(q, k) = top16((rowhash(q) ^ colhash(k)) * odd) >= t16.  Threads that own a query row compute the tile's
-//   key hashes once per warp (one per lane) and broadcast them with shuffles; key-owning threads do the converse.
+// Attention-probability dropout, symmetric in (query, key) so either orientation hoists the expensive hashes:
+//   keep(q, k) = rowhash(q) * colhash(k) >= t16 << 16   (colhash is odd: for a fixed key the product is a
+//   bijection of the query hash).  Threads that own a query row hash the tile's keys once per warp (one per
+//   lane) and re-read them as shared-memory broadcasts; key-owning threads do the converse.  Per element this is
+//   one IMAD, one ISETP and one select.
 __device__ __forceinline__ uint32_t drop_colhash(uint32_t key, uint32_t col) {
-  return mix32(key ^ 0xA511E9B3U ^ (col * 0x85EBCA6BU));
+  return mix32(key ^ 0xA511E9B3U ^ (col * 0x85EBCA6BU)) | 1u;
 }
-__device__ __forceinline__ bool drop_keep_rc(uint32_t rowhash, uint32_t colhash, uint32_t t16) {
-  return (((rowhash ^ colhash) * 0x9E3779B1U) >> 16) >= t16;
+__device__ __forceinline__ bool drop_keep_rc(uint32_t rowhash, uint32_t colhash, uint32_t t32) {
+  return rowhash * colhash >= t32;
 }
 __device__ __forceinline__ bool drop_keep_lo(uint32_t h, uint32_t t16) { return (h & 0xFFFFu) >= t16; }
 __device__ __forceinline__ bool drop_keep_hi(uint32_t h, uint32_t t16) { return (h >> 16) >= t16; }
