@@ -407,7 +407,7 @@ extern "C" int xf_attn_bwd(const XfAttnBwd* a, xf_stream_t stream_) {
   p.drop_p = a->drop_p;
   p.drop_scale = a->drop_p > 0.f ? 1.f / (1.f - a->drop_p) : 1.f;
   p.drop_key = drop_key(a->drop_seed, a->drop_stream);
-  { const uint32_t t16 = drop_thresh16(a->drop_p); p.drop_thresh = (t16 > 65535u ? 65535u : t16) << 16; }   // compared against the full hash word
+  p.drop_thresh = drop_thresh32(a->drop_p);   // compared against the full hash word
   p.dbg = reinterpret_cast<long long*>(a->debug_timeline);
   const bool drop = a->drop_p > 0.f;
 

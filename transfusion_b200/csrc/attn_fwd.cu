@@ -376,7 +376,7 @@ extern "C" int xf_attn_fwd(const XfAttnFwd* a, xf_stream_t stream_) {
   p.drop_p = a->drop_p;
   p.drop_scale = a->drop_p > 0.f ? 1.f / (1.f - a->drop_p) : 1.f;
   p.drop_seed = drop_key(a->drop_seed, a->drop_stream); p.drop_stream = a->drop_stream;
-  { const uint32_t t16 = drop_thresh16(a->drop_p); p.drop_thresh = (t16 > 65535u ? 65535u : t16) << 16; }   // compared against the full hash word
+  p.drop_thresh = drop_thresh32(a->drop_p);   // compared against the full hash word
 
   CUtensorMap tq, tk, tv;
   int rc;

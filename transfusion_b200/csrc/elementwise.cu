@@ -166,6 +166,7 @@ struct LnParams {
   float eps;
   // dropout on the output (backproj_dropout, utils.py:115)
   float drop_p; uint32_t drop_seed, drop_stream, drop_thresh; float drop_scale;
+  const uint32_t* coltab;   // xf::drop_col_table()
 };
 
 __device__ __forceinline__ long long remap_row(int r, int rin, int rout, int off) {
@@ -192,14 +193,13 @@ __device__ __forceinline__ void load8f(const float* p, float (&v)[8]) {
   const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
-// dropout on 8 consecutive columns col0.. (col0 % 8 == 0) of the row with hash rh
-__device__ __forceinline__ void drop8(float (&v)[8], uint32_t rh, uint32_t col0, uint32_t t16, float scale) {
+// dropout on 8 consecutive columns col0.. (col0 % 8 == 0) of the row with hash rh; tab = xf::drop_col_table()
+__device__ __forceinline__ void drop8(float (&v)[8], uint32_t rh, uint32_t col0, uint32_t t32, float scale, const uint32_t* __restrict__ tab) {
+  const uint4 c0 = __ldg(reinterpret_cast<const uint4*>(tab + col0));
+  const uint4 c1 = __ldg(reinterpret_cast<const uint4*>(tab + col0) + 1);
+  const uint32_t ch[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
 #pragma unroll
-  for (int k = 0; k < 8; k += 2) {
-    const uint32_t h = drop_pairhash(rh, (col0 + k) >> 1);
-    v[k] = drop_keep_lo(h, t16) ? v[k] * scale : 0.f;
-    v[k + 1] = drop_keep_hi(h, t16) ? v[k + 1] * scale : 0.f;
-  }
+  for (int k = 0; k < 8; ++k) v[k] = drop_keep_rc(rh, ch[k], t32) ? v[k] * scale : 0.f;
 }
 
 // NV = 16-byte vectors per lane (row cached in registers as packed bf16)
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const LnParams p) {
         load8f(p.beta + vidx * 8, b);
 #pragma unroll
         for (int k = 0; k < 8; ++k) v[k] = (v[k] - mean) * rstd * g[k] + b[k];
-        if (p.drop_p > 0.f) drop8(v, drop_rowhash(p.drop_seed, static_cast<uint64_t>(orow)), vidx * 8, p.drop_thresh, p.drop_scale);
+        if (p.drop_p > 0.f) drop8(v, drop_rowhash(p.drop_seed, static_cast<uint64_t>(orow)), vidx * 8, p.drop_thresh, p.drop_scale, p.coltab);
         *(reinterpret_cast<uint4*>(yr) + vidx) = pack8(v);
       }
     }
@@ -271,6 +271,7 @@ struct LnBwdParams {
   int out_rows_in, out_rows_out, out_row_off;
   float dy_drop_p; uint32_t dy_seed, dy_stream, dy_thresh; float dy_scale;
   float dx2_drop_p; uint32_t dx2_seed, dx2_stream, dx2_thresh; float dx2_scale;
+  const uint32_t* coltab;   // xf::drop_col_table()
 };
 
 // Phase 1 (row-wise, one warp per row, row cached as packed bf16): dx (+ dropout-masked copy dx2).
@@ -321,7 +322,7 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const LnBwdParams
           float xv[8], dv[8], gm[8];
           unpack8(qx[i], xv); unpack8(qd[i], dv);
           load8f(p.gamma + vidx * 8, gm);
-          if (p.dy_drop_p > 0.f) { drop8(dv, rh_dy, vidx * 8, p.dy_thresh, p.dy_scale); qd[i] = pack8(dv); }
+          if (p.dy_drop_p > 0.f) { drop8(dv, rh_dy, vidx * 8, p.dy_thresh, p.dy_scale, p.coltab); qd[i] = pack8(dv); }
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             const float g = dv[k] * gm[k];
@@ -345,7 +346,7 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const LnBwdParams
           for (int k = 0; k < 8; ++k) o[k] = rstd * (dv[k] * gm[k] - s1 - (xv[k] - mean) * rstd * s2);
           *(reinterpret_cast<uint4*>(dxr) + vidx) = pack8(o);
           if (p.dx2) {
-            if (p.dx2_drop_p > 0.f) drop8(o, rh_dx2, vidx * 8, p.dx2_thresh, p.dx2_scale);
+            if (p.dx2_drop_p > 0.f) drop8(o, rh_dx2, vidx * 8, p.dx2_thresh, p.dx2_scale, p.coltab);
             *(reinterpret_cast<uint4*>(p.dx2 + irow * p.lddx) + vidx) = pack8(o);
           }
         }
@@ -380,12 +381,11 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const LnBwdParams
               float dv[4] = {bf16_lo(qd[u].x), bf16_hi(qd[u].x), bf16_lo(qd[u].y), bf16_hi(qd[u].y)};
               if (p.dy_drop_p > 0.f) {
                 const uint32_t rh = drop_rowhash(p.dy_seed, static_cast<uint64_t>(orow[u]));
-#pragma unroll
-                for (int k = 0; k < 4; k += 2) {
-                  const uint32_t h = drop_pairhash(rh, static_cast<uint32_t>(col + k) >> 1);
-                  dv[k] = drop_keep_lo(h, p.dy_thresh) ? dv[k] * p.dy_scale : 0.f;
-                  dv[k + 1] = drop_keep_hi(h, p.dy_thresh) ? dv[k + 1] * p.dy_scale : 0.f;
-                }
+                const uint4 ch = __ldg(reinterpret_cast<const uint4*>(p.coltab + col));
+                dv[0] = drop_keep_rc(rh, ch.x, p.dy_thresh) ? dv[0] * p.dy_scale : 0.f;
+                dv[1] = drop_keep_rc(rh, ch.y, p.dy_thresh) ? dv[1] * p.dy_scale : 0.f;
+                dv[2] = drop_keep_rc(rh, ch.z, p.dy_thresh) ? dv[2] * p.dy_scale : 0.f;
+                dv[3] = drop_keep_rc(rh, ch.w, p.dy_thresh) ? dv[3] * p.dy_scale : 0.f;
               }
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
@@ -533,7 +533,7 @@ attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __re
 __global__ void __launch_bounds__(256)
 rows_gather_kernel(const __nv_bfloat16* __restrict__ in, long long ldi, __nv_bfloat16* __restrict__ out, long long ldo, int rows,
                    int D, int rin, int rout, int roff, int rows_per_cta, float* __restrict__ colsum, float drop_p,
-                   uint32_t seed, uint32_t stream, uint32_t thresh, float drop_scale) {
+                   uint32_t seed, uint32_t stream, uint32_t thresh, float drop_scale, const uint32_t* __restrict__ coltab) {
   const int vc = blockIdx.x * blockDim.x + threadIdx.x;
   if (vc * 8 >= D) return;
   const int r0 = blockIdx.y * rows_per_cta;
@@ -543,7 +543,7 @@ rows_gather_kernel(const __nv_bfloat16* __restrict__ in, long long ldi, __nv_bfl
     const long long ir = remap_row(r, rin, rout, roff);
     const uint4 q = __ldg(reinterpret_cast<const uint4*>(in + ir * ldi) + vc);
     float v[8] = {bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y), bf16_lo(q.z), bf16_hi(q.z), bf16_lo(q.w), bf16_hi(q.w)};
-    if (drop_p > 0.f) drop8(v, drop_rowhash(seed, static_cast<uint64_t>(ir)), vc * 8, thresh, drop_scale);
+    if (drop_p > 0.f) drop8(v, drop_rowhash(seed, static_cast<uint64_t>(ir)), vc * 8, thresh, drop_scale, coltab);
 #pragma unroll
     for (int k = 0; k < 8; ++k) s[k] += v[k];
     *(reinterpret_cast<uint4*>(out + static_cast<long long>(r) * ldo) + vc) =
@@ -644,8 +644,12 @@ extern "C" int xf_layernorm_fwd(const XfLayerNorm* a, xf_stream_t s) {
   p.out_rows_in = a->out_rows_in; p.out_rows_out = a->out_rows_out; p.out_row_off = a->out_row_off;
   p.eps = a->eps;
   p.drop_p = a->drop_p; p.drop_seed = drop_key(a->drop_seed, a->drop_stream); p.drop_stream = a->drop_stream;
-  p.drop_thresh = drop_thresh16(a->drop_p);
+  p.drop_thresh = drop_thresh32(a->drop_p);
   p.drop_scale = a->drop_p > 0.f ? 1.f / (1.f - a->drop_p) : 1.f;
+  if (a->drop_p > 0.f) {
+    if (a->D > static_cast<int>(XF_DROP_TABLE_COLS)) return fail(-6, "xf_layernorm_fwd: dropout supports D <= %u", XF_DROP_TABLE_COLS);
+    if (!(p.coltab = drop_col_table())) return fail(-7, "xf_layernorm_fwd: dropout column table allocation failed");
+  }
   const int nv = (a->D / 8 + 31) / 32;
   const int grid = grid_for(a->rows, 8);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(s);
@@ -676,11 +680,15 @@ extern "C" int xf_layernorm_bwd(const XfLayerNormBwd* a, xf_stream_t s) {
   p.in_rows_in = a->in_rows_in; p.in_rows_out = a->in_rows_out; p.in_row_off = a->in_row_off;
   p.out_rows_in = a->out_rows_in; p.out_rows_out = a->out_rows_out; p.out_row_off = a->out_row_off;
   p.dy_drop_p = a->dy_drop_p; p.dy_seed = drop_key(a->dy_drop_seed, a->dy_drop_stream); p.dy_stream = a->dy_drop_stream;
-  p.dy_thresh = drop_thresh16(a->dy_drop_p);
+  p.dy_thresh = drop_thresh32(a->dy_drop_p);
   p.dy_scale = a->dy_drop_p > 0.f ? 1.f / (1.f - a->dy_drop_p) : 1.f;
   p.dx2_drop_p = a->dx2_drop_p; p.dx2_seed = drop_key(a->dx2_drop_seed, a->dx2_drop_stream); p.dx2_stream = a->dx2_drop_stream;
-  p.dx2_thresh = drop_thresh16(a->dx2_drop_p);
+  p.dx2_thresh = drop_thresh32(a->dx2_drop_p);
   p.dx2_scale = a->dx2_drop_p > 0.f ? 1.f / (1.f - a->dx2_drop_p) : 1.f;
+  if (a->dy_drop_p > 0.f || a->dx2_drop_p > 0.f) {
+    if (a->D > static_cast<int>(XF_DROP_TABLE_COLS)) return fail(-6, "xf_layernorm_bwd: dropout supports D <= %u", XF_DROP_TABLE_COLS);
+    if (!(p.coltab = drop_col_table())) return fail(-7, "xf_layernorm_bwd: dropout column table allocation failed");
+  }
   int ctas = (a->rows + LNB_ROWS - 1) / LNB_ROWS;
   if (ctas > 4 * sm_count()) ctas = 4 * sm_count();
   if (ctas < 1) ctas = 1;
@@ -769,10 +777,15 @@ extern "C" int xf_rows_gather(const void* in, int64_t ldi, void* out, int64_t ld
   if (gy > rows) gy = rows;
   const int rows_per_cta = (rows + gy - 1) / gy;
   gy = (rows + rows_per_cta - 1) / rows_per_cta;
+  const uint32_t* coltab = nullptr;
+  if (drop_p > 0.f) {
+    if (D > static_cast<int>(XF_DROP_TABLE_COLS)) return fail(-6, "xf_rows_gather: dropout supports D <= %u", XF_DROP_TABLE_COLS);
+    if (!(coltab = drop_col_table())) return fail(-7, "xf_rows_gather: dropout column table allocation failed");
+  }
   rows_gather_kernel<<<dim3(gx, gy), 256, 0, reinterpret_cast<cudaStream_t>(s)>>>(
       reinterpret_cast<const __nv_bfloat16*>(in), ldi, reinterpret_cast<__nv_bfloat16*>(out), ldo, rows, D, rin, rout, roff,
-      rows_per_cta, colsum, drop_p, drop_key(seed, stream_id), stream_id, drop_thresh16(drop_p),
-      drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f);
+      rows_per_cta, colsum, drop_p, drop_key(seed, stream_id), stream_id, drop_thresh32(drop_p),
+      drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f, coltab);
   g_launches.fetch_add(1);
   XF_CUDA(cudaGetLastError());
   return 0;

@@ -26,9 +26,11 @@ namespace xf {
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_EPI_WARPS = 8;   // two warps per TMEM lane quadrant, each takes every other 32-column chunk
+constexpr int GEMM_EPI_GROUPS = GEMM_EPI_WARPS / 4;
 constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
 constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
-constexpr int GEMM_SMEM_BUDGET = 200 * 1024;         // stage ring budget
+constexpr int GEMM_CTRL_BYTES = 5120;                // barriers, TMEM pointer, per-tile bias / column-hash staging
+constexpr int GEMM_IO_BYTES = GEMM_EPI_WARPS * 4096;  // per epilogue warp: two [32 rows x 64 B] SWIZZLE_64B boxes (TMA store / load)
 
 struct GemmParams {
   int M, N, K;
@@ -109,11 +111,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int m, int n
   if (p.drop_p > 0.f && p.drop_first) {
     const uint32_t rh = drop_rowhash(p.drop_seed, static_cast<uint64_t>(m_out));
 #pragma unroll
-    for (int i = 0; i < 32; i += 2) {
-      const uint32_t hsh = drop_pairhash(rh, static_cast<uint32_t>(n0 + i) >> 1);
-      v[i] = drop_keep_lo(hsh, p.drop_thresh) ? v[i] * p.drop_scale : 0.f;
-      v[i + 1] = drop_keep_hi(hsh, p.drop_thresh) ? v[i + 1] * p.drop_scale : 0.f;
-    }
+    for (int i = 0; i < 32; ++i)
+      v[i] = drop_keep_rc(rh, drop_colodd(static_cast<uint32_t>(n0 + i)), p.drop_thresh) ? v[i] * p.drop_scale : 0.f;
   }
   if (p.act == 1) {
     if (p.preact_out) {
@@ -154,11 +153,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int m, int n
   if (p.drop_p > 0.f && !p.drop_first) {
     const uint32_t rh = drop_rowhash(p.drop_seed, static_cast<uint64_t>(m_out));
 #pragma unroll
-    for (int i = 0; i < 32; i += 2) {
-      const uint32_t hsh = drop_pairhash(rh, static_cast<uint32_t>(n0 + i) >> 1);
-      v[i] = drop_keep_lo(hsh, p.drop_thresh) ? v[i] * p.drop_scale : 0.f;
-      v[i + 1] = drop_keep_hi(hsh, p.drop_thresh) ? v[i + 1] * p.drop_scale : 0.f;
-    }
+    for (int i = 0; i < 32; ++i)
+      v[i] = drop_keep_rc(rh, drop_colodd(static_cast<uint32_t>(n0 + i)), p.drop_thresh) ? v[i] * p.drop_scale : 0.f;
   }
   if (p.residual) {
     const __nv_bfloat16* rs = p.residual + static_cast<long long>(m_out) * p.ldr + n0;
@@ -215,19 +211,157 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int m, int n
   }
 }
 
+// ---- specialised epilogues (the common cases; everything else takes epilogue_chunk above) --------------------
+// They exist because the epilogue, not the tensor pipe, paced the K = 896 GEMMs: ~40 instructions per element in
+// the generic path.  Here: packed fp32 math (fma/add/mul .f32x2), bias and dropout column hashes staged once per
+// tile in shared memory and re-read as 128-bit broadcasts, residual / pre-activation operands requested before
+// the accumulator load is waited for, no per-element bounds checks (host guarantees N % 32 == 0 and 16-byte
+// alignment), and one kernel instantiation per kind so each fits the instruction cache.
+enum { EPI_GENERIC = 0, EPI_LINEAR = 1, EPI_GELU = 2, EPI_DGELU = 3, EPI_RED = 4 };
+
+__device__ __forceinline__ void unpack32(const uint4 (&q)[4], float2 (&f)[16]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[4 * i] = make_float2(bf16_lo(q[i].x), bf16_hi(q[i].x));
+    f[4 * i + 1] = make_float2(bf16_lo(q[i].y), bf16_hi(q[i].y));
+    f[4 * i + 2] = make_float2(bf16_lo(q[i].z), bf16_hi(q[i].z));
+    f[4 * i + 3] = make_float2(bf16_lo(q[i].w), bf16_hi(q[i].w));
+  }
+}
+// This thread's row (lane) of a [32 rows x 64 B] SWIZZLE_64B box: 16-byte chunk ch sits at ch ^ ((row >> 1) & 3).
+__device__ __forceinline__ void box_store_row(uint32_t box, int lane, const float2 (&v)[16]) {
+  const uint32_t row = box + lane * 64, sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + ((i ^ sw) << 4)), "r"(pack_bf16(v[4 * i].x, v[4 * i].y)),
+                 "r"(pack_bf16(v[4 * i + 1].x, v[4 * i + 1].y)), "r"(pack_bf16(v[4 * i + 2].x, v[4 * i + 2].y)),
+                 "r"(pack_bf16(v[4 * i + 3].x, v[4 * i + 3].y))
+                 : "memory");
+}
+__device__ __forceinline__ void box_load_row(uint32_t box, int lane, uint4 (&q)[4]) {
+  const uint32_t row = box + lane * 64, sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q[i].x), "=r"(q[i].y), "=r"(q[i].z), "=r"(q[i].w) : "r"(row + ((i ^ sw) << 4)));
+}
+// Warp-collective: the 32 x 32 bf16 block in `box` -> global through the tensor map (one bulk group of lane 0).
+// PENDING = bulk groups of this warp that may still be reading OTHER boxes when `box` is overwritten.
+template <int PENDING>
+__device__ __forceinline__ void box_store_begin(int lane) {
+  if (lane == 0) tma_store_wait_read<PENDING>();
+  __syncwarp();
+}
+__device__ __forceinline__ void box_store_issue(const CUtensorMap* tmap, uint32_t box, int lane, int n0, int m0) {
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_2d(tmap, box, n0, m0);
+    tma_store_commit();
+  }
+}
+// dropout mask of row hash rh on 32 columns whose odd column hashes sit at shared address col_addr (no scaling)
+__device__ __forceinline__ void drop32(float2 (&v)[16], uint32_t rh, uint32_t col_addr, uint32_t t32) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    uint4 h;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(h.x), "=r"(h.y), "=r"(h.z), "=r"(h.w) : "r"(col_addr + 16 * i));
+    if (!drop_keep_rc(rh, h.x, t32)) v[2 * i].x = 0.f;
+    if (!drop_keep_rc(rh, h.y, t32)) v[2 * i].y = 0.f;
+    if (!drop_keep_rc(rh, h.z, t32)) v[2 * i + 1].x = 0.f;
+    if (!drop_keep_rc(rh, h.w, t32)) v[2 * i + 1].y = 0.f;
+  }
+}
+
+// One 32-column chunk of the warp's 32 accumulator rows (warp-collective; rows m0 .. m0+31, columns n0 .. n0+31).
+// All global traffic goes through TMA boxes: box0 receives the residual (EPI_LINEAR) or the saved pre-activation
+// (EPI_DGELU) -- already copied to `aux` registers by the caller -- and stages the pre-activation store of
+// EPI_GELU; box1 stages the output.  Row-per-thread global accesses (32 different 128-byte lines per warp
+// instruction) saturated the load/store unit and delayed the shared-memory broadcasts queued behind them.
+template <int EPI>
+__device__ __forceinline__ void epilogue_fast(const GemmParams& p, const CUtensorMap* tmap_out, const CUtensorMap* tmap_aux, int lane,
+                                              int m0, int n0, const uint32_t (&acc)[32], const uint4 (&aux)[4], uint32_t box0,
+                                              uint32_t box1, uint32_t bias_addr, uint32_t col_addr, uint32_t rh) {
+  if constexpr (EPI == EPI_RED) {
+    float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(m0 + lane) * p.ldc + n0;
+    if (m0 + lane < p.M) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4)   // 128-bit vector reductions: 8 L2 transactions per chunk instead of 32
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + i), "r"(acc[i]), "r"(acc[i + 1]), "r"(acc[i + 2]), "r"(acc[i + 3]) : "memory");
+    }
+  } else {
+    float2 v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = make_float2(__uint_as_float(acc[2 * i]), __uint_as_float(acc[2 * i + 1]));
+    if (EPI != EPI_DGELU && p.bias) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float4 b;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(bias_addr + 16 * i));
+        v[2 * i] = __fadd2_rn(v[2 * i], make_float2(b.x, b.y));
+        v[2 * i + 1] = __fadd2_rn(v[2 * i + 1], make_float2(b.z, b.w));
+      }
+    }
+    const float2 ds = make_float2(p.drop_scale, p.drop_scale);
+    if (EPI == EPI_GELU) {
+      if (p.preact_out) {
+        box_store_begin<1>(lane);   // the output store of the previous chunk may still be reading box1
+        box_store_row(box0, lane, v);
+        box_store_issue(tmap_aux, box0, lane, n0, m0);
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = gelu2(v[i]);
+      if (p.drop_p > 0.f) {
+        drop32(v, rh, col_addr, p.drop_thresh);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __fmul2_rn(v[i], ds);
+      }
+      box_store_begin<1>(lane);     // this chunk's pre-activation store may still be reading box0
+    } else if (EPI == EPI_DGELU) {
+      float2 u[16];
+      unpack32(aux, u);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = __fmul2_rn(v[i], gelu_grad2(u[i]));
+      if (p.drop_p > 0.f) {
+        drop32(v, rh, col_addr, p.drop_thresh);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __fmul2_rn(v[i], ds);
+      }
+      box_store_begin<0>(lane);
+    } else {  // EPI_LINEAR: [bias] [dropout] [+ residual]
+      if (p.drop_p > 0.f) drop32(v, rh, col_addr, p.drop_thresh);
+      if (p.residual) {
+        float2 rs[16];
+        unpack32(aux, rs);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __ffma2_rn(v[i], ds, rs[i]);   // ds = 1 without dropout
+      } else if (p.drop_p > 0.f) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __fmul2_rn(v[i], ds);
+      }
+      box_store_begin<0>(lane);
+    }
+    box_store_row(box1, lane, v);
+    box_store_issue(tmap_out, box1, lane, n0, m0);
+  }
+}
+
 // CG = 1: one CTA per 128 x tile_n tile.  CG = 2: a CTA pair (cluster of 2) per 256 x tile_n tile with
 // tcgen05.mma.cta_group::2 — each CTA stages its own 128 rows of A and tile_n/2 rows (columns of D) of
 // B, which halves the L2 -> SMEM operand traffic per FLOP (the 1-CTA tile is L2-bandwidth bound).
-template <int CG>
+template <int CG, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_aux,
                          const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   // control block: barriers + TMEM base pointer; stage ring starts at the next 1024-byte boundary
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);  // [0..7] full, [8..15] empty, [16,17] tmem_full, [18,19] tmem_empty
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + 256);
-  uint8_t* ring = smem + 1024;
+  float* s_bias = reinterpret_cast<float*>(smem + 1024);          // [2][256] bias of the tile's columns (per accumulator stage)
+  uint32_t* s_col = reinterpret_cast<uint32_t*>(smem + 3072);     // [2][256] odd dropout hashes of the tile's columns
+  uint8_t* s_io = smem + GEMM_CTRL_BYTES;                          // [warp][2] boxes of 2 KB (1024-aligned)
+  uint8_t* ring = smem + GEMM_CTRL_BYTES + GEMM_IO_BYTES;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -238,6 +372,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   auto empty_bar = [&](int s) { return bar_base + 8u * (8 + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (16 + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (18 + s); };
+  auto aux_bar = [&](int w) { return bar_base + 8u * (20 + w); };   // per epilogue warp: residual / pre-activation box landed
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -250,6 +385,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), GEMM_EPI_WARPS * CG);
     }
+    for (int w = 0; w < GEMM_EPI_WARPS; ++w) mbar_init(aux_bar(w), 1);
     fence_mbar_init();
   }
   if (warp == GEMM_EPI_WARPS + 1) {
@@ -357,23 +493,61 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   } else {
     // ===================== epilogue warps (every CTA: its own 128 accumulator rows) =====================
     const int quad = warp & 3;            // TMEM lane quadrant this warp may access
-    const int half = warp >> 2;           // which of the two warps of the quadrant: takes chunks half, half+2, ...
+    const int half = warp >> 2;           // which warp of the quadrant: takes chunks half, half + GROUPS, ...
     int acc = 0;
-    uint32_t acc_phase = 0;
+    uint32_t acc_phase = 0, aux_phase = 0;
     for (int item = first_item; item < num_items; item += item_stride) {
       int mt, nt, kb0, nkb;
       decode_item(p, item, mt, nt, kb0, nkb);
       if (nkb == 0) continue;
+      constexpr bool FAST = EPI != EPI_GENERIC;
+      constexpr bool STAGED = EPI == EPI_LINEAR || EPI == EPI_GELU || EPI == EPI_DGELU;
+      constexpr bool AUX_IN = EPI == EPI_LINEAR || EPI == EPI_DGELU;   // residual / saved pre-activation arrive by TMA
+      const int m0 = mt * GEMM_BM * CG + rank * GEMM_BM + quad * 32;   // first of this warp's 32 rows
+      const int m = m0 + lane;
+      const bool has_aux = AUX_IN && (EPI == EPI_DGELU || p.residual != nullptr) && m0 < p.M;
+      const uint32_t box0 = smem_u32(s_io + warp * 4096), box1 = box0 + 2048;
+      uint32_t rh = 0;
+      if (STAGED) {
+        // per-tile column constants, staged while the MMAs of this tile are still running.  Buffer `acc` was last
+        // read two tiles ago; every warp passed the previous tile's barrier since then.
+        const int et = threadIdx.x;   // epilogue threads are 0 .. 32 * GEMM_EPI_WARPS - 1
+        if (et < p.tile_n) {
+          const int n = nt * p.tile_n + et;
+          s_bias[acc * 256 + et] = (p.bias && n < p.N) ? __ldg(p.bias + n) : 0.f;
+          s_col[acc * 256 + et] = drop_colodd(static_cast<uint32_t>(n));
+        }
+        if (p.drop_p > 0.f) rh = drop_rowhash(p.drop_seed, static_cast<uint64_t>(m));
+        if (has_aux && lane == 0 && half * 32 < p.tile_n && nt * p.tile_n + half * 32 < p.N) {   // first chunk's operand box, before the MMAs finish
+          mbar_expect_tx(aux_bar(warp), 2048);
+          tma_load_2d(box0, &tmap_aux, aux_bar(warp), nt * p.tile_n + half * 32, m0);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * GEMM_EPI_WARPS) : "memory");
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int m = mt * GEMM_BM * CG + rank * GEMM_BM + quad * 32 + lane;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + acc * p.tile_n;
       bool released = false;
-      for (int c = half * 32; c < p.tile_n; c += 64) {
+      for (int c = half * 32; c < p.tile_n; c += 32 * GEMM_EPI_GROUPS) {
+        const int n0 = nt * p.tile_n + c;
+        const bool live = m0 < p.M && n0 < p.N;   // warp-uniform
+        uint4 aux[4] = {};
+        if (has_aux && n0 < p.N) {
+          mbar_wait(aux_bar(warp), aux_phase);
+          aux_phase ^= 1;
+          box_load_row(box0, lane, aux);
+          const int cn = c + 32 * GEMM_EPI_GROUPS;   // this warp's next chunk of the tile: request it now
+          __syncwarp();
+          if (lane == 0 && cn < p.tile_n && nt * p.tile_n + cn < p.N) {
+            fence_proxy_async_smem();
+            mbar_expect_tx(aux_bar(warp), 2048);
+            tma_load_2d(box0, &tmap_aux, aux_bar(warp), nt * p.tile_n + cn, m0);
+          }
+        }
         uint32_t r[32];
         tmem_ld32(t_row + c, r);
         tmem_ld_wait();
-        if (c + 64 >= p.tile_n) {
+        if (c + 32 * GEMM_EPI_GROUPS >= p.tile_n) {
           // this warp's share of the accumulator is in registers: hand the TMEM stage back to the MMA warp
           tc_fence_before();
           __syncwarp();
@@ -382,8 +556,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           }
           released = true;
         }
-        const int n0 = nt * p.tile_n + c;
-        if (n0 < p.N) epilogue_chunk(p, m, n0, r);
+        if (FAST) {
+          if (live) epilogue_fast<EPI>(p, &tmap_out, &tmap_aux, lane, m0, n0, r, aux, box0, box1, smem_u32(s_bias + acc * 256 + c),
+                                       smem_u32(s_col + acc * 256 + c), rh);
+        } else if (n0 < p.N) {
+          epilogue_chunk(p, m, n0, r);
+        }
       }
       if (!released) {  // tile_n == 32: the second warp of the quadrant has no chunk
         tc_fence_before();
@@ -394,6 +572,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (EPI != EPI_GENERIC && EPI != EPI_RED && lane == 0) tma_store_wait_all<0>();   // staged boxes fully written out
   }
 
   tc_fence_before();
@@ -417,6 +596,33 @@ static int pick_tile_n(long long N) {
     if (best_pad < 0 || pad < best_pad) { best = c; best_pad = pad; }
   }
   return best;
+}
+
+template <int CG, int EPI>
+static int launch_gemm(int ctas, int smem_bytes, cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+                       const CUtensorMap& td, const GemmParams& p) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    XF_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<CG, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  if (CG == 1) {
+    gemm_bf16_tcgen05_kernel<CG, EPI><<<ctas, GEMM_THREADS, smem_bytes, stream>>>(ta, tb, tc, td, p);
+    return 0;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(ctas);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  XF_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<CG, EPI>, ta, tb, tc, td, p));
+  return 0;
 }
 
 }  // namespace xf
@@ -454,7 +660,7 @@ extern "C" int xf_gemm(const XfGemm* g, xf_stream_t stream_) {
   const int cta_b_rows = tile_n / cg;
   p.b_bytes = p.b_mn ? ((cta_b_rows + 63) / 64) * 8192 : cta_b_rows * 128;   // per CTA
   p.stage_bytes = GEMM_A_BYTES + ((p.b_bytes + 1023) / 1024) * 1024;
-  p.stages = GEMM_SMEM_BUDGET / p.stage_bytes;
+  p.stages = (227 * 1024 - 1024 - GEMM_CTRL_BYTES - GEMM_IO_BYTES) / p.stage_bytes;
   if (p.stages > 8) p.stages = 8;
   p.bias = g->bias;
   p.pos_table = g->pos_table;
@@ -479,7 +685,7 @@ extern "C" int xf_gemm(const XfGemm* g, xf_stream_t stream_) {
   p.drop_seed = drop_key(g->drop_seed, g->drop_stream);  // per-call key
   p.drop_stream = g->drop_stream;
   p.drop_first = g->drop_first;
-  p.drop_thresh = drop_thresh16(g->drop_p);
+  p.drop_thresh = drop_thresh32(g->drop_p);
   p.drop_scale = g->drop_p > 0.f ? 1.0f / (1.0f - g->drop_p) : 1.0f;
   if (split_k > 1 && (g->bias || g->pos_table || g->act || g->dact_in || g->residual || g->drop_p > 0.f))
     return fail(-8, "xf_gemm: split_k cannot be combined with a non-linear / additive epilogue");
@@ -493,34 +699,52 @@ extern "C" int xf_gemm(const XfGemm* g, xf_stream_t stream_) {
   else         rc = make_tmap_2d_bf16(&tb, g->b, p.K, p.N, g->b_ld, 64, 64);
   if (rc) return rc;
 
-  const int smem_bytes = 1024 /*align slack*/ + 1024 /*control*/ + p.stages * p.stage_bytes;
-  static bool attr_set = false;
-  if (!attr_set) {
-    XF_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    XF_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+  // epilogue kind: the specialised epilogues need full, 16-byte aligned 32-column chunks and no row remap
+  const bool plain = !g->pos_table && g->rows_in == 0 && p.vec_ok && p.N % 32 == 0 && p.tile_n <= 256;
+  const bool drop_pre_act = g->drop_p > 0.f && g->drop_first;   // only matters when an activation follows the mask
+  int epi = EPI_GENERIC;
+  if (plain && p.out_f32) {
+    if (p.accumulate && !g->bias && !g->act && !g->dact_in && !g->residual && !(g->drop_p > 0.f)) epi = EPI_RED;
+  } else if (plain) {
+    if (g->act == 1 && !g->dact_in && !g->residual && !drop_pre_act) epi = EPI_GELU;
+    else if (g->act == 0 && g->dact_in && !g->residual && !g->bias && !g->preact_out) epi = EPI_DGELU;
+    else if (g->act == 0 && !g->dact_in && !g->preact_out) epi = EPI_LINEAR;
   }
+
+  // output / operand boxes of the specialised epilogues: [32 columns x 32 rows] bf16, SWIZZLE_64B
+  CUtensorMap tc, td;
+  memset(&tc, 0, sizeof(tc));
+  memset(&td, 0, sizeof(td));
+  if (epi == EPI_LINEAR || epi == EPI_GELU || epi == EPI_DGELU) {
+    if ((rc = make_tmap_2d_bf16(&tc, g->out, p.M, p.N, g->ldc, 32, 32, 64))) return rc;
+    const void* auxp = epi == EPI_GELU ? g->preact_out : epi == EPI_DGELU ? g->dact_in : g->residual;
+    const long long auxld = epi == EPI_LINEAR ? g->ldr : g->ldc;
+    if (auxp && (rc = make_tmap_2d_bf16(&td, auxp, p.M, p.N, auxld, 32, 32, 64))) return rc;
+  }
+  const int smem_bytes = 1024 /*align slack*/ + GEMM_CTRL_BYTES + GEMM_IO_BYTES + p.stages * p.stage_bytes;
   const int items = p.num_m_tiles * p.num_n_tiles * p.split_k;
   int sms = g->max_ctas > 0 ? g->max_ctas : sm_count();
   if (cg == 1) {
     int ctas = sms < items ? sms : items;
-    gemm_bf16_tcgen05_kernel<1><<<ctas, GEMM_THREADS, smem_bytes, stream>>>(ta, tb, p);
+    switch (epi) {
+      case EPI_LINEAR: rc = launch_gemm<1, EPI_LINEAR>(ctas, smem_bytes, stream, ta, tb, tc, td, p); break;
+      case EPI_GELU:   rc = launch_gemm<1, EPI_GELU>(ctas, smem_bytes, stream, ta, tb, tc, td, p); break;
+      case EPI_DGELU:  rc = launch_gemm<1, EPI_DGELU>(ctas, smem_bytes, stream, ta, tb, tc, td, p); break;
+      case EPI_RED:    rc = launch_gemm<1, EPI_RED>(ctas, smem_bytes, stream, ta, tb, tc, td, p); break;
+      default:         rc = launch_gemm<1, EPI_GENERIC>(ctas, smem_bytes, stream, ta, tb, tc, td, p); break;
+    }
   } else {
     int clusters = sms / 2 < items ? sms / 2 : items;
     if (clusters < 1) clusters = 1;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(2 * clusters);
-    cfg.blockDim = dim3(GEMM_THREADS);
-    cfg.dynamicSmemBytes = smem_bytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    XF_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<2>, ta, tb, p));
+    switch (epi) {
+      case EPI_LINEAR: rc = launch_gemm<2, EPI_LINEAR>(2 * clusters, smem_bytes, stream, ta, tb, tc, td, p); break;
+      case EPI_GELU:   rc = launch_gemm<2, EPI_GELU>(2 * clusters, smem_bytes, stream, ta, tb, tc, td, p); break;
+      case EPI_DGELU:  rc = launch_gemm<2, EPI_DGELU>(2 * clusters, smem_bytes, stream, ta, tb, tc, td, p); break;
+      case EPI_RED:    rc = launch_gemm<2, EPI_RED>(2 * clusters, smem_bytes, stream, ta, tb, tc, td, p); break;
+      default:         rc = launch_gemm<2, EPI_GENERIC>(2 * clusters, smem_bytes, stream, ta, tb, tc, td, p); break;
+    }
   }
+  if (rc) return rc;
   g_launches.fetch_add(1);
   XF_CUDA(cudaGetLastError());
   return 0;

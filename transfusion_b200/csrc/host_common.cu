@@ -1,4 +1,5 @@
 #include "host_common.cuh"
+#include "ptx.cuh"
 
 #include <mutex>
 
@@ -24,18 +25,19 @@ EncodeTiledFn get_encode_tiled() {
 }
 
 int make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld,
-                      uint32_t box_cols, uint32_t box_rows) {
+                      uint32_t box_cols, uint32_t box_rows, int swizzle_bytes) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return fail(-10, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return fail(-11, "TMA base pointer not 16-byte aligned");
   if ((ld * 2) % 16 != 0) return fail(-12, "TMA row pitch %llu B not a multiple of 16", (unsigned long long)(ld * 2));
-  if (box_cols * 2 > 128 || box_rows > 256) return fail(-13, "bad TMA box %u x %u", box_cols, box_rows);
+  if (static_cast<int>(box_cols * 2) > swizzle_bytes || box_rows > 256) return fail(-13, "bad TMA box %u x %u", box_cols, box_rows);
+  const CUtensorMapSwizzle swz2 = swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstr[1] = {ld * 2};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz2, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(-14, "cuTensorMapEncodeTiled failed: %d (rows=%llu cols=%llu ld=%llu)", (int)r,
                                      (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld);
@@ -71,6 +73,23 @@ int sm_count() {
     n = p.multiProcessorCount;
   }
   return n;
+}
+
+// Odd column hashes of the GEMM / LayerNorm dropout sites (ptx.cuh:drop_colodd), one table per device, filled
+// from the host on first use (synchronous copy: the first call must not happen inside a stream capture).
+const uint32_t* drop_col_table() {
+  static const uint32_t* tabs[64] = {nullptr};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!tabs[dev]) {
+    static uint32_t host_tab[XF_DROP_TABLE_COLS];
+    for (uint32_t c = 0; c < XF_DROP_TABLE_COLS; ++c) host_tab[c] = drop_colodd(c);
+    uint32_t* d = nullptr;
+    if (cudaMalloc(&d, sizeof(host_tab)) != cudaSuccess) return nullptr;
+    if (cudaMemcpy(d, host_tab, sizeof(host_tab), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); return nullptr; }
+    tabs[dev] = d;
+  }
+  return tabs[dev];
 }
 
 }  // namespace xf

@@ -41,7 +41,7 @@ EncodeTiledFn get_encode_tiled();
 // 2-D bf16 row-major tensor [rows, cols] with leading dimension ld (elements); box = box_cols x box_rows,
 // SWIZZLE_128B (box_cols * 2 bytes must be <= 128), out-of-bounds elements read as zero.
 int make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld,
-                      uint32_t box_cols, uint32_t box_rows);
+                      uint32_t box_cols, uint32_t box_rows, int swizzle_bytes = 128);
 
 // 3-D bf16 tensor [batch, rows, cols] (cols contiguous, row pitch ld, batch pitch rows*ld);
 // box = box_cols x box_rows x 1, SWIZZLE_128B, out-of-bounds reads as zero (per batch).
@@ -49,5 +49,9 @@ int make_tmap_3d_bf16(CUtensorMap* out, const void* ptr, uint64_t batch, uint64_
                       uint32_t box_cols, uint32_t box_rows, int swizzle_bytes = 128);
 
 int sm_count();
+
+// device table of drop_colodd(0 .. XF_DROP_TABLE_COLS-1) for the current device (nullptr on failure)
+constexpr uint32_t XF_DROP_TABLE_COLS = 16384;
+const uint32_t* drop_col_table();
 
 }  // namespace xf

@@ -88,6 +88,20 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint
 // half of the B tile; the even CTA issues the MMA and both CTAs' barriers are signalled by multicast.
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> even CTA
 
+// TMA store (shared -> global, bulk async group of the issuing thread).  The shared-memory writes that fill the
+// box must be followed by fence_proxy_async_smem() (generic -> async proxy) before the store is issued.
+__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
+               "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// waits until at most N of this thread's most recent bulk groups still READ their shared-memory source
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -342,8 +356,43 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-// Counter-based dropout (no mask storage; the backward recomputes the same bits).  One 32-bit hash
-// (lowbias32 finaliser) decides TWO adjacent columns of a row, t16 = round(p * 65536).
+// GELU(erf) on two values with packed fp32 math (fma.rn.f32x2): 0.5 erfc(|x| / sqrt 2) = exp2(P6(min(|x|, 6))),
+// P6 fitted in the log2 domain (max exponent error 6.5e-5 -> relative error 4.5e-5 of the tail probability,
+// |GELU error| <= 7e-6, |GELU' error| <= 2.3e-5; both far below bf16 resolution).  One exp2 per value, no divide.
+//   GELU(x)  = max(x, 0) - |x| q(|x|)            GELU'(x) = Phi(x) + x phi(x),  Phi = x >= 0 ? 1 - q : q
+__device__ __forceinline__ float2 gelu_tailprob2(float2 x, float2& a) {
+  a = make_float2(fminf(fabsf(x.x), 6.0f), fminf(fabsf(x.y), 6.0f));
+  float2 r = make_float2(2.29900633712532e-05f, 2.29900633712532e-05f);
+  r = __ffma2_rn(r, a, make_float2(-0.0006111000548116863f, -0.0006111000548116863f));
+  r = __ffma2_rn(r, a, make_float2(0.007195565849542618f, 0.007195565849542618f));
+  r = __ffma2_rn(r, a, make_float2(-0.05118533596396446f, -0.05118533596396446f));
+  r = __ffma2_rn(r, a, make_float2(-0.46127191185951233f, -0.46127191185951233f));
+  r = __ffma2_rn(r, a, make_float2(-1.1501742601394653f, -1.1501742601394653f));
+  r = __ffma2_rn(r, a, make_float2(-1.000064730644226f, -1.000064730644226f));
+  return make_float2(fast_exp2(r.x), fast_exp2(r.y));
+}
+__device__ __forceinline__ float2 gelu2(float2 x) {
+  float2 a;
+  const float2 q = gelu_tailprob2(x, a);
+  return __ffma2_rn(make_float2(-a.x, -a.y), q, make_float2(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f)));
+}
+__device__ __forceinline__ float2 gelu_grad2(float2 x) {
+  float2 a;
+  const float2 q = gelu_tailprob2(x, a);
+  const float2 h = __fadd2_rn(make_float2(0.5f, 0.5f), make_float2(-q.x, -q.y));       // 0.5 - q >= 0
+  const float2 cdf = __fadd2_rn(make_float2(copysignf(h.x, x.x), copysignf(h.y, x.y)), make_float2(0.5f, 0.5f));
+  // x phi(x) = x exp2(-x^2 log2(e)/2 - log2 sqrt(2 pi))
+  const float2 w = __ffma2_rn(__fmul2_rn(x, x), make_float2(-0.72134752044448170f, -0.72134752044448170f),
+                              make_float2(-1.32574806473616f, -1.32574806473616f));
+  return __ffma2_rn(x, make_float2(fast_exp2(w.x), fast_exp2(w.y)), cdf);
+}
+
+// Counter-based dropout (no mask storage; the backward recomputes the same bits).
+//   keep(row, col) = rowhash(key, row) * colhash(col) >= t32,   t32 = round(p * 65536) << 16
+// rowhash is a full avalanche hash of (site key, row); colhash is an ODD avalanche hash of the column, so for a
+// fixed column the product is a bijection of the row hash.  A thread that owns a row hashes it once; the column
+// hashes are tile / table constants (shared-memory broadcasts in the tensor-core kernels, a small global table
+// in the element-wise ones).  Per element: one IMAD, one unsigned compare, one select.
 __host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
   x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
   return x;
@@ -351,29 +400,26 @@ __host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
 __host__ __device__ __forceinline__ uint32_t drop_key(uint32_t seed, uint32_t stream) {
   return mix32(seed ^ (stream * 0x9E3779B9U) ^ 0x5bd1e995U);
 }
-__host__ __device__ __forceinline__ uint32_t drop_thresh16(float p) {
-  return static_cast<uint32_t>(static_cast<double>(p) * 65536.0 + 0.5);
+__host__ __device__ __forceinline__ uint32_t drop_thresh32(float p) {
+  uint32_t t16 = static_cast<uint32_t>(static_cast<double>(p) * 65536.0 + 0.5);
+  if (t16 > 65535u) t16 = 65535u;
+  return t16 << 16;
 }
-// decision(row, col): rowhash is computed once per row (thread), then one hash per column PAIR:
-//   h = mix32(rowhash(row) + (col >> 1) * golden);  even col keeps iff lo16(h) >= t16, odd col iff hi16(h) >= t16
 __device__ __forceinline__ uint32_t drop_rowhash(uint32_t key, uint64_t row) {
   return mix32(key ^ static_cast<uint32_t>(row) ^ (static_cast<uint32_t>(row >> 32) * 0x85EBCA6BU));
 }
-__device__ __forceinline__ uint32_t drop_pairhash(uint32_t rowhash, uint32_t col_pair) {
-  return mix32(rowhash + col_pair * 0x9E3779B9U);
+// GEMM / LayerNorm sites: key-independent odd column hash (xf::drop_col_table() holds the first 16384 of them)
+__host__ __device__ __forceinline__ uint32_t drop_colodd(uint32_t col) {
+  return mix32(col * 0x9E3779B9U + 0x7F4A7C15U) | 1u;
 }
-// Attention-probability dropout, symmetric in (query, key) so either orientation hoists the expensive hashes:
-//   keep(q, k) = rowhash(q) * colhash(k) >= t16 << 16   (colhash is odd: for a fixed key the product is a
-//   bijection of the query hash).  Threads that own a query row hash the tile's keys once per warp (one per
-//   lane) and re-read them as shared-memory broadcasts; key-owning threads do the converse.  Per element this is
-//   one IMAD, one ISETP and one select.
+// Attention probabilities: keep(q, k) = rowhash(q) * colhash(k) >= t32, symmetric in (query, key) so either
+// orientation hoists the hashes: threads that own a query row hash the tile's keys once per warp (one per lane)
+// and re-read them as shared-memory broadcasts; key-owning threads do the converse.
 __device__ __forceinline__ uint32_t drop_colhash(uint32_t key, uint32_t col) {
   return mix32(key ^ 0xA511E9B3U ^ (col * 0x85EBCA6BU)) | 1u;
 }
 __device__ __forceinline__ bool drop_keep_rc(uint32_t rowhash, uint32_t colhash, uint32_t t32) {
   return rowhash * colhash >= t32;
 }
-__device__ __forceinline__ bool drop_keep_lo(uint32_t h, uint32_t t16) { return (h & 0xFFFFu) >= t16; }
-__device__ __forceinline__ bool drop_keep_hi(uint32_t h, uint32_t t16) { return (h >> 16) >= t16; }
 
 }  // namespace xf
