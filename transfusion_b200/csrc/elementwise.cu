@@ -281,6 +281,32 @@ struct LnBwdParams {
 // 1.1 TB/s) so several CTAs per SM keep enough loads in flight.
 constexpr int LNB_ROWS = 32;  // rows per CTA pass
 
+// packed helpers: 8 bf16 (uint4) <-> 4 float2
+__device__ __forceinline__ void unpack8x2(const uint4& q, float2 (&v)[4]) {
+  v[0] = make_float2(bf16_lo(q.x), bf16_hi(q.x)); v[1] = make_float2(bf16_lo(q.y), bf16_hi(q.y));
+  v[2] = make_float2(bf16_lo(q.z), bf16_hi(q.z)); v[3] = make_float2(bf16_lo(q.w), bf16_hi(q.w));
+}
+__device__ __forceinline__ uint4 pack8x2(const float2 (&v)[4]) {
+  return make_uint4(pack_bf16(v[0].x, v[0].y), pack_bf16(v[1].x, v[1].y), pack_bf16(v[2].x, v[2].y), pack_bf16(v[3].x, v[3].y));
+}
+// dropout mask (no scaling) on 8 consecutive columns col0..; tab = xf::drop_col_table()
+__device__ __forceinline__ void dropmask8x2(float2 (&v)[4], uint32_t rh, uint32_t col0, uint32_t t32, const uint32_t* __restrict__ tab) {
+  const uint4 c0 = __ldg(reinterpret_cast<const uint4*>(tab + col0));
+  const uint4 c1 = __ldg(reinterpret_cast<const uint4*>(tab + col0) + 1);
+  if (!drop_keep_rc(rh, c0.x, t32)) v[0].x = 0.f;
+  if (!drop_keep_rc(rh, c0.y, t32)) v[0].y = 0.f;
+  if (!drop_keep_rc(rh, c0.z, t32)) v[1].x = 0.f;
+  if (!drop_keep_rc(rh, c0.w, t32)) v[1].y = 0.f;
+  if (!drop_keep_rc(rh, c1.x, t32)) v[2].x = 0.f;
+  if (!drop_keep_rc(rh, c1.y, t32)) v[2].y = 0.f;
+  if (!drop_keep_rc(rh, c1.z, t32)) v[3].x = 0.f;
+  if (!drop_keep_rc(rh, c1.w, t32)) v[3].y = 0.f;
+}
+
+// The kernel is instruction-bound (it ran at 43 instructions per element), so both phases use packed fp32 math
+// and the row phase uses the affine form of the gradient:
+//   g = dy * gamma,  s1 = mean_c(g),  s2 = mean_c(g * xhat) = rstd * (mean_c(g * x) - mean * s1)
+//   dx = rstd * (g - s1 - xhat * s2) = dy * (rstd * gamma) + x * b + c,   b = -rstd^2 s2,  c = -rstd s1 - b mean
 template <int NV>
 __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const LnBwdParams p) {
   const int warps_per_cta = blockDim.x >> 5;
@@ -288,25 +314,26 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const LnBwdParams
   const int lane = threadIdx.x & 31;
   const int nvec = p.D >> 3;
   const int c4 = threadIdx.x * 4;                 // phase-2 columns of this thread (+ 1024 * j)
-  float cg[NV][4], cb[NV][4], cbias[NV][4];       // NV * 32 lanes * 8 = up to 2 x 1024 columns per j-slot
   constexpr int NJ = (NV * 256 + 1023) / 1024;    // column slots of 1024 per thread
+  float2 cg[NJ][2], cb[NJ][2], cbias[NJ][2];
 #pragma unroll
-  for (int j = 0; j < NV; ++j)
+  for (int j = 0; j < NJ; ++j)
 #pragma unroll
-    for (int k = 0; k < 4; ++k) cg[j][k] = cb[j][k] = cbias[j][k] = 0.f;
+    for (int k = 0; k < 2; ++k) cg[j][k] = cb[j][k] = cbias[j][k] = make_float2(0.f, 0.f);
+  const float inv_d = 1.f / p.D;
+  const bool dy_drop = p.dy_drop_p > 0.f, dx2_drop = p.dx2_drop_p > 0.f;
 
   for (int base = blockIdx.x * LNB_ROWS; base < p.rows; base += gridDim.x * LNB_ROWS) {
     const int rend = min(p.rows, base + LNB_ROWS);
-    // ---------------- phase 1
+    // ---------------- phase 1: one warp per row, row cached as packed bf16
     for (int r = base + warp; r < rend; r += warps_per_cta) {
       const long long irow = remap_row(r, p.in_rows_in, p.in_rows_out, p.in_row_off);
       const long long orow = remap_row(r, p.out_rows_in, p.out_rows_out, p.out_row_off);
       const __nv_bfloat16* xr = p.x + irow * p.ldx;
       const __nv_bfloat16* dyr = p.dy + orow * p.lddy;
       const float mean = p.mean[r], rstd = p.rstd[r];
-      const uint32_t rh_dy = p.dy_drop_p > 0.f ? drop_rowhash(p.dy_seed, static_cast<uint64_t>(orow)) : 0u;
+      const uint32_t rh_dy = dy_drop ? drop_rowhash(p.dy_seed, static_cast<uint64_t>(orow)) : 0u;
       uint4 qx[NV], qd[NV];
-      float s1 = 0.f, s2 = 0.f;
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         const int vidx = lane + 32 * i;
@@ -315,61 +342,80 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const LnBwdParams
           qd[i] = __ldg(reinterpret_cast<const uint4*>(dyr) + vidx);
         }
       }
+      float2 s1v = make_float2(0.f, 0.f), tv = make_float2(0.f, 0.f);
+      const float2 dys = make_float2(p.dy_scale, p.dy_scale);
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         const int vidx = lane + 32 * i;
         if (vidx < nvec) {
-          float xv[8], dv[8], gm[8];
-          unpack8(qx[i], xv); unpack8(qd[i], dv);
-          load8f(p.gamma + vidx * 8, gm);
-          if (p.dy_drop_p > 0.f) { drop8(dv, rh_dy, vidx * 8, p.dy_thresh, p.dy_scale, p.coltab); qd[i] = pack8(dv); }
+          float2 xv[4], dv[4];
+          unpack8x2(qx[i], xv); unpack8x2(qd[i], dv);
+          if (dy_drop) {   // the incoming gradient passes the forward's dropout mask first; keep the masked copy
+            dropmask8x2(dv, rh_dy, vidx * 8, p.dy_thresh, p.coltab);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const float g = dv[k] * gm[k];
-            s1 += g;
-            s2 += g * (xv[k] - mean) * rstd;
+            for (int k = 0; k < 4; ++k) dv[k] = __fmul2_rn(dv[k], dys);
+            qd[i] = pack8x2(dv);
+          }
+          const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + vidx * 8));
+          const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + vidx * 8) + 1);
+          const float2 gm[4] = {make_float2(g0.x, g0.y), make_float2(g0.z, g0.w), make_float2(g1.x, g1.y), make_float2(g1.z, g1.w)};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 g = __fmul2_rn(dv[k], gm[k]);
+            s1v = __fadd2_rn(s1v, g);
+            tv = __ffma2_rn(g, xv[k], tv);
           }
         }
       }
-      s1 = warp_sum(s1) / p.D;
-      s2 = warp_sum(s2) / p.D;
+      const float s1 = warp_sum(s1v.x + s1v.y) * inv_d;
+      const float t = warp_sum(tv.x + tv.y) * inv_d;
+      const float s2 = rstd * (t - mean * s1);
+      const float bcoef = -rstd * rstd * s2, ccoef = -rstd * s1 - bcoef * mean;
+      const float2 b2 = make_float2(bcoef, bcoef), c2 = make_float2(ccoef, ccoef), r2 = make_float2(rstd, rstd);
       __nv_bfloat16* dxr = p.dx + irow * p.lddx;
-      const uint32_t rh_dx2 = p.dx2_drop_p > 0.f ? drop_rowhash(p.dx2_seed, static_cast<uint64_t>(irow)) : 0u;
+      const uint32_t rh_dx2 = dx2_drop ? drop_rowhash(p.dx2_seed, static_cast<uint64_t>(irow)) : 0u;
+      const float2 dx2s = make_float2(p.dx2_scale, p.dx2_scale);
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         const int vidx = lane + 32 * i;
         if (vidx < nvec) {
-          float xv[8], dv[8], gm[8], o[8];
-          unpack8(qx[i], xv); unpack8(qd[i], dv);
-          load8f(p.gamma + vidx * 8, gm);
+          float2 xv[4], dv[4], o[4];
+          unpack8x2(qx[i], xv); unpack8x2(qd[i], dv);
+          const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + vidx * 8));
+          const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + vidx * 8) + 1);
+          const float2 gm[4] = {make_float2(g0.x, g0.y), make_float2(g0.z, g0.w), make_float2(g1.x, g1.y), make_float2(g1.z, g1.w)};
 #pragma unroll
-          for (int k = 0; k < 8; ++k) o[k] = rstd * (dv[k] * gm[k] - s1 - (xv[k] - mean) * rstd * s2);
-          *(reinterpret_cast<uint4*>(dxr) + vidx) = pack8(o);
+          for (int k = 0; k < 4; ++k) o[k] = __ffma2_rn(dv[k], __fmul2_rn(gm[k], r2), __ffma2_rn(xv[k], b2, c2));
+          *(reinterpret_cast<uint4*>(dxr) + vidx) = pack8x2(o);
           if (p.dx2) {
-            if (p.dx2_drop_p > 0.f) drop8(o, rh_dx2, vidx * 8, p.dx2_thresh, p.dx2_scale, p.coltab);
-            *(reinterpret_cast<uint4*>(p.dx2 + irow * p.lddx) + vidx) = pack8(o);
+            if (dx2_drop) {
+              dropmask8x2(o, rh_dx2, vidx * 8, p.dx2_thresh, p.coltab);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) o[k] = __fmul2_rn(o[k], dx2s);
+            }
+            *(reinterpret_cast<uint4*>(p.dx2 + irow * p.lddx) + vidx) = pack8x2(o);
           }
         }
       }
     }
     __syncthreads();   // dx / dx2 of this row block are written (visible CTA-wide after the barrier)
-    // ---------------- phase 2: column sums over rows [base, rend)
+    // ---------------- phase 2: column sums over rows [base, rend); the rows are re-read (L1 / L2 hits)
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
       const int col = c4 + 1024 * j;
       if (col < p.D) {
-        float4 gm = make_float4(0.f, 0.f, 0.f, 0.f);
-        (void)gm;
+        uint4 ch = make_uint4(0u, 0u, 0u, 0u);
+        if (dy_drop) ch = __ldg(reinterpret_cast<const uint4*>(p.coltab + col));
         for (int rb = base; rb < rend; rb += 4) {   // 4 rows (12 independent 64-bit loads) in flight per thread
           uint2 qx[4], qd[4], qo[4];
-          float mean[4], rstd[4];
+          float rs[4], nmr[4];
           long long orow[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int r = min(rb + u, rend - 1);
             const long long irow = remap_row(r, p.in_rows_in, p.in_rows_out, p.in_row_off);
             orow[u] = remap_row(r, p.out_rows_in, p.out_rows_out, p.out_row_off);
-            mean[u] = p.mean[r]; rstd[u] = p.rstd[r];
+            rs[u] = p.rstd[r]; nmr[u] = -p.mean[r] * rs[u];
             qx[u] = *reinterpret_cast<const uint2*>(p.x + irow * p.ldx + col);
             qd[u] = *reinterpret_cast<const uint2*>(p.dy + orow[u] * p.lddy + col);
             if (p.dbias) qo[u] = *reinterpret_cast<const uint2*>((p.dx2 ? p.dx2 : p.dx) + irow * p.lddx + col);
@@ -377,24 +423,26 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const LnBwdParams
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             if (rb + u < rend) {
-              float xv[4] = {bf16_lo(qx[u].x), bf16_hi(qx[u].x), bf16_lo(qx[u].y), bf16_hi(qx[u].y)};
-              float dv[4] = {bf16_lo(qd[u].x), bf16_hi(qd[u].x), bf16_lo(qd[u].y), bf16_hi(qd[u].y)};
-              if (p.dy_drop_p > 0.f) {
+              float2 xv[2] = {make_float2(bf16_lo(qx[u].x), bf16_hi(qx[u].x)), make_float2(bf16_lo(qx[u].y), bf16_hi(qx[u].y))};
+              float2 dv[2] = {make_float2(bf16_lo(qd[u].x), bf16_hi(qd[u].x)), make_float2(bf16_lo(qd[u].y), bf16_hi(qd[u].y))};
+              if (dy_drop) {
                 const uint32_t rh = drop_rowhash(p.dy_seed, static_cast<uint64_t>(orow[u]));
-                const uint4 ch = __ldg(reinterpret_cast<const uint4*>(p.coltab + col));
-                dv[0] = drop_keep_rc(rh, ch.x, p.dy_thresh) ? dv[0] * p.dy_scale : 0.f;
-                dv[1] = drop_keep_rc(rh, ch.y, p.dy_thresh) ? dv[1] * p.dy_scale : 0.f;
-                dv[2] = drop_keep_rc(rh, ch.z, p.dy_thresh) ? dv[2] * p.dy_scale : 0.f;
-                dv[3] = drop_keep_rc(rh, ch.w, p.dy_thresh) ? dv[3] * p.dy_scale : 0.f;
+                if (!drop_keep_rc(rh, ch.x, p.dy_thresh)) dv[0].x = 0.f;
+                if (!drop_keep_rc(rh, ch.y, p.dy_thresh)) dv[0].y = 0.f;
+                if (!drop_keep_rc(rh, ch.z, p.dy_thresh)) dv[1].x = 0.f;
+                if (!drop_keep_rc(rh, ch.w, p.dy_thresh)) dv[1].y = 0.f;
+                dv[0] = __fmul2_rn(dv[0], make_float2(p.dy_scale, p.dy_scale));
+                dv[1] = __fmul2_rn(dv[1], make_float2(p.dy_scale, p.dy_scale));
               }
+              const float2 r2 = make_float2(rs[u], rs[u]), n2 = make_float2(nmr[u], nmr[u]);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                cg[j][k] += dv[k] * (xv[k] - mean[u]) * rstd[u];
-                cb[j][k] += dv[k];
+              for (int k = 0; k < 2; ++k) {
+                cg[j][k] = __ffma2_rn(dv[k], __ffma2_rn(xv[k], r2, n2), cg[j][k]);   // dy * xhat
+                cb[j][k] = __fadd2_rn(cb[j][k], dv[k]);
               }
               if (p.dbias) {
-                cbias[j][0] += bf16_lo(qo[u].x); cbias[j][1] += bf16_hi(qo[u].x);
-                cbias[j][2] += bf16_lo(qo[u].y); cbias[j][3] += bf16_hi(qo[u].y);
+                cbias[j][0] = __fadd2_rn(cbias[j][0], make_float2(bf16_lo(qo[u].x), bf16_hi(qo[u].x)));
+                cbias[j][1] = __fadd2_rn(cbias[j][1], make_float2(bf16_lo(qo[u].y), bf16_hi(qo[u].y)));
               }
             }
           }
@@ -408,13 +456,241 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const LnBwdParams
     const int col = c4 + 1024 * j;
     if (col < p.D) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        atomicAdd(p.dgamma + col + k, cg[j][k]);
-        atomicAdd(p.dbeta + col + k, cb[j][k]);
-        if (p.dbias) atomicAdd(p.dbias + col + k, cbias[j][k]);
+      for (int k = 0; k < 2; ++k) {
+        atomicAdd(p.dgamma + col + 2 * k, cg[j][k].x); atomicAdd(p.dgamma + col + 2 * k + 1, cg[j][k].y);
+        atomicAdd(p.dbeta + col + 2 * k, cb[j][k].x); atomicAdd(p.dbeta + col + 2 * k + 1, cb[j][k].y);
+        if (p.dbias) { atomicAdd(p.dbias + col + 2 * k, cbias[j][k].x); atomicAdd(p.dbias + col + 2 * k + 1, cbias[j][k].y); }
       }
     }
   }
+}
+
+// ---- TMA-pipelined variant (no row remap) --------------------------------------------------------------------
+// The kernel above is latency-bound: each warp serialises load -> reduce -> compute -> store for its row and the
+// column phase re-reads the rows from L2.  Here blocks of 8 rows (x and dy) arrive in a 3-stage shared-memory
+// ring by TMA, two blocks ahead of the math; both phases read shared memory, dx2 (the operand of the bias-gradient
+// column sum) is staged in shared memory too, and global memory is touched exactly once per element.
+// Stage layout = TMA boxes [chunk j][8 rows][bc columns] (bc = box width, a divisor of D).
+constexpr int LNT_ROWS = 8, LNT_STAGES = 3;
+
+// explicit shared-space accesses (32-bit shared addresses): the compiler cannot prove the address space of the
+// aligned dynamic shared-memory pointer and would emit generic loads with 64-bit address arithmetic
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t a) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float lds32f(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256, 2)
+layernorm_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
+                         const __grid_constant__ LnBwdParams p, const int bc) {
+  extern __shared__ uint8_t lnt_smem_raw[];
+  const uint32_t smem = (smem_u32(lnt_smem_raw) + 127u) & ~127u;   // shared-space address of the aligned block
+  const uint32_t bar0 = smem;                                       // full[3]
+  const uint32_t s_rstd = smem + 32, s_nmr = smem + 64;             // [8] each; nmr = -mean * rstd
+  const uint32_t row_bytes = p.D * 2u, half_stage = LNT_ROWS * row_bytes, stage_bytes = 2 * half_stage;
+  const uint32_t ring = smem + 128;
+  const uint32_t s_dx2 = ring + LNT_STAGES * stage_bytes;           // [8][D] bf16, row-major
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nvec = p.D >> 3, vpc = bc >> 3, nchunk = p.D / bc;
+  const int nblk = (p.rows + LNT_ROWS - 1) / LNT_ROWS;
+  const int nmine = blockIdx.x < nblk ? (nblk - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap_x); tma_prefetch_desc(&tmap_dy);
+    for (int s = 0; s < LNT_STAGES; ++s) mbar_init(bar0 + 8 * s, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  auto issue = [&](int k) {   // thread 0: block k of this CTA -> stage k % 3
+    const int st = k % LNT_STAGES, r0 = (blockIdx.x + k * gridDim.x) * LNT_ROWS;
+    const uint32_t bar = bar0 + 8 * st, dst = ring + st * stage_bytes;
+    mbar_expect_tx(bar, stage_bytes);
+    for (int j = 0; j < nchunk; ++j) {
+      tma_load_2d(dst + j * LNT_ROWS * bc * 2, &tmap_x, bar, j * bc, r0);
+      tma_load_2d(dst + half_stage + j * LNT_ROWS * bc * 2, &tmap_dy, bar, j * bc, r0);
+    }
+  };
+  if (threadIdx.x == 0) {
+    if (nmine > 0) issue(0);
+    if (nmine > 1) issue(1);
+  }
+  // this lane's vectors (8 columns each) of row `warp` inside a half stage, and this thread's phase-2 columns
+  uint32_t voff[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int v = lane + 32 * i, j = v / vpc, q = v - j * vpc;
+    voff[i] = ((j * LNT_ROWS + warp) * bc + q * 8) * 2;
+  }
+  constexpr int NJ = (NV * 256 + 1023) / 1024;
+  uint32_t coff[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int col = threadIdx.x * 4 + 1024 * j, cj = col / bc, cq = col - cj * bc;
+    coff[j] = (cj * LNT_ROWS * bc + cq) * 2;
+  }
+  float2 cg[NJ][2], cb[NJ][2], cbias[NJ][2];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j)
+#pragma unroll
+    for (int k = 0; k < 2; ++k) cg[j][k] = cb[j][k] = cbias[j][k] = make_float2(0.f, 0.f);
+  const float inv_d = 1.f / p.D;
+  const bool dy_drop = p.dy_drop_p > 0.f, dx2_drop = p.dx2_drop_p > 0.f;
+  const uint32_t bc2 = bc * 2;
+
+  for (int k = 0; k < nmine; ++k) {
+    const int st = k % LNT_STAGES, r0 = (blockIdx.x + k * gridDim.x) * LNT_ROWS;
+    // stage (k+2) % 3 was read by block k-1: every thread passed that block's trailing barrier
+    if (threadIdx.x == 0 && k + 2 < nmine) {
+      fence_proxy_async_smem();   // generic-proxy accesses of that stage are ordered before the TMA writes
+      issue(k + 2);
+    }
+    mbar_wait(bar0 + 8 * st, (k / LNT_STAGES) & 1);
+    const uint32_t sx = ring + st * stage_bytes, sdy = sx + half_stage;
+    const int r = r0 + warp;
+    // ---------------- phase 1: warp = row; the unpacked row stays in registers for the second pass
+    if (r < p.rows) {
+      const float mean = p.mean[r], rstd = p.rstd[r];
+      const uint32_t rh_dy = dy_drop ? drop_rowhash(p.dy_seed, static_cast<uint64_t>(r)) : 0u;
+      float2 xv[NV][4], dv[NV][4];
+      float2 s1v = make_float2(0.f, 0.f), tv = make_float2(0.f, 0.f);
+      const float2 dys = make_float2(p.dy_scale, p.dy_scale);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int vidx = lane + 32 * i;
+        if (vidx < nvec) {
+          unpack8x2(lds128(sx + voff[i]), xv[i]);
+          unpack8x2(lds128(sdy + voff[i]), dv[i]);
+          if (dy_drop) {   // the incoming gradient passes the forward's dropout mask first; phase 2 reads the masked copy
+            dropmask8x2(dv[i], rh_dy, vidx * 8, p.dy_thresh, p.coltab);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) dv[i][kk] = __fmul2_rn(dv[i][kk], dys);
+            sts128(sdy + voff[i], pack8x2(dv[i]));
+          }
+          const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + vidx * 8));
+          const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + vidx * 8) + 1);
+          const float2 gm[4] = {make_float2(g0.x, g0.y), make_float2(g0.z, g0.w), make_float2(g1.x, g1.y), make_float2(g1.z, g1.w)};
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            dv[i][kk] = __fmul2_rn(dv[i][kk], gm[kk]);   // g = dy * gamma (dy itself is not needed again)
+            s1v = __fadd2_rn(s1v, dv[i][kk]);
+            tv = __ffma2_rn(dv[i][kk], xv[i][kk], tv);
+          }
+        }
+      }
+      const float s1 = warp_sum(s1v.x + s1v.y) * inv_d;
+      const float t = warp_sum(tv.x + tv.y) * inv_d;
+      const float s2 = rstd * (t - mean * s1);
+      if (lane == 0) {
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(s_rstd + 4 * warp), "f"(rstd) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(s_nmr + 4 * warp), "f"(-mean * rstd) : "memory");
+      }
+      // dx = rstd * g + x * b + c
+      const float bcoef = -rstd * rstd * s2, ccoef = -rstd * s1 - bcoef * mean;
+      const float2 b2 = make_float2(bcoef, bcoef), c2 = make_float2(ccoef, ccoef), r2 = make_float2(rstd, rstd);
+      __nv_bfloat16* dxr = p.dx + static_cast<long long>(r) * p.lddx;
+      const uint32_t rh_dx2 = dx2_drop ? drop_rowhash(p.dx2_seed, static_cast<uint64_t>(r)) : 0u;
+      const float2 dx2s = make_float2(p.dx2_scale, p.dx2_scale);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int vidx = lane + 32 * i;
+        if (vidx < nvec) {
+          float2 o[4];
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) o[kk] = __ffma2_rn(dv[i][kk], r2, __ffma2_rn(xv[i][kk], b2, c2));
+          uint4 q = pack8x2(o);
+          *(reinterpret_cast<uint4*>(dxr) + vidx) = q;
+          if (p.dx2) {
+            if (dx2_drop) {
+              dropmask8x2(o, rh_dx2, vidx * 8, p.dx2_thresh, p.coltab);
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) o[kk] = __fmul2_rn(o[kk], dx2s);
+              q = pack8x2(o);
+            }
+            *(reinterpret_cast<uint4*>(p.dx2 + static_cast<long long>(r) * p.lddx) + vidx) = q;
+          }
+          if (p.dbias) sts128(s_dx2 + warp * row_bytes + vidx * 16, q);
+        }
+      }
+    }
+    __syncthreads();
+    // ---------------- phase 2: thread = 4 columns, all rows of the block from shared memory
+    const int nr = min(LNT_ROWS, p.rows - r0);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int col = threadIdx.x * 4 + 1024 * j;
+      if (col < p.D) {
+        uint32_t ax = sx + coff[j], ad = sdy + coff[j], ao = s_dx2 + col * 2;
+#pragma unroll
+        for (int u = 0; u < LNT_ROWS; ++u) {
+          if (u < nr) {
+            const uint2 qx = lds64(ax), qd = lds64(ad);
+            const float2 xv[2] = {make_float2(bf16_lo(qx.x), bf16_hi(qx.x)), make_float2(bf16_lo(qx.y), bf16_hi(qx.y))};
+            const float2 dv[2] = {make_float2(bf16_lo(qd.x), bf16_hi(qd.x)), make_float2(bf16_lo(qd.y), bf16_hi(qd.y))};
+            const float rs = lds32f(s_rstd + 4 * u), nm = lds32f(s_nmr + 4 * u);
+            const float2 r2 = make_float2(rs, rs), n2 = make_float2(nm, nm);
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+              cg[j][kk] = __ffma2_rn(dv[kk], __ffma2_rn(xv[kk], r2, n2), cg[j][kk]);   // dy * xhat
+              cb[j][kk] = __fadd2_rn(cb[j][kk], dv[kk]);
+            }
+            if (p.dbias) {
+              const uint2 qo = lds64(ao);
+              cbias[j][0] = __fadd2_rn(cbias[j][0], make_float2(bf16_lo(qo.x), bf16_hi(qo.x)));
+              cbias[j][1] = __fadd2_rn(cbias[j][1], make_float2(bf16_lo(qo.y), bf16_hi(qo.y)));
+            }
+          }
+          ax += bc2; ad += bc2; ao += row_bytes;
+        }
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int col = threadIdx.x * 4 + 1024 * j;
+    if (col < p.D) {
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        atomicAdd(p.dgamma + col + 2 * kk, cg[j][kk].x); atomicAdd(p.dgamma + col + 2 * kk + 1, cg[j][kk].y);
+        atomicAdd(p.dbeta + col + 2 * kk, cb[j][kk].x); atomicAdd(p.dbeta + col + 2 * kk + 1, cb[j][kk].y);
+        if (p.dbias) { atomicAdd(p.dbias + col + 2 * kk, cbias[j][kk].x); atomicAdd(p.dbias + col + 2 * kk + 1, cbias[j][kk].y); }
+      }
+    }
+  }
+}
+
+template <int NV>
+static int launch_ln_bwd_tma(const LnBwdParams& p, int bc, cudaStream_t st) {
+  CUtensorMap tx, td;
+  int rc;
+  if ((rc = make_tmap_2d_bf16(&tx, p.x, p.rows, p.D, p.ldx, bc, LNT_ROWS, 0))) return rc;
+  if ((rc = make_tmap_2d_bf16(&td, p.dy, p.rows, p.D, p.lddy, bc, LNT_ROWS, 0))) return rc;
+  const int smem = 128 + 128 + (2 * LNT_STAGES + 1) * LNT_ROWS * p.D * 2;
+  static bool attr_set = false;
+  if (!attr_set) {
+    XF_CUDA(cudaFuncSetAttribute(layernorm_bwd_tma_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+    attr_set = true;
+  }
+  const int nblk = (p.rows + LNT_ROWS - 1) / LNT_ROWS;
+  int ctas = 2 * sm_count();
+  if (ctas > nblk) ctas = nblk;
+  layernorm_bwd_tma_kernel<NV><<<ctas, 256, smem, st>>>(tx, td, p, bc);
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -696,6 +972,25 @@ extern "C" int xf_layernorm_bwd(const XfLayerNormBwd* a, xf_stream_t s) {
   const size_t sh = 0;
   if (a->D % 4) return fail(-4, "xf_layernorm_bwd: D must be a multiple of 4");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(s);
+  // TMA-pipelined kernel: contiguous row ranges (no remap), 16-byte aligned operands, stage ring within 113 KB
+  {
+    int bc = 0;
+    for (int c = 256; c >= 8; c -= 8)
+      if (a->D % c == 0) { bc = c; break; }
+    const bool aligned = ((reinterpret_cast<uintptr_t>(a->x) | reinterpret_cast<uintptr_t>(a->dy) | reinterpret_cast<uintptr_t>(a->dx) |
+                           reinterpret_cast<uintptr_t>(a->dx2)) & 15) == 0;
+    const int smem = 256 + (2 * LNT_STAGES + 1) * LNT_ROWS * a->D * 2;
+    if (a->in_rows_in == 0 && a->out_rows_in == 0 && bc >= 8 && aligned && smem <= 113 * 1024 && nv <= 4) {
+      int rc;
+      if (nv <= 1) rc = launch_ln_bwd_tma<1>(p, bc, st);
+      else if (nv <= 2) rc = launch_ln_bwd_tma<2>(p, bc, st);
+      else rc = launch_ln_bwd_tma<4>(p, bc, st);
+      if (rc) return rc;
+      g_launches.fetch_add(1);
+      XF_CUDA(cudaGetLastError());
+      return 0;
+    }
+  }
   if (nv <= 1) layernorm_bwd_kernel<1><<<ctas, 256, sh, st>>>(p);
   else if (nv <= 2) layernorm_bwd_kernel<2><<<ctas, 256, sh, st>>>(p);
   else if (nv <= 4) layernorm_bwd_kernel<4><<<ctas, 256, sh, st>>>(p);

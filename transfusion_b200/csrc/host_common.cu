@@ -30,8 +30,10 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t
   if (!enc) return fail(-10, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return fail(-11, "TMA base pointer not 16-byte aligned");
   if ((ld * 2) % 16 != 0) return fail(-12, "TMA row pitch %llu B not a multiple of 16", (unsigned long long)(ld * 2));
-  if (static_cast<int>(box_cols * 2) > swizzle_bytes || box_rows > 256) return fail(-13, "bad TMA box %u x %u", box_cols, box_rows);
-  const CUtensorMapSwizzle swz2 = swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  if ((swizzle_bytes > 0 && static_cast<int>(box_cols * 2) > swizzle_bytes) || box_cols > 256 || box_rows > 256)
+    return fail(-13, "bad TMA box %u x %u", box_cols, box_rows);
+  const CUtensorMapSwizzle swz2 = swizzle_bytes == 0 ? CU_TENSOR_MAP_SWIZZLE_NONE
+                                : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstr[1] = {ld * 2};
   cuuint32_t box[2] = {box_cols, box_rows};
