@@ -140,6 +140,17 @@ int xf_cast_pad(const float* src, int64_t lds, void* dst_bf16, int64_t ldd, int 
 int xf_unpad_add(const float* src_padded, int64_t lds, float* dst, int64_t ldd, int rows, int cols, int rin, int rout, int cin,
                  int cout, xf_stream_t stream);
 
+/* The same cast for up to XF_CAST_MAX_JOBS tensors in ONE launch (all bf16 weight copies of an FPN level:
+ * 18 small tensors whose separate launches were latency-bound).  Replaces the implicit per-module
+ * fp32 -> autocast-bf16 weight conversions of ego_fusion/cross_f_box_layers.py:75-103. */
+#define XF_CAST_MAX_JOBS 32
+typedef struct XfCastJob {
+  const float* src; int64_t lds;
+  void* dst_bf16;   int64_t ldd;
+  int32_t rows, cols, rin, rout, cin, cout;
+} XfCastJob;
+int xf_cast_pad_multi(const XfCastJob* jobs, int n_jobs, xf_stream_t stream);
+
 /* delta[b, h, s] = sum_e O[b*S+s, h*dp+e] * dO[b*S+s, h*dp+e]  (attention backward pre-pass);
  * delta is [B, H, stat_stride] like the LSE. */
 int xf_attn_delta(const void* o_bf16, const void* do_bf16, int64_t ld, int B, int S, int heads, int dp, int stat_stride,

@@ -293,6 +293,16 @@ def test_small_kernels():
     ops.cast_pad(w, wp, 30, 24, rin=10, rout=16)
     assert torch.equal(wp.view(3, 16, 24)[:, :10].reshape(30, 24), w.bfloat16())
     assert float(wp.view(3, 16, 24)[:, 10:].float().abs().max()) == 0
+    # multi-tensor cast: plain, row-padded, column-padded and an odd-shaped job (single-tensor fallback) in one call
+    ws = [torch.randn(64, 48, device=DEV), torch.randn(30, 24, device=DEV), torch.randn(16, 40, device=DEV), torch.randn(5, 7, device=DEV)]
+    ds = [torch.zeros(64, 48, device=DEV, dtype=torch.bfloat16), torch.zeros(48, 24, device=DEV, dtype=torch.bfloat16),
+          torch.zeros(16, 64, device=DEV, dtype=torch.bfloat16), torch.zeros(5, 7, device=DEV, dtype=torch.bfloat16)]
+    ops.cast_pad_multi([(ws[0], ds[0], 64, 48, 0, 0, 0, 0), (ws[1], ds[1], 30, 24, 10, 16, 0, 0),
+                        (ws[2], ds[2], 16, 40, 0, 0, 10, 16), (ws[3], ds[3], 5, 7, 0, 0, 0, 0)])
+    assert torch.equal(ds[0], ws[0].bfloat16()) and torch.equal(ds[3], ws[3].bfloat16())
+    assert torch.equal(ds[1].view(3, 16, 24)[:, :10].reshape(30, 24), ws[1].bfloat16())
+    assert torch.equal(ds[2].view(16, 4, 16)[:, :, :10].reshape(16, 40), ws[2].bfloat16())
+    assert float(ds[2].view(16, 4, 16)[:, :, 10:].float().abs().max()) == 0
     gsrc, gdst = torch.randn(30, 48, device=DEV), torch.ones(30, 30, device=DEV)
     ops.unpad_add(gsrc, gdst, 30, 30, cin=10, cout=16)
     assert torch.allclose(gdst, 1 + gsrc.view(30, 3, 16)[:, :, :10].reshape(30, 30))

@@ -34,6 +34,17 @@ class XfGemm(C.Structure):
     ]
 
 
+class XfCastJob(C.Structure):
+    _fields_ = [
+        ("src", C.c_void_p), ("lds", C.c_int64),
+        ("dst_bf16", C.c_void_p), ("ldd", C.c_int64),
+        ("rows", C.c_int32), ("cols", C.c_int32), ("rin", C.c_int32), ("rout", C.c_int32), ("cin", C.c_int32), ("cout", C.c_int32),
+    ]
+
+
+XF_CAST_MAX_JOBS = 32
+
+
 class XfLayerNorm(C.Structure):
     _fields_ = [
         ("x", C.c_void_p), ("ldx", C.c_int64),
@@ -126,7 +137,7 @@ def lib():
 EXPORTS = [
     "xf_version", "xf_last_error", "xf_launch_count", "xf_gemm",
     "xf_patchify", "xf_fold", "xf_lang_rows_fwd", "xf_lang_rows_bwd",
-    "xf_layernorm_fwd", "xf_layernorm_bwd", "xf_colsum", "xf_cast_pad", "xf_unpad_add",
+    "xf_layernorm_fwd", "xf_layernorm_bwd", "xf_colsum", "xf_cast_pad", "xf_cast_pad_multi", "xf_unpad_add",
     "xf_attn_delta", "xf_attn_fwd", "xf_attn_bwd", "xf_rows_gather",
 ]
 

@@ -135,26 +135,28 @@ class FusionLevelFunction(torch.autograd.Function):
         pd_back = cfg.backproj_dropout if train else 0.0
         seed = cfg.seed
 
-        # ---- bf16 weight copies (head dim padded d -> dp with zero rows / columns)
-        wpe_b = empty(D, K); ops.cast_pad(wpe.reshape(D, K), wpe_b, D, K)
-        wbp_b = empty(K, D); ops.cast_pad(wbp, wbp_b, K, D)
+        # ---- bf16 weight copies (head dim padded d -> dp with zero rows / columns): one launch for the level
+        casts = []
+        wpe_b = empty(D, K); casts.append((wpe.reshape(D, K), wpe_b, D, K, 0, 0, 0, 0))
+        wbp_b = empty(K, D); casts.append((wbp, wbp_b, K, D, 0, 0, 0, 0))
         lw = []
         for (in_w, in_b, out_w, out_b, w1, b1, w2, b2, n1w, n1b, n2w, n2b) in layer_params:
             if dp != d:
                 win_b = torch.zeros(3 * Dp, D, device=dev, dtype=bf)
-                ops.cast_pad(in_w, win_b, 3 * D, D, rin=d, rout=dp)
+                casts.append((in_w, win_b, 3 * D, D, d, dp, 0, 0))
                 bin_p = torch.zeros(3 * H, dp, device=dev, dtype=torch.float32)
                 bin_p[:, :d] = in_b.reshape(3 * H, d)
                 bin_p = bin_p.reshape(3 * Dp)
                 wo_b = torch.zeros(D, Dp, device=dev, dtype=bf)
-                ops.cast_pad(out_w, wo_b, D, D, cin=d, cout=dp)
+                casts.append((out_w, wo_b, D, D, 0, 0, d, dp))
             else:
-                win_b = empty(3 * D, D); ops.cast_pad(in_w, win_b, 3 * D, D)
+                win_b = empty(3 * D, D); casts.append((in_w, win_b, 3 * D, D, 0, 0, 0, 0))
                 bin_p = in_b
-                wo_b = empty(D, D); ops.cast_pad(out_w, wo_b, D, D)
-            w1_b = empty(F, D); ops.cast_pad(w1, w1_b, F, D)
-            w2_b = empty(D, F); ops.cast_pad(w2, w2_b, D, F)
+                wo_b = empty(D, D); casts.append((out_w, wo_b, D, D, 0, 0, 0, 0))
+            w1_b = empty(F, D); casts.append((w1, w1_b, F, D, 0, 0, 0, 0))
+            w2_b = empty(D, F); casts.append((w2, w2_b, D, F, 0, 0, 0, 0))
             lw.append((win_b, bin_p, wo_b, w1_b, w2_b))
+        ops.cast_pad_multi(casts)
 
         # ---- patch embedding + positional / kind embeddings, language rows   (K1-K4)
         tok = empty(B * n, K)

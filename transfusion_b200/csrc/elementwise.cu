@@ -761,6 +761,36 @@ __global__ void __launch_bounds__(256) cast_vec8_kernel(const float4* __restrict
   }
 }
 
+// all jobs of one call in a single launch: work unit = 8 consecutive source elements of a row
+struct CastJobs {
+  int n;
+  long long unit_start[XF_CAST_MAX_JOBS + 1];   // prefix sums of units per job
+  XfCastJob job[XF_CAST_MAX_JOBS];
+};
+__global__ void __launch_bounds__(256) cast_multi_kernel(const __grid_constant__ CastJobs js) {
+  const long long total = js.unit_start[js.n];
+  int j = 0;
+  for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < total;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    while (t >= js.unit_start[j + 1]) ++j;   // t only grows
+    const XfCastJob& J = js.job[j];
+    const long long u = t - js.unit_start[j];
+    const int upr = J.cols >> 3;              // units per row (cols % 8 == 0)
+    const int r = static_cast<int>(u / upr), c = static_cast<int>(u - static_cast<long long>(r) * upr) * 8;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(J.src + static_cast<long long>(r) * J.lds + c));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(J.src + static_cast<long long>(r) * J.lds + c) + 1);
+    const long long dr = J.rin > 0 ? static_cast<long long>(r / J.rin) * J.rout + r % J.rin : r;
+    __nv_bfloat16* drow = reinterpret_cast<__nv_bfloat16*>(J.dst_bf16) + dr * J.ldd;
+    if (J.cin > 0) {   // column blocks are padded: element-wise destination columns
+      const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) drow[static_cast<long long>((c + k) / J.cin) * J.cout + (c + k) % J.cin] = __float2bfloat16(v[k]);
+    } else {
+      *reinterpret_cast<uint4*>(drow + c) = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+    }
+  }
+}
+
 __global__ void unpad_add_kernel(const float* __restrict__ src, long long lds, float* __restrict__ dst, long long ldd,
                                  int rows, int cols, int rin, int rout, int cin, int cout) {
   // dst is compact [rows, cols]; src is padded
@@ -1044,6 +1074,36 @@ extern "C" int xf_unpad_add(const float* src, int64_t lds, float* dst, int64_t l
   if (rows == 0 || cols == 0) return 0;
   unpad_add_kernel<<<grid_for(static_cast<long long>(rows) * cols, 256 * 4), 256, 0, reinterpret_cast<cudaStream_t>(s)>>>(
       src, lds, dst, ldd, rows, cols, rin, rout, cin, cout);
+  g_launches.fetch_add(1);
+  XF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int xf_cast_pad_multi(const XfCastJob* jobs, int n_jobs, xf_stream_t s) {
+  if (!jobs || n_jobs < 0) return fail(-1, "xf_cast_pad_multi: null pointer");
+  if (n_jobs > XF_CAST_MAX_JOBS) return fail(-2, "xf_cast_pad_multi: at most %d jobs per call", XF_CAST_MAX_JOBS);
+  CastJobs js;
+  memset(&js, 0, sizeof(js));
+  long long units = 0;
+  for (int i = 0; i < n_jobs; ++i) {
+    const XfCastJob& J = jobs[i];
+    if (!J.src || !J.dst_bf16) return fail(-1, "xf_cast_pad_multi: null pointer in job %d", i);
+    if (J.rows <= 0 || J.cols <= 0) continue;
+    const bool ok = J.cols % 8 == 0 && J.lds % 4 == 0 && (reinterpret_cast<uintptr_t>(J.src) & 15) == 0 &&
+                    (J.cin > 0 || (J.ldd % 8 == 0 && (reinterpret_cast<uintptr_t>(J.dst_bf16) & 15) == 0));
+    if (!ok) {   // odd shapes / alignments: the single-tensor path handles them
+      int rc = xf_cast_pad(J.src, J.lds, J.dst_bf16, J.ldd, J.rows, J.cols, J.rin, J.rout, J.cin, J.cout, s);
+      if (rc) return rc;
+      continue;
+    }
+    js.job[js.n] = J;
+    js.unit_start[js.n] = units;
+    units += static_cast<long long>(J.rows) * (J.cols / 8);
+    ++js.n;
+  }
+  js.unit_start[js.n] = units;
+  if (units == 0) return 0;
+  cast_multi_kernel<<<grid_for(units, 256), 256, 0, reinterpret_cast<cudaStream_t>(s)>>>(js);
   g_launches.fetch_add(1);
   XF_CUDA(cudaGetLastError());
   return 0;

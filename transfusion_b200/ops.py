@@ -208,6 +208,23 @@ def cast_pad(src: torch.Tensor, dst: torch.Tensor, rows: int, cols: int, rin=0, 
           "xf_cast_pad")
 
 
+def cast_pad_multi(jobs):
+    """jobs: iterable of (src fp32, dst bf16, rows, cols, rin, rout, cin, cout) -- one launch per 32 tensors."""
+    jobs = list(jobs)
+    for i in range(0, len(jobs), _lib.XF_CAST_MAX_JOBS):
+        chunk = jobs[i:i + _lib.XF_CAST_MAX_JOBS]
+        arr = (_lib.XfCastJob * len(chunk))()
+        nbytes = 0.0
+        for j, (src, dst, rows, cols, rin, rout, cin, cout) in zip(arr, chunk):
+            _req(src, torch.float32, "src"); _req(dst, torch.bfloat16, "dst")
+            j.src, j.lds = src.data_ptr(), (src.stride(0) if src.dim() > 1 else cols)
+            j.dst_bf16, j.ldd = dst.data_ptr(), (dst.stride(0) if dst.dim() > 1 else cols)
+            j.rows, j.cols, j.rin, j.rout, j.cin, j.cout = rows, cols, rin, rout, cin, cout
+            nbytes += 6.0 * rows * cols
+        with _Prof("cast", 0.0, nbytes):
+            check(lib().xf_cast_pad_multi(arr, len(chunk), _stream()), "xf_cast_pad_multi")
+
+
 def unpad_add(src: torch.Tensor, dst: torch.Tensor, rows: int, cols: int, rin=0, rout=0, cin=0, cout=0):
     _req(src, torch.float32, "src"); _req(dst, torch.float32, "dst")
     with _Prof("cast", 0.0, 12.0 * rows * cols):
