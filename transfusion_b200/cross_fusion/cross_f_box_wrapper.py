@@ -8,6 +8,8 @@ as ~60 ATen calls; here each level is ONE autograd node (FusionLevelFunction) th
 hand-written sm_100a kernels of libxfusion_sm100a.so.  There is no PyTorch fallback."""
 from __future__ import annotations
 
+import os as _os
+
 import torch
 from torch import nn
 
@@ -17,6 +19,7 @@ from .lm_layers import get_lm_layer
 from .utils import PositionalEmbeddingLayer, RegroupPatchesLayerBox, get_visual_token_mask
 
 MAX_NUM_PATCHES = 8192  # cross_f_box_wrapper.py:21
+LEVEL_STREAMS = bool(int(_os.environ.get("XF_LEVEL_STREAMS", "1")))   # run independent FPN levels on side streams
 
 
 def _default_pooling_factory(narr_embed_args, cross_layer_args):
@@ -136,6 +139,21 @@ class CrossFusionBoxWrapper(nn.Module):
         fused, lang_out = FusionLevelFunction.apply(cfg, feat, language_f, lang_pad_mask, *params)
         return fused, (lang_out if need_lang_out else None)
 
+    def _level_streams(self, ref):
+        """One side stream per FPN level on `ref`'s device (None on CPU tensors: the kernels will raise anyway)."""
+        if not (isinstance(ref, torch.Tensor) and ref.is_cuda):
+            return None
+        cache = self.__dict__.setdefault("_xf_streams", {})
+        dev = ref.device.index
+        if dev not in cache:
+            cache[dev] = [torch.cuda.Stream(device=ref.device) for _ in range(len(self.fpn_features_idx))]
+            # parameter gradients are produced on the side streams and accumulated on the caller's stream: the
+            # engine inserts the synchronisation; the mismatch it warns about is intended
+            quiet = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+            if quiet is not None:
+                quiet(False)
+        return cache[dev]
+
     def forward(self, x, targets=None):
         visual_data = x[self.vis_input_key]
         features_dict = self.rcnn_model.forward_features(visual_data, targets)
@@ -150,12 +168,32 @@ class CrossFusionBoxWrapper(nn.Module):
         level_order = list(enumerate(self.fpn_features_idx))
         if not self.forward_language_f and not self.multi_lm:
             level_order = level_order[::-1]
+        # Independent levels run on their own CUDA streams: the persistent GEMM / attention kernels of one level
+        # fill the tail waves of another (the three coarse levels have 2.3 - 4.6 waves per GEMM), and autograd
+        # replays each level's backward on the stream its forward ran on.
+        side = self._level_streams(language_f) if (LEVEL_STREAMS and len(level_order) > 1 and not self.forward_language_f
+                                                   and not self.multi_lm) else None
+        cur = torch.cuda.current_stream() if side is not None else None
         for i, key in level_order:
             key = str(key)
             feat = features_dict["features"][key]
             self.tokens_to_features[i].init_h = feat.shape[2]
             self.tokens_to_features[i].init_w = feat.shape[3]
-            fused, fused_l_features = self.run_level(i, feat, language_f, lang_pad, need_lang_out)
+            if side is not None:
+                st = side[i % len(side)]
+                st.wait_stream(cur)
+                with torch.cuda.stream(st):
+                    fused, fused_l_features = self.run_level(i, feat, language_f, lang_pad, need_lang_out)
+                # inputs were allocated on the caller's stream and are read on `st`; the output is allocated on `st`
+                # and consumed on the caller's stream
+                for t in (feat, language_f, lang_pad):
+                    if isinstance(t, torch.Tensor) and t.is_cuda:
+                        t.record_stream(st)
+                fused.record_stream(cur)
+                if isinstance(fused_l_features, torch.Tensor):
+                    fused_l_features.record_stream(cur)
+            else:
+                fused, fused_l_features = self.run_level(i, feat, language_f, lang_pad, need_lang_out)
             if self.multi_lm:
                 mscale_l_features.append(fused_l_features)
             if self.forward_language_f:
@@ -166,6 +204,9 @@ class CrossFusionBoxWrapper(nn.Module):
                 else:
                     raise NotImplementedError()
             features_dict["features"][key] = fused
+        if side is not None:
+            for st in side:
+                cur.wait_stream(st)
         features_dict = self.rcnn_model.apply_fpn(features_dict)
         if "hand_boxes" in x:
             features_dict["hand_boxes"] = x["hand_boxes"]
