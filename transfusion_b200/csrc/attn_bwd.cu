@@ -137,12 +137,14 @@ attn_bwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gr
         const uint32_t lpar = ((i / NB_LONG) & 1) ^ 1, spar = ((i / NB_SHORT) & 1) ^ 1;
         const uint32_t la = smem_u32(sL + ls * t_bytes), sa = smem_u32(sS + ss * t_bytes);
         if (MODE != MODE_DV) {   // T1 -> long ring (score + accumulate), T2 -> short ring (score only)
-          mbar_wait(L_EMPTY(ls), lpar);
-          mbar_expect_tx(L_FULL(ls), t_bytes);
-          for (int c = 0; c < p.nch; ++c) tma_load_3d(la + c * 4096, &tmap_t1, L_FULL(ls), col0 + 32 * c, i * NB_BN, b);
+          // the short-ring slot is released first (after the score MMAs of tile i-2, one accumulate MMA earlier than
+          // the long-ring slot of tile i-3), so its load is requested first
           mbar_wait(S_EMPTY(ss), spar);
           mbar_expect_tx(S_FULL(ss), t_bytes);
           for (int c = 0; c < p.nch; ++c) tma_load_3d(sa + c * 4096, &tmap_t2, S_FULL(ss), col0 + 32 * c, i * NB_BN, b);
+          mbar_wait(L_EMPTY(ls), lpar);
+          mbar_expect_tx(L_FULL(ls), t_bytes);
+          for (int c = 0; c < p.nch; ++c) tma_load_3d(la + c * 4096, &tmap_t1, L_FULL(ls), col0 + 32 * c, i * NB_BN, b);
         } else {                 // T1 -> short ring (score only), T2 -> long ring (accumulate only)
           mbar_wait(S_EMPTY(ss), spar);
           mbar_expect_tx(S_FULL(ss), t_bytes);
