@@ -21,11 +21,20 @@ qkv = torch.empty(M, 3 * D, device=dev, dtype=torch.bfloat16)
 w1 = (torch.randn(2 * D, D, device=dev) * 0.03).bfloat16()
 b1 = torch.randn(2 * D, device=dev)
 u = torch.empty(M, 2 * D, device=dev, dtype=torch.bfloat16)
+w2 = (torch.randn(D, 2 * D, device=dev) * 0.03).bfloat16()
+wo = (torch.randn(D, D, device=dev) * 0.03).bfloat16()
+bo = torch.randn(D, device=dev)
 h = torch.empty(M, 2 * D, device=dev, dtype=torch.bfloat16)
 for it in range(2):
     # forward GEMMs
     ops.gemm(x, w_in, qkv, M=M, N=3 * D, K=D, bias=b_in)
     ops.gemm(x, w1, h, M=M, N=2 * D, K=D, bias=b1, act=1, preact_out=u, drop_p=0.15, drop_seed=1, drop_stream=2)
+    # FFN2 dgrad: GELU' from the saved pre-activation + dropout mask (EPI_DGELU)
+    dh = torch.empty(M, 2 * D, device=dev, dtype=torch.bfloat16)
+    ops.gemm(x, w2, dh, M=M, N=2 * D, K=D, b_mn_major=True, dact_in=u, drop_p=0.15, drop_seed=1, drop_stream=2)
+    # out-proj forward: bias + dropout + residual (EPI_LINEAR)
+    y1 = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
+    ops.gemm(x, wo, y1, M=M, N=D, K=D, bias=bo, drop_p=0.1, drop_seed=1, drop_stream=3, residual=x)
     # dgrad (B operand MN-major) and wgrad (both MN-major, split-K, fp32 atomics)
     dx = torch.empty(M, D, device=dev, dtype=torch.bfloat16)
     ops.gemm(h, w1, dx, M=M, N=D, K=2 * D, b_mn_major=True, residual=x)
