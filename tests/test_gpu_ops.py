@@ -126,7 +126,10 @@ def _pack(src, dp):
 
 
 @pytest.mark.parametrize("B,H,S,d,mask", [(2, 4, 300, 64, True), (2, 4, 832, 224, True), (2, 4, 333, 178, True),
-                                          (1, 2, 64, 32, False), (2, 4, 70, 16, True)])
+                                          (1, 2, 64, 32, False), (2, 4, 70, 16, True),
+                                          # the longest sequence the reference admits: MAX_NUM_PATCHES = 8192 visual tokens
+                                          # (cross_f_box_wrapper.py:21) + 64 language tokens
+                                          (1, 1, 8256, 32, True)])
 def test_attention_forward_backward(B, H, S, d, mask):
     torch.manual_seed(4)
     dp = (d + 31) // 32 * 32
