@@ -151,6 +151,28 @@ typedef struct XfCastJob {
 } XfCastJob;
 int xf_cast_pad_multi(const XfCastJob* jobs, int n_jobs, xf_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * LM head: PoolPredictor, modeling/cross_fusion/ego_fusion/lm_layers.py:30-81, in fp32.
+ *   pool   : pooled[b,d] = mean_l | max_l (tok[b,l,d] * mask[b,l])   (:60-66; mean divides by the padded L;
+ *            type 0 = mean, 1 = max; mask uint8 [B,L] 1 = valid, may be NULL; argmax [B,D] only for max)
+ *   rowln  : nn.LayerNorm over the rows of a small fp32 [rows, D] matrix (:68-69)
+ *   linear : y[r,c] = sum_d act(x[r,d]) W[c,d] + bias[c], act 0 = identity, 1 = GELU(erf) applied to the INPUT
+ *            (nn.Sequential(GELU, Linear) :43-45, mlp_noun / mlp_verb :47-55).  The backward ACCUMULATES into
+ *            dW / dbias (either may be NULL together with dx to skip that part).
+ * ------------------------------------------------------------------------------------------ */
+int xf_lm_pool_fwd(const float* tok, const uint8_t* mask, int B, int L, int D, int type, float* pooled, int32_t* argmax,
+                   xf_stream_t stream);
+int xf_lm_pool_bwd(const float* dpooled, const uint8_t* mask, const int32_t* argmax, int B, int L, int D, int type, float* dtok,
+                   xf_stream_t stream);
+int xf_rowln_fwd(const float* x, const float* gamma, const float* beta, int rows, int D, float eps, float* y, float* mean,
+                 float* rstd, xf_stream_t stream);
+int xf_rowln_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd, int rows, int D,
+                 float* dx, float* dgamma, float* dbeta, xf_stream_t stream);
+int xf_small_linear_fwd(const float* x, const float* W, const float* bias, int rows, int C, int D, int act, float* y,
+                        xf_stream_t stream);
+int xf_small_linear_bwd(const float* dy, const float* x, const float* W, int rows, int C, int D, int act, float* dx, float* dW,
+                        float* dbias, xf_stream_t stream);
+
 /* delta[b, h, s] = sum_e O[b*S+s, h*dp+e] * dO[b*S+s, h*dp+e]  (attention backward pre-pass);
  * delta is [B, H, stat_stride] like the LSE. */
 int xf_attn_delta(const void* o_bf16, const void* do_bf16, int64_t ld, int B, int S, int heads, int dp, int stat_stride,

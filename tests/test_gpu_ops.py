@@ -315,3 +315,39 @@ def test_small_kernels():
     cs = torch.zeros(64, device=DEV)
     ops.rows_gather(src, dst, 36, 64, in_map=(12, 20, 0), colsum=cs)
     assert torch.equal(dst.view(3, 12, 64), src.view(3, 20, 64)[:, :12]) and rel(cs, dst.float().sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize("kind,ln,repr_size", [("mean", True, None), ("max", True, 48), ("mean", False, 40)])
+def test_lm_head_matches_reference_modules(kind, ln, repr_size):
+    """PoolPredictor (lm_layers.py:30-81) through the fp32 LM-head kernels vs the same math in stock torch:
+    logits and every gradient (tokens, LayerNorm, optional GELU+Linear, noun / verb Linears)."""
+    from transfusion_b200.cross_fusion.lm_layers import PoolPredictor
+    torch.manual_seed(21)
+    B, L, D, nn_, nv = 5, 11, 96, 13, 7
+    args = {"type": kind, "ln": ln}
+    if repr_size:
+        args["repr_size"] = repr_size
+    head = PoolPredictor(args, D, nn_, nv).to(DEV)
+    tok = torch.randn(B, L, D, device=DEV, requires_grad=True)
+    mask = torch.ones(B, L, dtype=torch.bool, device=DEV)
+    mask[1, 6:] = False
+    mask[3, 1:] = False
+    out = head(tok, mask)
+    (out["noun_logits"].pow(2).sum() + out["verb_logits"].sum()).backward()
+    got = {k: p.grad.clone() for k, p in head.named_parameters()}
+    gtok = tok.grad.clone()
+    # stock torch restatement of lm_layers.py:59-81 on the same parameters
+    head.zero_grad(set_to_none=True)
+    tok2 = tok.detach().clone().requires_grad_(True)
+    x = tok2 * mask.unsqueeze(2)
+    f = x.max(dim=1)[0] if kind == "max" else x.mean(dim=1)
+    if head.ln:
+        f = head.ln(f)
+    if head.repr_mlp:
+        f = head.repr_mlp(f)
+    noun, verb = head.mlp_noun(f), head.mlp_verb(f)
+    (noun.pow(2).sum() + verb.sum()).backward()
+    assert rel(out["noun_logits"], noun) < 1e-5 and rel(out["verb_logits"], verb) < 1e-5
+    assert rel(gtok, tok2.grad) < 1e-5
+    for k, p in head.named_parameters():
+        assert rel(got[k], p.grad) < 1e-5, k

@@ -298,3 +298,79 @@ def rows_gather(src: torch.Tensor, dst: torch.Tensor, rows: int, D: int, in_map=
       check(lib().xf_rows_gather(_ptr(src), C.c_int64(src.stride(-2)), _ptr(dst), C.c_int64(dst.stride(-2)), rows, D,
                                in_map[0], in_map[1], in_map[2], _ptr(colsum), C.c_float(drop_p), C.c_uint32(drop_seed),
                                C.c_uint32(drop_stream), _stream()), "xf_rows_gather")
+
+
+# ---- LM head (fp32) ------------------------------------------------------------------------------
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    _req(t, torch.float32, name)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def lm_pool_fwd(tok: torch.Tensor, mask: Optional[torch.Tensor], kind: str):
+    """tok fp32 [B, L, D]; mask uint8 [B, L] (1 = valid) or None -> (pooled [B, D], argmax int32 [B, D] | None)."""
+    tok = _f32c(tok, "tok")
+    B, L, D = tok.shape
+    t = {"mean": 0, "max": 1}[kind]
+    pooled = torch.empty(B, D, device=tok.device, dtype=torch.float32)
+    argmax = torch.empty(B, D, device=tok.device, dtype=torch.int32) if t == 1 else None
+    with _Prof("lm_head", 0.0, 4.0 * B * L * D):
+        check(lib().xf_lm_pool_fwd(_ptr(tok), _ptr(mask), B, L, D, t, _ptr(pooled), _ptr(argmax), _stream()), "xf_lm_pool_fwd")
+    return pooled, argmax
+
+
+def lm_pool_bwd(dpooled: torch.Tensor, mask: Optional[torch.Tensor], argmax: Optional[torch.Tensor], L: int, kind: str):
+    dpooled = _f32c(dpooled, "dpooled")
+    B, D = dpooled.shape
+    t = {"mean": 0, "max": 1}[kind]
+    dtok = torch.empty(B, L, D, device=dpooled.device, dtype=torch.float32)
+    with _Prof("lm_head", 0.0, 4.0 * B * L * D):
+        check(lib().xf_lm_pool_bwd(_ptr(dpooled), _ptr(mask), _ptr(argmax), B, L, D, t, _ptr(dtok), _stream()), "xf_lm_pool_bwd")
+    return dtok
+
+
+def rowln_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float):
+    x = _f32c(x, "x")
+    R, D = x.shape
+    y = torch.empty_like(x)
+    mean = torch.empty(R, device=x.device, dtype=torch.float32)
+    rstd = torch.empty(R, device=x.device, dtype=torch.float32)
+    with _Prof("lm_head", 0.0, 8.0 * R * D):
+        check(lib().xf_rowln_fwd(_ptr(x), _ptr(_f32c(gamma, "gamma")), _ptr(_f32c(beta, "beta")), R, D, C.c_float(eps), _ptr(y),
+                                 _ptr(mean), _ptr(rstd), _stream()), "xf_rowln_fwd")
+    return y, mean, rstd
+
+
+def rowln_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor):
+    dy, x = _f32c(dy, "dy"), _f32c(x, "x")
+    R, D = x.shape
+    dx = torch.empty_like(x)
+    dgamma = torch.zeros(D, device=x.device, dtype=torch.float32)
+    dbeta = torch.zeros(D, device=x.device, dtype=torch.float32)
+    with _Prof("lm_head", 0.0, 12.0 * R * D):
+        check(lib().xf_rowln_bwd(_ptr(dy), _ptr(x), _ptr(_f32c(gamma, "gamma")), _ptr(mean), _ptr(rstd), R, D, _ptr(dx), _ptr(dgamma),
+                                 _ptr(dbeta), _stream()), "xf_rowln_bwd")
+    return dx, dgamma, dbeta
+
+
+def small_linear_fwd(x: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], act: int):
+    x, W = _f32c(x, "x"), _f32c(W, "W")
+    R, D = x.shape
+    Cn = W.shape[0]
+    y = torch.empty(R, Cn, device=x.device, dtype=torch.float32)
+    with _Prof("lm_head", 2.0 * R * Cn * D):
+        check(lib().xf_small_linear_fwd(_ptr(x), _ptr(W), _ptr(None if bias is None else _f32c(bias, "bias")), R, Cn, D, act, _ptr(y),
+                                        _stream()), "xf_small_linear_fwd")
+    return y
+
+
+def small_linear_bwd(dy: torch.Tensor, x: torch.Tensor, W: torch.Tensor, act: int, need_dx=True, need_dw=True, has_bias=True):
+    dy, x, W = _f32c(dy, "dy"), _f32c(x, "x"), _f32c(W, "W")
+    R, D = x.shape
+    Cn = W.shape[0]
+    dx = torch.empty_like(x) if need_dx else None
+    dW = torch.zeros_like(W) if need_dw else None
+    db = torch.zeros(Cn, device=x.device, dtype=torch.float32) if (need_dw and has_bias) else None
+    with _Prof("lm_head", 4.0 * R * Cn * D):
+        check(lib().xf_small_linear_bwd(_ptr(dy), _ptr(x), _ptr(W), R, Cn, D, act, _ptr(dx), _ptr(dW), _ptr(db), _stream()),
+              "xf_small_linear_bwd")
+    return dx, dW, db
