@@ -215,7 +215,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int m, int n
 // They exist because the epilogue, not the tensor pipe, paced the K = 896 GEMMs: ~40 instructions per element in
 // the generic path.  Here: packed fp32 math (fma/add/mul .f32x2), bias and dropout column hashes staged once per
 // tile in shared memory and re-read as 128-bit broadcasts, residual / pre-activation operands requested before
-// the accumulator load is waited for, no per-element bounds checks (host guarantees N % 32 == 0 and 16-byte
+// the accumulator load is waited for, no per-element bounds checks (host guarantees N % 8 == 0 and 16-byte
 // alignment), and one kernel instantiation per kind so each fits the instruction cache.
 enum { EPI_GENERIC = 0, EPI_LINEAR = 1, EPI_GELU = 2, EPI_DGELU = 3, EPI_RED = 4 };
 
@@ -286,7 +286,8 @@ __device__ __forceinline__ void epilogue_fast(const GemmParams& p, const CUtenso
     if (m0 + lane < p.M) {
 #pragma unroll
       for (int i = 0; i < 32; i += 4)   // 128-bit vector reductions: 8 L2 transactions per chunk instead of 32
-        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + i), "r"(acc[i]), "r"(acc[i + 1]), "r"(acc[i + 2]), "r"(acc[i + 3]) : "memory");
+        if (n0 + i < p.N)               // N % 4 == 0: a vector is entirely inside or outside
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + i), "r"(acc[i]), "r"(acc[i + 1]), "r"(acc[i + 2]), "r"(acc[i + 3]) : "memory");
     }
   } else {
     float2 v[16];
@@ -700,7 +701,8 @@ extern "C" int xf_gemm(const XfGemm* g, xf_stream_t stream_) {
   if (rc) return rc;
 
   // epilogue kind: the specialised epilogues need full, 16-byte aligned 32-column chunks and no row remap
-  const bool plain = !g->pos_table && g->rows_in == 0 && p.vec_ok && p.N % 32 == 0 && p.tile_n <= 256;
+  // (a last chunk that sticks out of N is clipped by the TMA boxes; bias / hash staging stops at N)
+  const bool plain = !g->pos_table && g->rows_in == 0 && p.vec_ok && p.N % 8 == 0 && p.tile_n <= 256;
   const bool drop_pre_act = g->drop_p > 0.f && g->drop_first;   // only matters when an activation follows the mask
   int epi = EPI_GENERIC;
   if (plain && p.out_f32) {
