@@ -49,7 +49,9 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms.  The process is started BEFORE the warm-up steps
+    (its NVML initialisation takes locks in the driver and stalled kernel launches when it overlapped the ~0.3 s timed
+    region); only the samples that arrive between mark() and stop() -- the timed region -- are reported."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -59,11 +61,12 @@ class ClockSampler:
         self.lines = []
         self.proc = None
         self.thread = None
+        self.t_mark = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.gpu_index)],
+                                          "-lms", "50", "-i", str(self.gpu_index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -73,7 +76,12 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            if self.t_mark is not None:
+                self.lines.append(line.strip())
+
+    def mark(self):
+        """Start of the timed region: samples from here on count."""
+        self.t_mark = time.monotonic()
 
     def stop(self):
         if self.proc is None:
@@ -304,11 +312,13 @@ def run_ours(args):
             ms = float(t.item())
         return ms
 
-    for _ in range(max(3, args.warmup)):
-        step_resident()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    torch.cuda.synchronize()
+    sampler.mark()
     launches0 = _lib.lib().xf_launch_count()
     ms = timed(step_resident, args.steps)
     launches = _lib.lib().xf_launch_count() - launches0

@@ -174,6 +174,13 @@ class CrossFusionBoxWrapper(nn.Module):
         side = self._level_streams(language_f) if (LEVEL_STREAMS and len(level_order) > 1 and not self.forward_language_f
                                                    and not self.multi_lm) else None
         cur = torch.cuda.current_stream() if side is not None else None
+        if side is not None:
+            # Host run-ahead limiter: with several streams an unthrottled host fills one stream's launch queue while
+            # the others starve (observed: 29 -> 51 ms per step, at random).  The host may be at most two forward
+            # calls ahead of the device.
+            pending = self.__dict__.setdefault("_xf_fwd_events", [])
+            if len(pending) >= 2:
+                pending.pop(0).synchronize()
         for i, key in level_order:
             key = str(key)
             feat = features_dict["features"][key]
@@ -207,6 +214,9 @@ class CrossFusionBoxWrapper(nn.Module):
         if side is not None:
             for st in side:
                 cur.wait_stream(st)
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            self.__dict__["_xf_fwd_events"].append(ev)
         features_dict = self.rcnn_model.apply_fpn(features_dict)
         if "hand_boxes" in x:
             features_dict["hand_boxes"] = x["hand_boxes"]

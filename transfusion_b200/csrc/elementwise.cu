@@ -712,33 +712,36 @@ layernorm_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
       }
     }
     __syncthreads();
-    // ---------------- phase 2: thread = 4 columns, all rows of the block from shared memory
+    // ---------------- phase 2: thread = 4 columns, all rows of the block from shared memory (full blocks take the
+    // branch-free unrolled path)
     const int nr = min(LNT_ROWS, p.rows - r0);
+    auto col_row = [&](int j, uint32_t ax, uint32_t ad, uint32_t ao, int u) {
+      const uint2 qx = lds64(ax), qd = lds64(ad);
+      const float2 xv[2] = {make_float2(bf16_lo(qx.x), bf16_hi(qx.x)), make_float2(bf16_lo(qx.y), bf16_hi(qx.y))};
+      const float2 dv[2] = {make_float2(bf16_lo(qd.x), bf16_hi(qd.x)), make_float2(bf16_lo(qd.y), bf16_hi(qd.y))};
+      const float rs = lds32f(s_rstd + 4 * u), nm = lds32f(s_nmr + 4 * u);
+      const float2 r2 = make_float2(rs, rs), n2 = make_float2(nm, nm);
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        cg[j][kk] = __ffma2_rn(dv[kk], __ffma2_rn(xv[kk], r2, n2), cg[j][kk]);   // dy * xhat
+        cb[j][kk] = __fadd2_rn(cb[j][kk], dv[kk]);
+      }
+      if (p.dbias) {
+        const uint2 qo = lds64(ao);
+        cbias[j][0] = __fadd2_rn(cbias[j][0], make_float2(bf16_lo(qo.x), bf16_hi(qo.x)));
+        cbias[j][1] = __fadd2_rn(cbias[j][1], make_float2(bf16_lo(qo.y), bf16_hi(qo.y)));
+      }
+    };
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
       const int col = threadIdx.x * 4 + 1024 * j;
       if (col < p.D) {
-        uint32_t ax = sx + coff[j], ad = sdy + coff[j], ao = s_dx2 + col * 2;
+        const uint32_t ax = sx + coff[j], ad = sdy + coff[j], ao = s_dx2 + col * 2;
+        if (nr == LNT_ROWS) {
 #pragma unroll
-        for (int u = 0; u < LNT_ROWS; ++u) {
-          if (u < nr) {
-            const uint2 qx = lds64(ax), qd = lds64(ad);
-            const float2 xv[2] = {make_float2(bf16_lo(qx.x), bf16_hi(qx.x)), make_float2(bf16_lo(qx.y), bf16_hi(qx.y))};
-            const float2 dv[2] = {make_float2(bf16_lo(qd.x), bf16_hi(qd.x)), make_float2(bf16_lo(qd.y), bf16_hi(qd.y))};
-            const float rs = lds32f(s_rstd + 4 * u), nm = lds32f(s_nmr + 4 * u);
-            const float2 r2 = make_float2(rs, rs), n2 = make_float2(nm, nm);
-#pragma unroll
-            for (int kk = 0; kk < 2; ++kk) {
-              cg[j][kk] = __ffma2_rn(dv[kk], __ffma2_rn(xv[kk], r2, n2), cg[j][kk]);   // dy * xhat
-              cb[j][kk] = __fadd2_rn(cb[j][kk], dv[kk]);
-            }
-            if (p.dbias) {
-              const uint2 qo = lds64(ao);
-              cbias[j][0] = __fadd2_rn(cbias[j][0], make_float2(bf16_lo(qo.x), bf16_hi(qo.x)));
-              cbias[j][1] = __fadd2_rn(cbias[j][1], make_float2(bf16_lo(qo.y), bf16_hi(qo.y)));
-            }
-          }
-          ax += bc2; ad += bc2; ao += row_bytes;
+          for (int u = 0; u < LNT_ROWS; ++u) col_row(j, ax + u * bc2, ad + u * bc2, ao + u * row_bytes, u);
+        } else {
+          for (int u = 0; u < nr; ++u) col_row(j, ax + u * bc2, ad + u * bc2, ao + u * row_bytes, u);
         }
       }
     }
