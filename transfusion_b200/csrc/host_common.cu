@@ -81,8 +81,10 @@ int sm_count() {
 // from the host on first use (synchronous copy: the first call must not happen inside a stream capture).
 const uint32_t* drop_col_table() {
   static const uint32_t* tabs[64] = {nullptr};
+  static std::mutex mu;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
   if (!tabs[dev]) {
     static uint32_t host_tab[XF_DROP_TABLE_COLS];
     for (uint32_t c = 0; c < XF_DROP_TABLE_COLS; ++c) host_tab[c] = drop_colodd(c);
