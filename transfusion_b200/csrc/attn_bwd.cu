@@ -16,7 +16,8 @@
 //     MEMORY with tcgen05.cp (dp/2 columns); C1 is a ".ts" MMA (A from TMEM), so R1 costs no shared memory
 //     and no shared-memory bandwidth while streaming;
 //   * the second resident operand R2 (dO or V) stays in shared memory (SWIZZLE_64B, 32-column chunks);
-//   * streamed 64-row tiles T1/T2 arrive by TMA: the tile that is also the B operand of the accumulate MMA
+//   * streamed 64-row tiles T1/T2 arrive by TMA, one 4-D box instruction per tile (all 32-column chunks; issuing
+//     seven 4 KB boxes per tile paced the producer): the tile that is also the B operand of the accumulate MMA
 //     (read a second time MN-major) lives in a 3-stage ring, the tile that only feeds a score MMA in a
 //     2-stage ring;
 //   * the element-wise stage reads C1/C2 from TMEM (tcgen05.ld), and writes E as packed bf16 straight back to
@@ -141,17 +142,17 @@ attn_bwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gr
           // the long-ring slot of tile i-3), so its load is requested first
           mbar_wait(S_EMPTY(ss), spar);
           mbar_expect_tx(S_FULL(ss), t_bytes);
-          for (int c = 0; c < p.nch; ++c) tma_load_3d(sa + c * 4096, &tmap_t2, S_FULL(ss), col0 + 32 * c, i * NB_BN, b);
+          tma_load_4d(sa, &tmap_t2, S_FULL(ss), 0, i * NB_BN, hd * p.nch, b);   // all nch chunks in one instruction
           mbar_wait(L_EMPTY(ls), lpar);
           mbar_expect_tx(L_FULL(ls), t_bytes);
-          for (int c = 0; c < p.nch; ++c) tma_load_3d(la + c * 4096, &tmap_t1, L_FULL(ls), col0 + 32 * c, i * NB_BN, b);
+          tma_load_4d(la, &tmap_t1, L_FULL(ls), 0, i * NB_BN, hd * p.nch, b);
         } else {                 // T1 -> short ring (score only), T2 -> long ring (accumulate only)
           mbar_wait(S_EMPTY(ss), spar);
           mbar_expect_tx(S_FULL(ss), t_bytes);
-          for (int c = 0; c < p.nch; ++c) tma_load_3d(sa + c * 4096, &tmap_t1, S_FULL(ss), col0 + 32 * c, i * NB_BN, b);
+          tma_load_4d(sa, &tmap_t1, S_FULL(ss), 0, i * NB_BN, hd * p.nch, b);
           mbar_wait(L_EMPTY(ls), lpar);
           mbar_expect_tx(L_FULL(ls), t_bytes);
-          for (int c = 0; c < p.nch; ++c) tma_load_3d(la + c * 4096, &tmap_t2, L_FULL(ls), col0 + 32 * c, i * NB_BN, b);
+          tma_load_4d(la, &tmap_t2, L_FULL(ls), 0, i * NB_BN, hd * p.nch, b);
         }
       }
     }
@@ -420,10 +421,10 @@ extern "C" int xf_attn_bwd(const XfAttnBwd* a, xf_stream_t stream_) {
   if ((rc = make_tmap_3d_bf16(&k_stage, a->k, a->B, a->Sk, cols, a->ldk, 64, NB_BM, 128))) return rc;
   if ((rc = make_tmap_3d_bf16(&do_res, a->d_out, a->B, a->Sq, cols, a->lddo, 32, NB_BM, 64))) return rc;
   if ((rc = make_tmap_3d_bf16(&v_res, a->v, a->B, a->Sk, cols, a->ldv, 32, NB_BM, 64))) return rc;
-  if ((rc = make_tmap_3d_bf16(&k64, a->k, a->B, a->Sk, cols, a->ldk, 32, NB_BN, 64))) return rc;
-  if ((rc = make_tmap_3d_bf16(&v64, a->v, a->B, a->Sk, cols, a->ldv, 32, NB_BN, 64))) return rc;
-  if ((rc = make_tmap_3d_bf16(&q64, a->q, a->B, a->Sq, cols, a->ldq, 32, NB_BN, 64))) return rc;
-  if ((rc = make_tmap_3d_bf16(&do64, a->d_out, a->B, a->Sq, cols, a->lddo, 32, NB_BN, 64))) return rc;
+  if ((rc = make_tmap_chunks_bf16(&k64, a->k, a->B, a->Sk, cols, a->ldk, NB_BN, p.nch))) return rc;
+  if ((rc = make_tmap_chunks_bf16(&v64, a->v, a->B, a->Sk, cols, a->ldv, NB_BN, p.nch))) return rc;
+  if ((rc = make_tmap_chunks_bf16(&q64, a->q, a->B, a->Sq, cols, a->ldq, NB_BN, p.nch))) return rc;
+  if ((rc = make_tmap_chunks_bf16(&do64, a->d_out, a->B, a->Sq, cols, a->lddo, NB_BN, p.nch))) return rc;
 
   const int ring = (NB_LONG + NB_SHORT) * p.nch * 4096;
   const int smem2 = 1024 + 4096 + p.nch * 8192 + ring;   // align slack + control/stats + R2 + rings

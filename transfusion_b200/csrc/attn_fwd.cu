@@ -17,7 +17,8 @@
 // S is double-buffered in TMEM so QK^T of tile j+1 overlaps the softmax of tile j.
 // Both A operands live in TENSOR MEMORY (".ts" MMAs): Q is staged once through shared memory (SWIZZLE_128B,
 // aliasing the rings) and copied with tcgen05.cp (dp/2 columns); P never touches shared memory.
-// K / V tiles: SWIZZLE_64B, 32-column chunks of [64 rows x 64 B] (no padding of a 224-wide head to 256);
+// K / V tiles: SWIZZLE_64B, 32-column chunks of [64 rows x 64 B] (no padding of a 224-wide head to 256), all chunks of
+// a tile moved by ONE 4-D TMA instruction (seven 4 KB box instructions per tile paced the producer);
 // K is the K-major B operand of S, V the MN-major B operand of PV.
 // The softmax stage is written for instruction count (it paces the kernel together with the 16/clk exp2
 // unit): packed fp32 math (fma/add .f32x2), product-form dropout hash with the tile's key hashes re-read as
@@ -124,12 +125,10 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         const int ks = j % AF_KST, vs = j % AF_VST;
         mbar_wait(K_EMPTY(ks), ((j / AF_KST) & 1) ^ 1);
         mbar_expect_tx(K_FULL(ks), t_bytes);
-        for (int c = 0; c < p.nch; ++c)
-          tma_load_3d(smem_u32(sK + ks * t_bytes + c * 4096), &tmap_k, K_FULL(ks), col0 + 32 * c, j * AF_BN, b);
+        tma_load_4d(smem_u32(sK + ks * t_bytes), &tmap_k, K_FULL(ks), 0, j * AF_BN, hd * p.nch, b);   // all chunks, one instruction
         mbar_wait(V_EMPTY(vs), ((j / AF_VST) & 1) ^ 1);
         mbar_expect_tx(V_FULL(vs), t_bytes);
-        for (int c = 0; c < p.nch; ++c)
-          tma_load_3d(smem_u32(sV + vs * t_bytes + c * 4096), &tmap_v, V_FULL(vs), col0 + 32 * c, j * AF_BN, b);
+        tma_load_4d(smem_u32(sV + vs * t_bytes), &tmap_v, V_FULL(vs), 0, j * AF_BN, hd * p.nch, b);
       }
     }
   } else if (warp == AF_SM_WARPS + 1) {
@@ -382,8 +381,8 @@ extern "C" int xf_attn_fwd(const XfAttnFwd* a, xf_stream_t stream_) {
   int rc;
   const uint64_t cols = static_cast<uint64_t>(a->H) * a->dp;
   if ((rc = make_tmap_3d_bf16(&tq, a->q, a->B, a->Sq, cols, a->ldq, 64, AF_BM, 128))) return rc;
-  if ((rc = make_tmap_3d_bf16(&tk, a->k, a->B, a->Sk, cols, a->ldk, 32, AF_BN, 64))) return rc;
-  if ((rc = make_tmap_3d_bf16(&tv, a->v, a->B, a->Sk, cols, a->ldv, 32, AF_BN, 64))) return rc;
+  if ((rc = make_tmap_chunks_bf16(&tk, a->k, a->B, a->Sk, cols, a->ldk, AF_BN, p.nch))) return rc;
+  if ((rc = make_tmap_chunks_bf16(&tv, a->v, a->B, a->Sk, cols, a->ldv, AF_BN, p.nch))) return rc;
 
   const int ring = (AF_KST + AF_VST) * p.nch * 4096;
   const int stage = ((a->dp + 63) / 64) * 16384;   // Q staging aliases the rings

@@ -65,6 +65,24 @@ int make_tmap_3d_bf16(CUtensorMap* out, const void* ptr, uint64_t batch, uint64_
   return 0;
 }
 
+int make_tmap_chunks_bf16(CUtensorMap* out, const void* ptr, uint64_t batch, uint64_t rows, uint64_t cols, uint64_t ld,
+                          uint32_t box_rows, uint32_t box_chunks) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return fail(-10, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return fail(-11, "TMA base pointer not 16-byte aligned");
+  if ((ld * 2) % 16 != 0) return fail(-12, "TMA row pitch %llu B not a multiple of 16", (unsigned long long)(ld * 2));
+  if (cols % 32 != 0 || box_rows > 256 || box_chunks > 256 || box_chunks == 0) return fail(-13, "bad chunked TMA box");
+  cuuint64_t gdim[4] = {32, rows, cols / 32, batch};
+  cuuint64_t gstr[3] = {ld * 2, 64, rows * ld * 2};
+  cuuint32_t box[4] = {32, box_rows, box_chunks, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(-14, "cuTensorMapEncodeTiled(4d chunks) failed: %d", (int)r);
+  return 0;
+}
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {

@@ -48,6 +48,12 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t
 int make_tmap_3d_bf16(CUtensorMap* out, const void* ptr, uint64_t batch, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint32_t box_cols, uint32_t box_rows, int swizzle_bytes = 128);
 
+// 4-D view of the same [batch, rows, cols] bf16 tensor as (32-column chunk, row, chunk index, batch): one TMA
+// instruction moves `box_chunks` SWIZZLE_64B chunks of [box_rows x 64 B], laid out chunk-major in shared memory
+// (the layout the attention kernels' 32-column-chunk descriptors expect).  cols % 32 == 0.
+int make_tmap_chunks_bf16(CUtensorMap* out, const void* ptr, uint64_t batch, uint64_t rows, uint64_t cols, uint64_t ld,
+                          uint32_t box_rows, uint32_t box_chunks);
+
 int sm_count();
 
 // device table of drop_colodd(0 .. XF_DROP_TABLE_COLS-1) for the current device (nullptr on failure)
