@@ -83,6 +83,24 @@ int make_tmap_chunks_bf16(CUtensorMap* out, const void* ptr, uint64_t batch, uin
   return 0;
 }
 
+int make_tmap_rowblock_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t bc,
+                            uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return fail(-10, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return fail(-11, "TMA base pointer not 16-byte aligned");
+  if ((ld * 2) % 16 != 0) return fail(-12, "TMA row pitch %llu B not a multiple of 16", (unsigned long long)(ld * 2));
+  if (bc == 0 || bc > 256 || bc % 8 || cols % bc || cols / bc > 256 || box_rows > 256) return fail(-13, "bad row-block TMA box");
+  cuuint64_t gdim[3] = {bc, rows, cols / bc};
+  cuuint64_t gstr[2] = {ld * 2, static_cast<cuuint64_t>(bc) * 2};
+  cuuint32_t box[3] = {bc, box_rows, static_cast<cuuint32_t>(cols / bc)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(-14, "cuTensorMapEncodeTiled(row block) failed: %d", (int)r);
+  return 0;
+}
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {

@@ -48,6 +48,11 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t
 int make_tmap_3d_bf16(CUtensorMap* out, const void* ptr, uint64_t batch, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint32_t box_cols, uint32_t box_rows, int swizzle_bytes = 128);
 
+// 3-D view of a [rows, cols] bf16 matrix as (bc-column chunk, row, chunk index), no swizzle: one TMA instruction moves
+// a [box_rows x cols] row block into shared memory laid out [chunk][box_rows][bc].  cols % bc == 0, bc <= 256.
+int make_tmap_rowblock_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t bc,
+                            uint32_t box_rows);
+
 // 4-D view of the same [batch, rows, cols] bf16 tensor as (32-column chunk, row, chunk index, batch): one TMA
 // instruction moves `box_chunks` SWIZZLE_64B chunks of [box_rows x 64 B], laid out chunk-major in shared memory
 // (the layout the attention kernels' 32-column-chunk descriptors expect).  cols % 32 == 0.
