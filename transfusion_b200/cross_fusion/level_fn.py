@@ -254,8 +254,25 @@ class FusionLevelFunction(torch.autograd.Function):
         def empty(*shape, dtype=bf):
             return torch.empty(*shape, device=dev, dtype=dtype)
 
+        # fp32 gradient buffers (accumulated into by split-K wgrads, column sums and LayerNorm backward) are carved
+        # from one zero-filled arena per level: one memset launch instead of ~57 tiny fills.  autograd adopts the
+        # views as .grad without copying.
+        arena = {"buf": None, "off": 0}
+        arena_cap = sum(int(q.numel()) for q in params if q is not None and q.requires_grad) + 8 * len(params) * 64 + (1 << 16)
+
         def zeros(*shape, dtype=f32):
-            return torch.zeros(*shape, device=dev, dtype=dtype)
+            if dtype != f32:
+                return torch.zeros(*shape, device=dev, dtype=dtype)
+            numel = 1
+            for s_ in shape:
+                numel *= int(s_)
+            need = (numel + 63) // 64 * 64   # 256-byte aligned slices
+            if arena["buf"] is None or arena["off"] + need > arena["buf"].numel():
+                arena["buf"] = torch.zeros(max(need, arena_cap if arena["buf"] is None else 1 << 24), device=dev, dtype=f32)
+                arena["off"] = 0
+            out = arena["buf"][arena["off"]:arena["off"] + numel].view(*shape)
+            arena["off"] += need
+            return out
 
         grads: List[Optional[torch.Tensor]] = [None] * len(params)
 
