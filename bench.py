@@ -313,7 +313,7 @@ def run_ours(args):
         return ms
 
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("XF_NO_CLOCK_SAMPLER"):
         sampler.start()
     for _ in range(max(3, args.warmup)):
         step_resident()

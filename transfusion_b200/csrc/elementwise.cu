@@ -916,6 +916,33 @@ attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __re
   }
 }
 
+// 128-bit variant: one warp per token row, one head at a time (dp / 8 <= 32 vectors per head), 32-bit index math.
+// The scalar kernel above spends most of its instructions on 64-bit div / mod per (row, head).
+__global__ void __launch_bounds__(256)
+attn_delta_vec_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o, long long ld, int B, int S,
+                      int heads, int dp, int stat_stride, float* __restrict__ delta) {
+  const int warps_per_cta = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rows = B * S, vph = dp >> 3;
+  for (int r = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); r < rows; r += gridDim.x * warps_per_cta) {
+    const int b = r / S, sidx = r - b * S;
+    const uint4* po = reinterpret_cast<const uint4*>(o + static_cast<long long>(r) * ld);
+    const uint4* pd = reinterpret_cast<const uint4*>(d_o + static_cast<long long>(r) * ld);
+    for (int h = 0; h < heads; ++h) {
+      float2 acc = make_float2(0.f, 0.f);
+      if (lane < vph) {
+        const uint4 a = __ldg(po + h * vph + lane), c = __ldg(pd + h * vph + lane);
+        acc = __ffma2_rn(make_float2(bf16_lo(a.x), bf16_hi(a.x)), make_float2(bf16_lo(c.x), bf16_hi(c.x)), acc);
+        acc = __ffma2_rn(make_float2(bf16_lo(a.y), bf16_hi(a.y)), make_float2(bf16_lo(c.y), bf16_hi(c.y)), acc);
+        acc = __ffma2_rn(make_float2(bf16_lo(a.z), bf16_hi(a.z)), make_float2(bf16_lo(c.z), bf16_hi(c.z)), acc);
+        acc = __ffma2_rn(make_float2(bf16_lo(a.w), bf16_hi(a.w)), make_float2(bf16_lo(c.w), bf16_hi(c.w)), acc);
+      }
+      const float sum = warp_sum(acc.x + acc.y);
+      if (lane == 0) delta[(static_cast<long long>(b) * heads + h) * stat_stride + sidx] = sum;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // rows gather: out[r, :] = in[remap(r), :] (optionally dropout-masked with the mask of the forward
 // write at that source position) and colsum += sum_r out[r, :].  Used for the visual rows of dz0
@@ -930,15 +957,27 @@ rows_gather_kernel(const __nv_bfloat16* __restrict__ in, long long ldi, __nv_bfl
   const int r0 = blockIdx.y * rows_per_cta;
   const int r1 = min(rows, r0 + rows_per_cta);
   float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int r = r0; r < r1; ++r) {
-    const long long ir = remap_row(r, rin, rout, roff);
-    const uint4 q = __ldg(reinterpret_cast<const uint4*>(in + ir * ldi) + vc);
-    float v[8] = {bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y), bf16_lo(q.z), bf16_hi(q.z), bf16_lo(q.w), bf16_hi(q.w)};
-    if (drop_p > 0.f) drop8(v, drop_rowhash(seed, static_cast<uint64_t>(ir)), vc * 8, thresh, drop_scale, coltab);
+  for (int rb = r0; rb < r1; rb += 4) {   // four independent 128-bit loads in flight per thread
+    uint4 q[4];
+    long long ir[4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) s[k] += v[k];
-    *(reinterpret_cast<uint4*>(out + static_cast<long long>(r) * ldo) + vc) =
-        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    for (int u = 0; u < 4; ++u) {
+      ir[u] = remap_row(min(rb + u, r1 - 1), rin, rout, roff);
+      q[u] = __ldg(reinterpret_cast<const uint4*>(in + ir[u] * ldi) + vc);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = rb + u;
+      if (r < r1) {
+        float v[8] = {bf16_lo(q[u].x), bf16_hi(q[u].x), bf16_lo(q[u].y), bf16_hi(q[u].y),
+                      bf16_lo(q[u].z), bf16_hi(q[u].z), bf16_lo(q[u].w), bf16_hi(q[u].w)};
+        if (drop_p > 0.f) drop8(v, drop_rowhash(seed, static_cast<uint64_t>(ir[u])), vc * 8, thresh, drop_scale, coltab);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s[k] += v[k];
+        *(reinterpret_cast<uint4*>(out + static_cast<long long>(r) * ldo) + vc) =
+            make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+      }
+    }
   }
   if (colsum) {
 #pragma unroll
@@ -1200,8 +1239,14 @@ extern "C" int xf_attn_delta(const void* o, const void* d_o, int64_t ld, int B, 
   if (dp % 2) return fail(-2, "xf_attn_delta: dp must be even");
   if (stat_stride < S) return fail(-3, "xf_attn_delta: stat_stride < S");
   if (B * S == 0) return 0;
-  attn_delta_kernel<<<grid_for(static_cast<long long>(B) * S * heads, 8), 256, 0, reinterpret_cast<cudaStream_t>(s)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(o), reinterpret_cast<const __nv_bfloat16*>(d_o), ld, B, S, heads, dp, stat_stride, delta);
+  const bool vec = dp % 8 == 0 && dp <= 256 && ld % 8 == 0 && ((reinterpret_cast<uintptr_t>(o) | reinterpret_cast<uintptr_t>(d_o)) & 15) == 0 &&
+                   static_cast<long long>(B) * S < (1ll << 31);
+  if (vec)
+    attn_delta_vec_kernel<<<grid_for(static_cast<long long>(B) * S, 8), 256, 0, reinterpret_cast<cudaStream_t>(s)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(o), reinterpret_cast<const __nv_bfloat16*>(d_o), ld, B, S, heads, dp, stat_stride, delta);
+  else
+    attn_delta_kernel<<<grid_for(static_cast<long long>(B) * S * heads, 8), 256, 0, reinterpret_cast<cudaStream_t>(s)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(o), reinterpret_cast<const __nv_bfloat16*>(d_o), ld, B, S, heads, dp, stat_stride, delta);
   g_launches.fetch_add(1);
   XF_CUDA(cudaGetLastError());
   return 0;
