@@ -300,12 +300,25 @@ def run_ours(args):
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        per_step = [] if os.environ.get("XF_STEP_TIMES") else None
+        n_alloc0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
         e0.record()
         for _ in range(steps):
             fn()
+            if per_step is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                per_step.append(ev)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
+        if per_step is not None and rank == 0:
+            prev, out = e0, []
+            for ev in per_step:
+                out.append(round(prev.elapsed_time(ev), 2))
+                prev = ev
+            print(f"[step times ms] {out}  cudaMalloc calls in region: "
+                  f"{torch.cuda.memory_stats(dev).get('num_device_alloc', 0) - n_alloc0}", file=sys.stderr)
         if world > 1:
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -175,11 +175,15 @@ class CrossFusionBoxWrapper(nn.Module):
                                                    and not self.multi_lm) else None
         cur = torch.cuda.current_stream() if side is not None else None
         if side is not None:
-            # Host run-ahead limiter: with several streams an unthrottled host fills one stream's launch queue while
-            # the others starve (observed: 29 -> 51 ms per step, at random).  The host may be at most two forward
-            # calls ahead of the device.
+            # Host run-ahead limiter.  Tensors that cross streams (the fused maps) return to the caching allocator
+            # only when the consuming stream has passed the point of the free, so how many blocks the allocator needs
+            # depends on how far the host runs ahead of the device; an unthrottled host kept provoking cudaMalloc
+            # calls in steady state, and cudaMalloc synchronises the device (observed: single steps of 60-120 ms).
+            # Training: wait for the previous forward to have finished on the device (its backward is still queued,
+            # so the device never idles); inference: stay at most two forwards ahead.
             pending = self.__dict__.setdefault("_xf_fwd_events", [])
-            if len(pending) >= 2:
+            depth = 1 if (self.training and torch.is_grad_enabled()) else 2
+            while len(pending) >= depth:
                 pending.pop(0).synchronize()
         for i, key in level_order:
             key = str(key)

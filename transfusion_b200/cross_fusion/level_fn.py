@@ -276,6 +276,13 @@ class FusionLevelFunction(torch.autograd.Function):
 
         grads: List[Optional[torch.Tensor]] = [None] * len(params)
 
+        # the incoming gradients may have been produced on another stream (the caller's): tell the caching allocator
+        # that this stream reads them (the autograd engine has already ordered the streams)
+        if d_fused.is_cuda:
+            cur_stream = torch.cuda.current_stream()
+            d_fused.record_stream(cur_stream)
+            if isinstance(d_lang_out, torch.Tensor) and d_lang_out.is_cuda:
+                d_lang_out.record_stream(cur_stream)
         # ---- fold^T, back-projection
         d_fused_c = d_fused.contiguous()
         if d_fused_c.dtype not in (torch.float32, torch.bfloat16):
