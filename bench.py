@@ -300,24 +300,25 @@ def run_ours(args):
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        per_step = [] if os.environ.get("XF_STEP_TIMES") else None
+        per_step, host_t = [], [time.perf_counter()]
         n_alloc0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
         e0.record()
         for _ in range(steps):
             fn()
-            if per_step is not None:
-                ev = torch.cuda.Event(enable_timing=True)
-                ev.record()
-                per_step.append(ev)
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            per_step.append(ev)
+            host_t.append(time.perf_counter())
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
-        if per_step is not None and rank == 0:
+        if rank == 0:   # diagnostics: per-step device times and cudaMalloc calls inside the timed region (stderr)
             prev, out = e0, []
             for ev in per_step:
                 out.append(round(prev.elapsed_time(ev), 2))
                 prev = ev
-            print(f"[step times ms] {out}  cudaMalloc calls in region: "
+            host_ms = [round(1e3 * (b - a), 1) for a, b in zip(host_t[:-1], host_t[1:])]
+            print(f"[step times ms] {out}  host enqueue ms {host_ms}  cudaMalloc calls in region: "
                   f"{torch.cuda.memory_stats(dev).get('num_device_alloc', 0) - n_alloc0}", file=sys.stderr)
         if world > 1:
             t = torch.tensor([ms], device=dev)
