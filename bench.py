@@ -19,6 +19,7 @@ peak; `cpu_baseline` = the CPU oracle port timed on this box's host cores on a b
 from __future__ import annotations
 
 import argparse
+import faulthandler
 import json
 import os
 import statistics
@@ -298,6 +299,18 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def timed(fn, steps):
+        # watchdog: if a timed phase does not finish, dump every thread's Python stack and exit non-zero instead of
+        # hanging the box (XF_WATCHDOG_S seconds, default 120; 0 disables)
+        wd = int(os.environ.get("XF_WATCHDOG_S", "120"))
+        if wd > 0:
+            faulthandler.dump_traceback_later(wd, exit=True)
+        try:
+            return _timed(fn, steps)
+        finally:
+            if wd > 0:
+                faulthandler.cancel_dump_traceback_later()
+
+    def _timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         per_step, host_t = [], [time.perf_counter()]

@@ -115,7 +115,7 @@ class CrossFusionBoxWrapper(nn.Module):
                          stride=(patch_h, patch_w), bias=False)
 
     # ---- the hot path -----------------------------------------------------------------------
-    def run_level(self, i: int, feat: torch.Tensor, language_f: torch.Tensor, lang_pad_mask, need_lang_out=False):
+    def run_level(self, i: int, feat: torch.Tensor, language_f: torch.Tensor, lang_pad_mask, need_lang_out=False, out_stream=None):
         """One FPN level: reference :180-212.  Returns (fused [B,C,h,w], fused language tokens or None)."""
         enc: CrossTransformerModuleBox = self.cross_fusion_encoders[i]
         t2f: RegroupPatchesLayerBox = self.tokens_to_features[i]
@@ -132,7 +132,8 @@ class CrossFusionBoxWrapper(nn.Module):
             seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
         cfg = LevelConfig(level=i, patch=p, num_heads=enc.num_heads, num_layers=enc.num_layers, training=self.training,
                           patch_dropout=float(enc.patch_dropout), token_dropout=float(enc.token_dropout),
-                          backproj_dropout=float(t2f.back_dropout.p), seed=seed, need_lang_out=need_lang_out)
+                          backproj_dropout=float(t2f.back_dropout.p), seed=seed, need_lang_out=need_lang_out,
+                          out_stream=out_stream)
         params = [pe.weight, enc.image_kind_embedding, enc.lang_kind_embedding, enc.pos_embedding_layer.table(),
                   *enc.level_params(), enc.final_norm_layer.weight, enc.final_norm_layer.bias, t2f.linear.weight,
                   t2f.linear.bias]
@@ -174,6 +175,7 @@ class CrossFusionBoxWrapper(nn.Module):
         side = self._level_streams(language_f) if (LEVEL_STREAMS and len(level_order) > 1 and not self.forward_language_f
                                                    and not self.multi_lm) else None
         cur = torch.cuda.current_stream() if side is not None else None
+        keep_alive = []
         if side is not None:
             # Host run-ahead limiter.  Tensors that cross streams (the fused maps) return to the caching allocator
             # only when the consuming stream has passed the point of the free, so how many blocks the allocator needs
@@ -194,15 +196,12 @@ class CrossFusionBoxWrapper(nn.Module):
                 st = side[i % len(side)]
                 st.wait_stream(cur)
                 with torch.cuda.stream(st):
-                    fused, fused_l_features = self.run_level(i, feat, language_f, lang_pad, need_lang_out)
-                # inputs were allocated on the caller's stream and are read on `st`; the output is allocated on `st`
-                # and consumed on the caller's stream
-                for t in (feat, language_f, lang_pad):
-                    if isinstance(t, torch.Tensor) and t.is_cuda:
-                        t.record_stream(st)
-                fused.record_stream(cur)
-                if isinstance(fused_l_features, torch.Tensor):
-                    fused_l_features.record_stream(cur)
+                    fused, fused_l_features = self.run_level(i, feat, language_f, lang_pad, need_lang_out, out_stream=cur)
+                # Memory safety across streams without record_stream (whose deferred frees made the allocator's
+                # demand depend on host run-ahead): the outputs come from the caller stream's pool (out_stream) and
+                # are written on `st`, which waited for everything the caller had enqueued; the inputs, allocated on
+                # the caller's stream and read on `st`, are kept alive until the caller's stream has joined `st`.
+                keep_alive.append((feat, language_f, lang_pad))
             else:
                 fused, fused_l_features = self.run_level(i, feat, language_f, lang_pad, need_lang_out)
             if self.multi_lm:
@@ -221,6 +220,7 @@ class CrossFusionBoxWrapper(nn.Module):
             ev = torch.cuda.Event()
             ev.record(cur)
             self.__dict__["_xf_fwd_events"].append(ev)
+            keep_alive.clear()   # the join is enqueued: later frees are ordered after the side streams' reads
         features_dict = self.rcnn_model.apply_fpn(features_dict)
         if "hand_boxes" in x:
             features_dict["hand_boxes"] = x["hand_boxes"]

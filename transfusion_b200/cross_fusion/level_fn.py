@@ -41,6 +41,10 @@ class LevelConfig:
     backproj_dropout: float
     seed: int = 0
     need_lang_out: bool = False
+    # stream that consumes the level's outputs when the level itself runs on a side stream: the outputs are then
+    # allocated from THAT stream's pool (no record_stream, so no deferred frees that make the allocator's needs
+    # depend on how far the host runs ahead)
+    out_stream: object = None
 
     def stream(self, layer: int, site: int) -> int:
         return ((self.level * 16 + layer) * 64 + site) & 0xFFFFFFFF
@@ -213,9 +217,16 @@ class FusionLevelFunction(torch.autograd.Function):
         yb = empty(B * n, K)
         ops.gemm(vis, wbp_b, yb, M=B * n, N=K, K=D, bias=bbp)
         _dbg("vis", vis); _dbg("yb", yb)
-        fused = torch.empty(B, C, Hf, Wf, device=dev, dtype=feat_c.dtype)
+        if cfg.out_stream is not None:
+            with torch.cuda.stream(cfg.out_stream):
+                fused = torch.empty(B, C, Hf, Wf, device=dev, dtype=feat_c.dtype)
+                lang_out = torch.empty(B, L, D, device=dev, dtype=torch.float32) if cfg.need_lang_out else lang.new_zeros(())
+        else:
+            fused = torch.empty(B, C, Hf, Wf, device=dev, dtype=feat_c.dtype)
+            lang_out = torch.empty(B, L, D, device=dev, dtype=torch.float32) if cfg.need_lang_out else lang.new_zeros(())
         ops.fold(yb, fused, p)
-        lang_out = x.view(B, S, D)[:, n:].float() if cfg.need_lang_out else lang.new_zeros(())
+        if cfg.need_lang_out:
+            lang_out.copy_(x.view(B, S, D)[:, n:])
 
         if need_grad:
             ctx.cfg = cfg
