@@ -17,7 +17,8 @@ def _worker(rank, world, port, q):
     w1 = torch.nn.Parameter(torch.randn(5, 3))
     w2 = torch.nn.Parameter(torch.randn(3))
     frozen = torch.nn.Parameter(torch.randn(2), requires_grad=False)
-    red = BucketedGradAllReduce([[w1, frozen], [w2]])
+    unused = torch.nn.Parameter(torch.randn(4))   # requires grad but takes no part in the graph (the reference's
+    red = BucketedGradAllReduce([[w1, frozen, unused], [w2]])   # heatmap_token): must not switch the exchange off
     x_all = torch.arange(8 * 5, dtype=torch.float32).reshape(8, 5) / 10.0
     lo, hi = shard_range(8, rank, world)
     for it in range(2):  # two steps: buffers are reused
@@ -32,6 +33,7 @@ def _worker(rank, world, port, q):
     tot = sum(((x_all[slice(*shard_range(8, r, world))] @ w1r + w2r) ** 2).sum() for r in range(world)) / world
     tot.backward()
     ok = torch.allclose(w1.grad, w1r.grad, rtol=1e-5, atol=1e-5) and torch.allclose(w2.grad, w2r.grad, rtol=1e-5, atol=1e-5)
+    ok = ok and unused.grad is None
     q.put((rank, bool(ok), (lo, hi)))
     dist.destroy_process_group()
 

@@ -383,7 +383,8 @@ class FusionLevelFunction(torch.autograd.Function):
         # ---- sequence assembly backward: language rows and visual rows
         dz0 = dcur.view(B, S, D)
         g_lang_kind = zeros(D)
-        d_lang = zeros(B, L, D) if ctx.needs[1] else None
+        # not from the arena: the arena holds parameter gradients only (a data-parallel reducer sums it in place)
+        d_lang = torch.zeros(B, L, D, device=dev, dtype=f32) if ctx.needs[1] else None
         ops.lang_rows_bwd(dz0, d_lang, g_lang_kind, B, L, n)
         dz0v = empty(B * n, D)
         g_img_kind = zeros(D)
@@ -406,4 +407,11 @@ class FusionLevelFunction(torch.autograd.Function):
                 out_grads.append(None)
             else:
                 out_grads.append(g.view_as(prm) if g.shape != prm.shape else g)
+        # every parameter gradient of the level lives in the arena: a data-parallel reducer can all-reduce that one
+        # buffer in place (parallel.BucketedGradAllReduce) instead of flattening ~70 tensors
+        if arena["buf"] is not None:
+            used = arena["buf"][:arena["off"]]
+            for prm in params:
+                if prm is not None and prm.requires_grad:
+                    prm._xf_grad_arena = used
         return (None, d_feat, d_lang, None, *out_grads)

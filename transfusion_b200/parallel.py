@@ -52,18 +52,45 @@ class BucketedGradAllReduce:
                 self._launch(bi)
         return hook
 
+    @staticmethod
+    def _arena_of(bucket):
+        """The level's gradient arena (cross_fusion/level_fn.py) if EVERY gradient of the bucket is a view into it
+        (true when autograd adopted the freshly produced gradients, i.e. after zero_grad(set_to_none=True))."""
+        arena = getattr(bucket[0], "_xf_grad_arena", None)
+        if arena is None or not arena.is_cuda:
+            return None
+        lo, hi = arena.data_ptr(), arena.data_ptr() + arena.numel() * arena.element_size()
+        for p in bucket:
+            g = p.grad
+            if g is None:
+                continue   # took no part in this backward: nothing to reduce (every rank runs the same graph)
+            if g.dtype != arena.dtype or not (lo <= g.data_ptr() and g.data_ptr() + g.numel() * g.element_size() <= hi):
+                return None
+        return arena
+
     def _launch(self, bi):
         bucket = self.buckets[bi]
+        arena = self._arena_of(bucket)
+        if arena is not None:   # one in-place all-reduce of the level's arena: no flatten / scatter copies
+            if self.world > 1:
+                self.works.append((bi, dist.all_reduce(arena, op=dist.ReduceOp.SUM, group=self.group, async_op=True), arena))
+            else:
+                self.works.append((bi, None, arena))
+            return
         offs, total = self._offsets(bi)
-        if self.flat[bi] is None or self.flat[bi].device != bucket[0].grad.device:
-            self.flat[bi] = torch.empty(total, dtype=torch.float32, device=bucket[0].grad.device)
+        dev = next((p.grad.device for p in bucket if p.grad is not None), bucket[0].device)
+        if self.flat[bi] is None or self.flat[bi].device != dev:
+            self.flat[bi] = torch.empty(total, dtype=torch.float32, device=dev)
         flat = self.flat[bi]
         for p, (o, n) in zip(bucket, offs):
-            flat[o:o + n].copy_(p.grad.reshape(-1))
+            if p.grad is None:          # unused on this rank (e.g. the reference's heatmap_token): contributes zeros
+                flat[o:o + n].zero_()
+            else:
+                flat[o:o + n].copy_(p.grad.reshape(-1))
         if self.world > 1:
-            self.works.append((bi, dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)))
+            self.works.append((bi, dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True), None))
         else:
-            self.works.append((bi, None))
+            self.works.append((bi, None, None))
 
     def reset(self):
         """Call before each backward."""
@@ -71,16 +98,27 @@ class BucketedGradAllReduce:
         self.works = []
 
     def finish(self):
-        """Wait for the outstanding all-reduces and scatter the (averaged) result back into .grad."""
-        for bi, work in self.works:
+        """Wait for the outstanding all-reduces and scatter the (averaged) result back into .grad.  Buckets whose
+        hooks did not all fire (a parameter that took no part in this backward) are reduced here, so an unused
+        parameter cannot silently switch the exchange off."""
+        launched = {w[0] for w in self.works}
+        for bi, bucket in enumerate(self.buckets):
+            if bi not in launched and any(p.grad is not None for p in bucket):
+                self._launch(bi)
+        for bi, work, arena in self.works:
             if work is not None:
                 work.wait()
+            if arena is not None:
+                if self.average and self.world > 1:
+                    arena.div_(self.world)
+                continue
             flat = self.flat[bi]
             if self.average and self.world > 1:
                 flat.div_(self.world)
             offs, _ = self._offsets(bi)
             for p, (o, n) in zip(self.buckets[bi], offs):
-                p.grad = flat[o:o + n].view_as(p)
+                if p.grad is not None:
+                    p.grad = flat[o:o + n].view_as(p)
         self.works = []
 
     def remove(self):
