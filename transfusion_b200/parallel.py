@@ -71,11 +71,16 @@ class BucketedGradAllReduce:
     def _launch(self, bi):
         bucket = self.buckets[bi]
         arena = self._arena_of(bucket)
+        if arena is not None:
+            self._arena_buckets.add(bi)
         if arena is not None:   # one in-place all-reduce of the level's arena: no flatten / scatter copies
             if self.world > 1:
-                self.works.append((bi, dist.all_reduce(arena, op=dist.ReduceOp.SUM, group=self.group, async_op=True), arena))
+                # NCCL averages inside the collective; other backends sum and finish() divides
+                avg = self.average and dist.get_backend(self.group) == "nccl"
+                op = dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM
+                self.works.append((bi, dist.all_reduce(arena, op=op, group=self.group, async_op=True), None if avg else arena))
             else:
-                self.works.append((bi, None, arena))
+                self.works.append((bi, None, None))
             return
         offs, total = self._offsets(bi)
         dev = next((p.grad.device for p in bucket if p.grad is not None), bucket[0].device)
@@ -96,6 +101,7 @@ class BucketedGradAllReduce:
         """Call before each backward."""
         self.pending = [len(b) for b in self.buckets]
         self.works = []
+        self._arena_buckets = set()
 
     def finish(self):
         """Wait for the outstanding all-reduces and scatter the (averaged) result back into .grad.  Buckets whose
@@ -112,6 +118,8 @@ class BucketedGradAllReduce:
                 if self.average and self.world > 1:
                     arena.div_(self.world)
                 continue
+            if bi in self._arena_buckets:
+                continue   # reduced (and averaged) in place
             flat = self.flat[bi]
             if self.average and self.world > 1:
                 flat.div_(self.world)
