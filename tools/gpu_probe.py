@@ -66,7 +66,7 @@ def attn_ref(q, k, v, H, d, kpm):
 def attn_case(B, H, Sq, Sk, d, mask=False, fused=True, seed=0):
     torch.manual_seed(seed)
     dev = "cuda"
-    dp = (d + 15) // 16 * 16
+    dp = (d + 31) // 32 * 32
     D = H * d
     if fused and Sq == Sk:
         qkv = torch.zeros(B * Sq, 3 * H * dp, device=dev, dtype=torch.bfloat16)
