@@ -85,6 +85,18 @@ def test_cpu_tensors_fail_loudly_no_fallback():
         m({"image": None, "language_f": (torch.randn(1, 4, 64), torch.ones(1, 4, dtype=torch.int64))})
 
 
+def test_lm_head_fails_loudly_on_cpu_and_keeps_reference_parameter_names():
+    """PoolPredictor (lm_layers.py:30-81): same submodule / parameter names as the reference, no CPU path."""
+    from transfusion_b200._lib import XfError
+    from transfusion_b200.cross_fusion.lm_layers import PoolPredictor
+    head = PoolPredictor({"type": "mean", "ln": True, "repr_size": 16}, 32, 5, 3)
+    assert sorted(k for k, _ in head.named_parameters()) == sorted([
+        "ln.weight", "ln.bias", "repr_mlp.1.weight", "repr_mlp.1.bias", "mlp_noun.weight", "mlp_noun.bias",
+        "mlp_verb.weight", "mlp_verb.bias"])
+    with pytest.raises(XfError):
+        head(torch.randn(2, 4, 32), torch.ones(2, 4, dtype=torch.bool))
+
+
 def test_workload_shapes_match_survey_appendix_b():
     v2, v1 = WORKLOADS["ego4dv2"], WORKLOADS["ego4dv1"]
     n2 = [(h // p) * (w // p) for (h, w), p in zip(level_shapes(v2), v2["patch"])]
