@@ -49,6 +49,11 @@ int64_t xf_launch_count(void);
  *   -> [drop_first: dropout] -> act / dact -> [!drop_first: dropout] -> (+ residual[m_out, n])
  *   -> store / atomic-add to out[m_out, n],  m_out = (m / rows_in) * rows_out + m % rows_in + row_off
  *   (rows_in = 0: m_out = m).
+ * The common combinations (bf16 out with [bias] [dropout] [residual]; bias + saved pre-activation + GELU
+ * [+ dropout]; GELU' [+ dropout mask]; fp32 accumulate for wgrad) run specialised kernels that need
+ * N % 8 == 0 and 16-byte aligned operands; everything else takes a generic element-wise epilogue.
+ * Dropout: keep(m_out, n) = rowhash(seed, stream, m_out) * colhash(n) >= p * 2^32 (csrc/ptx.cuh) -- the same
+ * (seed, stream) reproduces the mask in any kernel of the library (GEMM, LayerNorm, row gather).
  * ------------------------------------------------------------------------------------------ */
 typedef struct XfGemm {
   const void* a; int64_t a_ld;
@@ -184,7 +189,7 @@ int xf_attn_delta(const void* o_bf16, const void* do_bf16, int64_t ld, int B, in
  * :789-798 (_scaled_dot_product_attention) and :607 (head merge); general Sq != Sk, so the
  * QKVEncoder cross-attention (cross_qkv_layers.py:70-77) is the same call.
  * q/k/v/out: bf16, token-major [B*S, ld], head hd in columns [hd*dp, hd*dp+dp) (dp = head dim
- * padded to a multiple of 16; pad columns must be zero).  For a fused in-proj output
+ * padded to a multiple of 32, <= 256; pad columns must be zero).  For a fused in-proj output
  * [B*S, 3*H*dp] pass k = q + H*dp, v = q + 2*H*dp with ldq = ldk = ldv = 3*H*dp.
  * ------------------------------------------------------------------------------------------ */
 typedef struct XfAttnFwd {
@@ -204,8 +209,9 @@ typedef struct XfAttnFwd {
 int xf_attn_fwd(const XfAttnFwd* a, xf_stream_t stream);
 
 /* Attention backward (recomputes the probabilities from q, k and the saved LSE): dq, dk, dv in the
- * same token-major layout as q, k, v (pad columns come out zero).  Two tcgen05 passes: a
- * query-stationary dQ pass and a key-stationary dK/dV pass.  dp must be a multiple of 32, <= 224. */
+ * same token-major layout as q, k, v (pad columns come out zero).  Three tcgen05 passes with one TMEM
+ * accumulator each: a query-stationary dQ pass and key-stationary dK and dV passes.  dp must be a multiple
+ * of 32, <= 224; stat_stride a multiple of 64 >= Sq rounded up to 64. */
 typedef struct XfAttnBwd {
   const void* q; int64_t ldq;
   const void* k; int64_t ldk;
