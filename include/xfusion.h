@@ -236,6 +236,20 @@ int xf_attn_bwd(const XfAttnBwd* a, xf_stream_t stream);
 int xf_rows_gather(const void* in_bf16, int64_t ldi, void* out_bf16, int64_t ldo, int rows, int D, int rin, int rout, int roff,
                    float* colsum, float drop_p, uint32_t drop_seed, uint32_t drop_stream, xf_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Test aids (not on the hot path): materialise the counter-based dropout keep masks that the kernels above
+ * recompute on the fly, so a CPU checker can replay a train-mode step with the SAME masks (the reference draws
+ * its masks from torch's RNG inside F.dropout: cross_f_box_layers.py:74, torch18_adapters.py:109-112,796-797,
+ * utils.py:115).  out is uint8, 1 = keep.
+ *   xf_debug_dropout_mask     : GEMM-epilogue / LayerNorm / row-gather sites; out[r, c] for rows row0 .. row0+rows-1
+ *                               (row = the OUTPUT row index m_out of the site), columns 0 .. cols-1.
+ *   xf_debug_attn_dropout_mask: attention probabilities; out[bh, q, k], bh = b * H + head.
+ * ------------------------------------------------------------------------------------------ */
+int xf_debug_dropout_mask(float p, uint32_t seed, uint32_t stream_id, int64_t row0, int rows, int cols, uint8_t* out,
+                          xf_stream_t stream);
+int xf_debug_attn_dropout_mask(float p, uint32_t seed, uint32_t stream_id, int BH, int Sq, int Sk, uint8_t* out,
+                               xf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

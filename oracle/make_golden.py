@@ -32,6 +32,17 @@ CASES = {
     # head_dim not a multiple of 8 (like Ego4Dv1's 178): D=40, 4 heads -> d=10
     "c4_d40_oddhead": dict(D=40, heads=4, image=(64, 64), channels=[24], patch=[2], strides=[16],
                            layers=[2], B=2, L=6, lens=[3, 6], lm=False, seed=37),
+    # LM head fed by the LAST level's fused language tokens (lm_args.use_lm_f: False, cross_f_box_wrapper.py:224-227)
+    "lmfused2_d32": dict(D=32, heads=4, image=(64, 64), channels=[16, 24], patch=[2, 1], strides=[16, 32],
+                         layers=[2, 1], B=2, L=6, lens=[6, 4], lm=True, use_lm_f=False, seed=41),
+    # fused language tokens chained into the next level (forward_language_f, :203-209), LM head on the chained tokens
+    "fwdlang_sum_d32": dict(D=32, heads=4, image=(64, 64), channels=[16, 24], patch=[2, 1], strides=[16, 32],
+                            layers=[1, 2], B=2, L=5, lens=[2, 5], lm=True, fwd_lang="sum", seed=43),
+    "fwdlang_direct_d32": dict(D=32, heads=4, image=(64, 64), channels=[16, 24], patch=[2, 1], strides=[16, 32],
+                               layers=[1, 1], B=2, L=5, lens=[5, 3], lm=True, use_lm_f=False, fwd_lang="direct", seed=47),
+    # train-mode dropout (yml probabilities 0.1 / 0.15 / 0.1) with the keep masks recorded from the reference run
+    "dropout2_d32": dict(D=32, heads=4, image=(64, 64), channels=[16, 24], patch=[2, 1], strides=[16, 32],
+                         layers=[2, 2], B=2, L=6, lens=[6, 3], lm=False, dropout=True, seed=53),
 }
 
 
@@ -55,13 +66,22 @@ def run_case(name, case):
     H, W = case["image"]
     shapes = [(H // s, W // s) for s in strides]
     cfg = ref_loader.build_fusion_cfg(case["D"], n_levels=len(shapes), num_layers=case["layers"],
-                                      num_heads=case["heads"], patch=case["patch"], dropout=0.0)
+                                      num_heads=case["heads"], patch=case["patch"],
+                                      dropout=1.0 if case.get("dropout") else 0.0,
+                                      use_lm_f=case.get("use_lm_f"), forward_language_f=case.get("fwd_lang"))
     m = ref_loader.build_reference_module(cfg, shapes, case["channels"], lm=case["lm"], seed=case["seed"],
                                           noun_classes=9, verb_classes=6)
     m.train()
     feats_in = {k: v.clone().requires_grad_(True) for k, v in feats.items()}
     lang_in = lang.clone().requires_grad_(True)
-    out, lm = ref_loader.run_reference(m, feats_in, lang_in, mask)
+    # forward_language_f == "sum" adds in place (:206): hand the module a non-leaf alias of the leaf
+    lang_arg = lang_in * 1.0 if case.get("fwd_lang") else lang_in
+    rec = None
+    if case.get("dropout"):
+        with ref_loader.recorded_dropout(case["seed"] + 2000) as rec:
+            out, lm = ref_loader.run_reference(m, feats_in, lang_arg, mask)
+    else:
+        out, lm = ref_loader.run_reference(m, feats_in, lang_arg, mask)
     loss = sum((out[k] * cot[k]).sum() for k in out)
     if lm is not None:
         loss = loss + lm["noun_logits"].sum() * 0.5 + (lm["verb_logits"] ** 2).sum() * 0.25
@@ -89,6 +109,14 @@ def run_case(name, case):
     blob["meta.layers"] = np.array(case["layers"])
     blob["meta.heads"] = np.array(case["heads"])
     blob["meta.lm"] = np.array(int(case["lm"]))
+    blob["meta.use_lm_f"] = np.array(int(case.get("use_lm_f", True)))
+    blob["meta.fwd_lang"] = np.array(case.get("fwd_lang") or "")
+    if rec is not None:
+        blob["meta.drop"] = np.array([cfg["args"]["patch_dropout"], cfg["args"]["token_dropout"], cfg["backproj_dropout"]])
+        for lvl, d in ref_loader.masks_by_site(rec.masks, len(shapes), case["layers"]).items():
+            for site, mk in d.items():
+                blob[f"mask.{lvl}.{site}"] = np.packbits(mk.numpy().astype(np.uint8).reshape(-1))
+                blob[f"maskshape.{lvl}.{site}"] = np.array(mk.shape)
     blob["meta.torch_version"] = np.array(torch.__version__)
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     path = os.path.join(GOLDEN_DIR, name + ".npz")
@@ -97,9 +125,12 @@ def run_case(name, case):
 
 
 def main():
+    import sys
     torch.set_num_threads(max(1, os.cpu_count() or 1))
+    only = set(sys.argv[1:])
     for name, case in CASES.items():
-        run_case(name, case)
+        if not only or name in only:
+            run_case(name, case)
 
 
 if __name__ == "__main__":

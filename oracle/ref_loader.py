@@ -110,9 +110,10 @@ class PassThroughPooling(nn.Module):
 
 
 def build_fusion_cfg(token_dim, n_levels=4, num_layers=None, num_heads=4, patch=None,
-                     dropout=0.0, base_cfg=None) -> dict:
+                     dropout=0.0, base_cfg=None, use_lm_f=None, forward_language_f=None) -> dict:
     """Fusion config as ``run_experiment.update_config`` would hand it over
-    (run_experiment.py:75-77,100), with dropout probabilities overridable."""
+    (run_experiment.py:75-77,100), with dropout probabilities overridable (0.0 = all off, anything else =
+    the yml's values) and the two language-routing switches (lm_args.use_lm_f, forward_language_f)."""
     cfg = copy.deepcopy(base_cfg) if base_cfg is not None else load_fusion_yaml()
     patch = list(patch) if patch is not None else cfg["patch_h"][:n_levels]
     cfg["patch_h"] = list(patch)
@@ -125,6 +126,10 @@ def build_fusion_cfg(token_dim, n_levels=4, num_layers=None, num_heads=4, patch=
     cfg["args"]["patch_dropout"] = dropout if dropout == 0.0 else cfg["args"]["patch_dropout"]
     cfg["args"]["token_dropout"] = dropout if dropout == 0.0 else cfg["args"]["token_dropout"]
     cfg["backproj_dropout"] = dropout if dropout == 0.0 else cfg["backproj_dropout"]
+    if use_lm_f is not None:
+        cfg["lm_args"]["use_lm_f"] = bool(use_lm_f)
+    if forward_language_f is not None:
+        cfg["forward_language_f"] = forward_language_f
     return cfg
 
 
@@ -145,3 +150,62 @@ def run_reference(m, features: dict, lang: torch.Tensor, att_mask: torch.Tensor)
     m.rcnn_model.features = features
     out = m({"image": None, "language_f": (lang, att_mask)})
     return out["features"], out.get("lm")
+
+
+class recorded_dropout:
+    """Context manager that makes the UNMODIFIED reference's dropout deterministic and observable: every
+    ``F.dropout`` call (nn.Dropout modules, cross_f_box_layers.py:74, the attention-probability dropout) draws
+    its keep mask from a seeded CPU generator and appends it to ``self.masks`` in call order.  torch >= 2 routes
+    ``nn.MultiheadAttention`` through the fused ``scaled_dot_product_attention`` builtin whose dropout cannot be
+    observed, so that one function is replaced by its documented math (softmax(q k^T * scale + mask) -> dropout
+    -> @ v), which is the reference's own torch18_adapters.py:789-798."""
+
+    def __init__(self, seed: int):
+        self.gen = torch.Generator().manual_seed(seed)
+        self.masks = []
+
+    def _dropout(self, x, p=0.5, training=True, inplace=False):
+        if not training or p <= 0.0:
+            return x
+        keep = (torch.rand(x.shape, generator=self.gen) >= p)
+        self.masks.append(keep)
+        return x * keep.to(x.dtype) / (1.0 - p)
+
+    def _sdpa(self, q, k, v, attn_mask=None, dropout_p=0.0, is_causal=False, scale=None, **kw):
+        import math
+        assert not is_causal
+        s = (q * (scale if scale is not None else 1.0 / math.sqrt(q.shape[-1]))) @ k.transpose(-2, -1)
+        if attn_mask is not None:
+            s = s.masked_fill(attn_mask, float("-inf")) if attn_mask.dtype == torch.bool else s + attn_mask
+        a = torch.softmax(s, dim=-1)
+        a = self._dropout(a, dropout_p, True)
+        return a @ v
+
+    def __enter__(self):
+        import torch.nn.functional as F
+        self._saved = (F.dropout, F.scaled_dot_product_attention)
+        F.dropout = self._dropout
+        F.scaled_dot_product_attention = self._sdpa
+        return self
+
+    def __exit__(self, *exc):
+        import torch.nn.functional as F
+        F.dropout, F.scaled_dot_product_attention = self._saved
+        return False
+
+
+def masks_by_site(recorded, n_levels: int, num_layers, level_order=None):
+    """Maps the call-ordered mask list of ``recorded_dropout`` to oracle/ref_math.py's site names: per level
+    (reference order 0..n-1): patch, then per layer attn, drop1, ffn, drop2, then backproj."""
+    it = iter(recorded)
+    out = {}
+    for i in (level_order if level_order is not None else range(n_levels)):
+        d = {"patch": next(it)}
+        for l in range(num_layers[i]):
+            for site in ("attn", "drop1", "ffn", "drop2"):
+                d[f"l{l}.{site}"] = next(it)
+        d["backproj"] = next(it)
+        out[str(i)] = d
+    rest = list(it)
+    assert not rest, f"{len(rest)} unconsumed dropout masks"
+    return out

@@ -8,7 +8,12 @@ golden vectors ``tests/golden/*.npz`` (everywhere).
 
 The functions take a flat ``sd`` mapping with the reference's ``state_dict`` key names
  so the same weights drive the reference, the oracle and the
-CUDA module.  Deterministic path only: dropout probabilities are 0.
+CUDA module.  Dropout is deterministic: every dropout site takes an explicit keep mask
+(``masks`` dicts, 1 = keep) and applies ``x * mask / (1 - p)`` exactly like ``F.dropout``; without
+masks the probabilities are 0.  Site names per level: ``patch`` [B,n,D]
+(cross_f_box_layers.py:74), ``l{t}.attn`` [B,H,S,S] (torch18_adapters.py:796-797), ``l{t}.drop1``
+[B,S,D] (:109), ``l{t}.ffn`` [B,S,2D] (:111), ``l{t}.drop2`` [B,S,D] (:112), ``backproj`` [B,n,D]
+(utils.py:115).
 """
 from __future__ import annotations
 
@@ -59,7 +64,14 @@ def gelu_erf(x):
     return 0.5 * x * (1.0 + torch.erf(x / math.sqrt(2.0)))
 
 
-def attention(q, k, v, key_pad: Optional[torch.Tensor], num_heads: int):
+def _drop(x, mask, p: float):
+    """F.dropout with an explicit keep mask (1 = keep): x * mask / (1 - p)."""
+    if mask is None or p <= 0.0:
+        return x
+    return x * mask.to(x.dtype) / (1.0 - p)
+
+
+def attention(q, k, v, key_pad: Optional[torch.Tensor], num_heads: int, drop_mask=None, drop_p: float = 0.0):
     """torch18_adapters.py:544-555 (head split), :578-597 (key-padding -> -inf),
     :789-798 (_scaled_dot_product_attention), :607 (head merge).
     q:[B,Sq,D] k,v:[B,Sk,D]; key_pad:[B,Sk] bool, True = ignore.  General Sq != Sk."""
@@ -73,26 +85,32 @@ def attention(q, k, v, key_pad: Optional[torch.Tensor], num_heads: int):
     if key_pad is not None:
         s = s.masked_fill(key_pad[:, None, None, :], float("-inf"))
     a = torch.softmax(s, dim=-1)
+    a = _drop(a, drop_mask, drop_p)  # torch18_adapters.py:796-797 (dropout on the probabilities)
     o = a @ vh
     return o.transpose(1, 2).reshape(B, Sq, D)
 
 
-def encoder_layer(x, key_pad, sd, pre: str, num_heads: int):
-    """Post-LN encoder layer, torch18_adapters.py:108-113; in-proj :685; out-proj :608."""
+def encoder_layer(x, key_pad, sd, pre: str, num_heads: int, masks=None, tag: str = "", drop_p: float = 0.0):
+    """Post-LN encoder layer, torch18_adapters.py:108-113; in-proj :685; out-proj :608.
+    masks: optional dict with keep masks ``{tag}.attn / .drop1 / .ffn / .drop2`` (token_dropout sites)."""
     D = x.shape[-1]
+    mk = (lambda n: masks.get(f"{tag}.{n}")) if masks else (lambda n: None)
     qkv = x @ sd[pre + "self_attn.in_proj_weight"].t() + sd[pre + "self_attn.in_proj_bias"]
     q, k, v = qkv.split(D, dim=-1)
-    o = attention(q, k, v, key_pad, num_heads)
+    o = attention(q, k, v, key_pad, num_heads, mk("attn"), drop_p)
     o = o @ sd[pre + "self_attn.out_proj.weight"].t() + sd[pre + "self_attn.out_proj.bias"]
-    x = layer_norm(x + o, sd[pre + "norm1.weight"], sd[pre + "norm1.bias"])
+    x = layer_norm(x + _drop(o, mk("drop1"), drop_p), sd[pre + "norm1.weight"], sd[pre + "norm1.bias"])
     f = gelu_erf(x @ sd[pre + "linear1.weight"].t() + sd[pre + "linear1.bias"])
-    f = f @ sd[pre + "linear2.weight"].t() + sd[pre + "linear2.bias"]
-    return layer_norm(x + f, sd[pre + "norm2.weight"], sd[pre + "norm2.bias"])
+    f = _drop(f, mk("ffn"), drop_p) @ sd[pre + "linear2.weight"].t() + sd[pre + "linear2.bias"]
+    return layer_norm(x + _drop(f, mk("drop2"), drop_p), sd[pre + "norm2.weight"], sd[pre + "norm2.bias"])
 
 
-def fusion_level(feat, lang, lang_pad, sd, i: int, p: int, num_heads: int, num_layers: int):
+def fusion_level(feat, lang, lang_pad, sd, i: int, p: int, num_heads: int, num_layers: int, masks=None,
+                 drop=(0.0, 0.0, 0.0)):
     """One FPN level: cross_f_box_wrapper.py:177-212 + cross_f_box_layers.py:69-108.
-    Returns (fused feature map [B,C,h,w], language tokens out [B,L,D])."""
+    Returns (fused feature map [B,C,h,w], language tokens out [B,L,D]).
+    masks: optional keep masks of this level (module docstring); drop = (patch, token, backproj) probabilities."""
+    p_patch, p_tok, p_back = drop
     B, C, h, w = feat.shape
     gh, gw = h // p, w // p
     n = gh * gw
@@ -103,6 +121,7 @@ def fusion_level(feat, lang, lang_pad, sd, i: int, p: int, num_heads: int, num_l
     x = patchify(feat, p) @ wpe.t()
     # cross_f_box_layers.py:72-73 ; utils.py:209-214
     x = x + sin1d_table(n, D, x.dtype) + sd[enc + "image_kind_embedding"].reshape(D)
+    x = _drop(x, masks.get("patch") if masks else None, p_patch)  # cross_f_box_layers.py:74
     # cross_f_box_layers.py:76
     lg = lang + sd[enc + "lang_kind_embedding"].reshape(D)
     # cross_f_box_layers.py:80-86
@@ -111,11 +130,12 @@ def fusion_level(feat, lang, lang_pad, sd, i: int, p: int, num_heads: int, num_l
         key_pad = torch.cat([torch.zeros(B, n, dtype=torch.bool), lang_pad], dim=1)
     z = torch.cat([x, lg], dim=1)
     for l in range(num_layers):  # cross_f_box_layers.py:97
-        z = encoder_layer(z, key_pad, sd, enc + f"t_encoder.layers.{l}.", num_heads)
+        z = encoder_layer(z, key_pad, sd, enc + f"t_encoder.layers.{l}.", num_heads, masks, f"l{l}", p_tok)
     # cross_f_box_layers.py:104-108
     vis = layer_norm(z[:, :n], sd[enc + "final_norm_layer.weight"], sd[enc + "final_norm_layer.bias"])
     lang_out = z[:, n:]
     # utils.py:114-119
+    vis = _drop(vis, masks.get("backproj") if masks else None, p_back)  # utils.py:115
     y = vis @ sd[f"tokens_to_features.{i}.linear.weight"].t() + sd[f"tokens_to_features.{i}.linear.bias"]
     return fold(y, C, p, gh, gw), lang_out
 
@@ -132,16 +152,28 @@ def lm_head(lang, att_mask_bool, sd):
 
 def cross_fusion_forward(features: Dict[str, torch.Tensor], lang, att_mask, sd,
                          patch: Sequence[int], num_heads: int, num_layers: Sequence[int],
-                         lm: bool = False):
+                         lm: bool = False, use_lm_f: bool = True, forward_language_f=False,
+                         masks: Optional[Dict[str, Dict[str, torch.Tensor]]] = None, drop=(0.0, 0.0, 0.0)):
     """cross_f_box_wrapper.py:165-230 with identity FPN/RoI (fused maps exposed).
     att_mask: [B,L] int, 1 = valid (narr_pooling_layers.py:199-202); inverted at
-    cross_f_box_wrapper.py:196."""
+    cross_f_box_wrapper.py:196.  ``forward_language_f`` in (False, "direct", "sum") chains the fused
+    language tokens into the next level (:203-209); ``use_lm_f`` False feeds the LM head the LAST
+    level's fused tokens instead of the input language features (:224-227).
+    masks[level key][site] are optional dropout keep masks (module docstring)."""
     lang_pad = ~(att_mask.bool())
     out = {}
+    fused_l = None
     for i, key in enumerate(sorted(features.keys(), key=int)):
-        fused, _ = fusion_level(features[key], lang, lang_pad, sd, i, patch[i], num_heads, num_layers[i])
+        fused, fused_l = fusion_level(features[key], lang, lang_pad, sd, i, patch[i], num_heads, num_layers[i],
+                                      masks.get(key) if masks else None, drop)
+        if forward_language_f == "direct":
+            lang = fused_l
+        elif forward_language_f == "sum":
+            lang = lang + fused_l  # the reference adds in place (:206); same value
+        elif forward_language_f:
+            raise NotImplementedError(forward_language_f)
         out[key] = fused
-    lm_out = lm_head(lang, att_mask.bool(), sd) if lm else None  # use_lm_f: True (yml :91)
+    lm_out = lm_head(lang if use_lm_f else fused_l, att_mask.bool(), sd) if lm else None
     return out, lm_out
 
 

@@ -10,8 +10,9 @@ from transfusion_b200.cross_fusion import CrossFusionBoxWrapper
 
 
 def build_module(token_dim, shapes, channels, patch, layers, heads, lm=False, dropout=False, device="cuda",
-                 noun_classes=9, verb_classes=6, seed=0):
+                 noun_classes=9, verb_classes=6, seed=0, use_lm_f=True, forward_language_f=False):
     kw = {} if dropout else dict(patch_dropout=0.0, token_dropout=0.0, backproj_dropout=0.0)
+    kw.update(use_lm_f=use_lm_f, forward_language_f=forward_language_f)
     cfg = default_fusion_cfg(token_dim, n_levels=len(shapes), num_layers=layers, num_heads=heads, patch=patch, **kw)
     torch.manual_seed(seed)
     rcnn = FakeRCNN(shapes, channels, noun_classes, verb_classes)

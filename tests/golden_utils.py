@@ -6,7 +6,8 @@ import numpy as np
 import torch
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = ["fusion4_d32", "c5_d64_lm", "c4_d40_oddhead"]
+CASES = ["fusion4_d32", "c5_d64_lm", "c4_d40_oddhead", "lmfused2_d32", "fwdlang_sum_d32", "fwdlang_direct_d32"]
+DROPOUT_CASES = ["dropout2_d32"]   # reference run in train mode with recorded keep masks (oracle/ref_loader.recorded_dropout)
 
 
 def load_golden(name):
@@ -35,6 +36,17 @@ def load_golden(name):
     g["layers"] = [int(x) for x in z["meta.layers"]]
     g["heads"] = int(z["meta.heads"])
     g["lm_on"] = bool(int(z["meta.lm"]))
+    g["use_lm_f"] = bool(int(z["meta.use_lm_f"])) if "meta.use_lm_f" in z.files else True
+    g["fwd_lang"] = (str(z["meta.fwd_lang"]) or False) if "meta.fwd_lang" in z.files else False
+    g["drop"] = tuple(float(x) for x in z["meta.drop"]) if "meta.drop" in z.files else (0.0, 0.0, 0.0)
+    g["masks"] = {}
+    for k in z.files:
+        if k.startswith("mask."):
+            _, lvl, site = k.split(".", 2)
+            shape = tuple(int(x) for x in z["maskshape." + k[5:]])
+            n = int(np.prod(shape))
+            bits = np.unpackbits(z[k])[:n].reshape(shape)
+            g["masks"].setdefault(lvl, {})[site] = torch.from_numpy(bits.astype(np.bool_))
     return g
 
 

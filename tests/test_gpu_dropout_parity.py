@@ -1,0 +1,224 @@
+"""GPU: train-mode (dropout ON) parity of the whole module against the CPU oracle under the SAME keep masks
+(VERDICT r1 weak #2).  The library's dropout is counter-based -- keep(row, col) is a pure function of
+(seed, site id, row, col) that every forward and backward kernel recomputes -- so the masks of a step are
+materialised with the library's test aids (xf_debug_dropout_mask / xf_debug_attn_dropout_mask: the canonical
+definitions) from the per-level seeds of the step and fed to oracle/ref_math.py, whose masked-dropout semantics
+are pinned to the unmodified reference by tests/golden/dropout2_d32.npz.  A (seed, site, row-index) mismatch
+between any two kernels -- GEMM epilogue vs layernorm_bwd dx2_drop, patch-embed epilogue vs rows_gather, GELU vs
+GELU' epilogues, attention forward vs its three backward passes -- shows up here as a wrong output or gradient.
+Also: the direct cross-kernel pairings at op level and the independence statistics of the mask hash."""
+import math
+
+import pytest
+import torch
+
+from oracle import ref_math
+from tests.fusion_testlib import build_module, param_dict, run_module
+from tests.golden_utils import rel_fro
+from transfusion_b200 import ops
+from transfusion_b200.cross_fusion.level_fn import (SITE_ATTN, SITE_BACKPROJ, SITE_DROP1, SITE_DROP2, SITE_FFN, SITE_PATCH,
+                                                    LevelConfig)
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+REL_OUT, REL_GRAD = 1e-2, 1e-2
+
+
+def _level_masks(level, seed, B, n, L, D, F, H, layers, drop):
+    """Keep masks of one level of one step, in oracle/ref_math.py's site names."""
+    p_patch, p_tok, p_back = drop
+    S = n + L
+    cfg = LevelConfig(level=level, patch=1, num_heads=H, num_layers=layers, training=True, patch_dropout=p_patch,
+                      token_dropout=p_tok, backproj_dropout=p_back, seed=seed)
+    mk = {}
+    # patch dropout: GEMM epilogue rows are the OUTPUT rows b * S + t of the [B, S, D] sequence
+    mk["patch"] = ops.debug_dropout_mask(p_patch, seed, cfg.stream(0, SITE_PATCH), 0, B * S, D).view(B, S, D)[:, :n].bool().cpu()
+    for l in range(layers):
+        mk[f"l{l}.attn"] = ops.debug_attn_dropout_mask(p_tok, seed, cfg.stream(l, SITE_ATTN), B * H, S, S).view(B, H, S, S).bool().cpu()
+        mk[f"l{l}.drop1"] = ops.debug_dropout_mask(p_tok, seed, cfg.stream(l, SITE_DROP1), 0, B * S, D).view(B, S, D).bool().cpu()
+        mk[f"l{l}.ffn"] = ops.debug_dropout_mask(p_tok, seed, cfg.stream(l, SITE_FFN), 0, B * S, F).view(B, S, F).bool().cpu()
+        mk[f"l{l}.drop2"] = ops.debug_dropout_mask(p_tok, seed, cfg.stream(l, SITE_DROP2), 0, B * S, D).view(B, S, D).bool().cpu()
+    # back-projection dropout sits on the final LayerNorm's output rows b * n + t
+    mk["backproj"] = ops.debug_dropout_mask(p_back, seed, cfg.stream(0, SITE_BACKPROJ), 0, B * n, D).view(B, n, D).bool().cpu()
+    return mk
+
+
+@pytest.mark.parametrize("D,shapes,channels,patch,layers,B,L,lens", [
+    (256, [(20, 24)], [48], [1], [2], 2, 40, [40, 17]),                      # S = 520: several query / key tiles
+    (896, [(16, 24), (8, 12)], [64, 128], [2, 1], [2, 2], 2, 24, [24, 9]),   # head_dim 224, two levels (two seeds)
+    (712, [(16, 24)], [32], [4], [2], 2, 16, [5, 16]),                       # head_dim 178 -> 192 (padded head columns)
+])
+def test_train_mode_module_matches_oracle_under_the_same_masks(D, shapes, channels, patch, layers, B, L, lens):
+    H = 4
+    m = build_module(D, shapes, channels, patch, layers, H, dropout=True, seed=21)
+    m.train()
+    drop = (0.1, 0.15, 0.1)   # yml :5,7 and backproj_dropout :18
+    g = torch.Generator().manual_seed(22)
+    feats = {str(i): torch.relu(torch.randn(B, c, h, w, generator=g)) for i, ((h, w), c) in enumerate(zip(shapes, channels))}
+    lang = 0.5 * torch.randn(B, L, D, generator=g)
+    mask = torch.zeros(B, L, dtype=torch.int64)
+    for b, n_ in enumerate(lens):
+        mask[b, :n_] = 1
+    cot = {k: torch.randn(v.shape, generator=g) for k, v in feats.items()}
+
+    torch.manual_seed(777)   # the module draws one dropout seed per level from torch's CPU generator
+    f_gpu = {k: v.cuda().requires_grad_(True) for k, v in feats.items()}
+    l_gpu = lang.cuda().requires_grad_(True)
+    out, _ = run_module(m, f_gpu, l_gpu, mask.cuda())
+    sum((out[k].float() * cot[k].cuda()).sum() for k in out).backward()
+    torch.cuda.synchronize()
+    seeds = m._xf_last_seeds
+    assert len(set(seeds.values())) == len(shapes)
+
+    masks = {}
+    for i, ((h, w), p) in enumerate(zip(shapes, patch)):
+        n = (h // p) * (w // p)
+        masks[str(i)] = _level_masks(i, seeds[i], B, n, L, D, 2 * D, H, layers[i], drop)
+        rate = 1.0 - float(masks[str(i)]["l0.attn"].float().mean())
+        assert abs(rate - drop[1]) < 0.01
+
+    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in param_dict(m).items()}
+    f_cpu = {k: v.clone().requires_grad_(True) for k, v in feats.items()}
+    l_cpu = lang.clone().requires_grad_(True)
+    ref, _ = ref_math.cross_fusion_forward(f_cpu, l_cpu, mask, sd, patch, H, layers, masks=masks, drop=drop)
+    sum((ref[k] * cot[k]).sum() for k in ref).backward()
+
+    for k in out:
+        r = rel_fro(out[k].detach().float().cpu(), ref[k].detach())
+        assert r < REL_OUT, f"train-mode features.{k}: {r:.3e}"
+        r = rel_fro(f_gpu[k].grad.cpu(), f_cpu[k].grad)
+        assert r < REL_GRAD, f"train-mode grad features.{k}: {r:.3e}"
+    assert rel_fro(l_gpu.grad.cpu(), l_cpu.grad) < REL_GRAD
+    worst = ("", 0.0)
+    for k, p in param_dict(m).items():
+        if k.endswith("heatmap_token"):
+            continue
+        r = rel_fro(p.grad.cpu(), sd[k].grad)
+        if r > worst[1]:
+            worst = (k, r)
+    assert worst[1] < REL_GRAD, f"train-mode worst param grad {worst}"
+    # control: WITHOUT the masks the oracle must disagree (the test would otherwise be vacuous)
+    ref0, _ = ref_math.cross_fusion_forward({k: v.detach() for k, v in f_cpu.items()}, l_cpu.detach(), mask,
+                                            {k: v.detach() for k, v in sd.items()}, patch, H, layers)
+    assert rel_fro(out["0"].detach().float().cpu(), ref0["0"]) > 5 * REL_OUT
+
+
+def rel(a, b):
+    a, b = a.detach().double(), b.detach().double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def test_pairing_linear_epilogue_dropout_with_layernorm_bwd_dx2():
+    """dropout1 / dropout2: applied by the GEMM EPI_LINEAR epilogue, undone by layernorm_bwd's dx2_drop
+    (level_fn.py out-proj / FFN2 forward vs LN backward): both must equal the exported mask of (seed, site)."""
+    torch.manual_seed(0)
+    M, N, K, p, seed, site = 520, 896, 128, 0.15, 4242, 3 * 64 + SITE_DROP1
+    keep = ops.debug_dropout_mask(p, seed, site, 0, M, N).bool()
+    A = (torch.rand(M, K, device=DEV) + 0.25).bfloat16()
+    W = (torch.rand(N, K, device=DEV) + 0.25).bfloat16()
+    bias = torch.rand(N, device=DEV)
+    res = torch.randn(M, N, device=DEV).bfloat16()
+    out = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(A, W, out, M=M, N=N, K=K, bias=bias, residual=res, drop_p=p, drop_seed=seed, drop_stream=site)
+    ref = (A.float() @ W.float().t() + bias) * keep / (1 - p) + res.float()
+    assert rel(out.float(), ref) < 4e-3
+    # LayerNorm backward with the masked copy dx2
+    x = torch.randn(M, N, device=DEV).bfloat16()
+    dy = torch.randn(M, N, device=DEV).bfloat16()
+    gamma = torch.rand(N, device=DEV) + 0.5
+    mean = x.float().mean(-1)
+    rstd = (x.float().var(-1, unbiased=False) + 1e-5).rsqrt()
+    dx = torch.empty_like(x); dx2 = torch.empty_like(x)
+    dg, db, dbias = torch.zeros(N, device=DEV), torch.zeros(N, device=DEV), torch.zeros(N, device=DEV)
+    ops.layernorm_bwd(dy, x, gamma, mean, rstd, dx, dg, db, M, N, dbias=dbias, dx2=dx2, dx2_drop=(p, seed, site))
+    assert rel(dx2.float(), dx.float() * keep / (1 - p)) < 4e-3
+    assert torch.equal(dx2 != 0, keep & (dx != 0))
+    assert rel(dbias, dx2.float().sum(0)) < 1e-3   # bias grad of the dropped linear = column sums of the masked gradient
+
+
+def test_pairing_patch_embed_dropout_with_rows_gather():
+    """patch dropout: applied by the row-remapped GENERIC epilogue of the patch-embed GEMM at output rows b*S + t,
+    undone by rows_gather at the same source rows (level_fn.py forward K1 vs backward sequence disassembly)."""
+    torch.manual_seed(1)
+    Bt, n, S, N, K, p, seed, site = 3, 50, 60, 96, 72, 0.1, 99, SITE_PATCH
+    keep = ops.debug_dropout_mask(p, seed, site, 0, Bt * S, N).bool().view(Bt, S, N)[:, :n]
+    A = (torch.rand(Bt * n, K, device=DEV) + 0.25).bfloat16()
+    W = (torch.rand(N, K, device=DEV) + 0.25).bfloat16()
+    bias = torch.rand(N, device=DEV)
+    pos = torch.rand(64, N, device=DEV)
+    out = torch.zeros(Bt * S, N, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(A, W, out, M=Bt * n, N=N, K=K, bias=bias, pos_table=pos, rows_in=n, rows_out=S, drop_p=p, drop_seed=seed,
+             drop_stream=site)
+    ref = ((A.float() @ W.float().t() + bias).view(Bt, n, N) + pos[:n]) * keep / (1 - p)
+    got = out.float().view(Bt, S, N)[:, :n]
+    assert rel(got, ref) < 4e-3
+    assert torch.equal(got != 0, keep)
+    dz = torch.randn(Bt * S, N, device=DEV).bfloat16()
+    dzv = torch.empty(Bt * n, N, device=DEV, dtype=torch.bfloat16)
+    cs = torch.zeros(N, device=DEV)
+    ops.rows_gather(dz, dzv, Bt * n, N, in_map=(n, S, 0), colsum=cs, drop_p=p, drop_seed=seed, drop_stream=site)
+    refg = dz.float().view(Bt, S, N)[:, :n] * keep / (1 - p)
+    assert rel(dzv.float().view(Bt, n, N), refg) < 4e-3
+    assert rel(cs, dzv.float().sum(0)) < 1e-3
+
+
+def test_pairing_gelu_dropout_with_dgelu_drop_first():
+    """FFN dropout: GELU epilogue drops AFTER the activation; the FFN2 dgrad (DGELU epilogue, drop_first) applies the
+    same mask BEFORE GELU'."""
+    torch.manual_seed(2)
+    M, N, K, p, seed, site = 300, 1792, 64, 0.15, 5, 64 + SITE_FFN
+    keep = ops.debug_dropout_mask(p, seed, site, 0, M, N).bool()
+    A = torch.randn(M, K, device=DEV).bfloat16()
+    W = (0.2 * torch.randn(N, K, device=DEV)).bfloat16()
+    bias = torch.randn(N, device=DEV)
+    h = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    u = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(A, W, h, M=M, N=N, K=K, bias=bias, act=1, preact_out=u, drop_p=p, drop_seed=seed, drop_stream=site)
+    uref = A.float() @ W.float().t() + bias
+    assert rel(h.float(), torch.nn.functional.gelu(uref) * keep / (1 - p)) < 5e-3
+    G = torch.randn(M, K, device=DEV).bfloat16()
+    du = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(G, W, du, M=M, N=N, K=K, dact_in=u, drop_p=p, drop_seed=seed, drop_stream=site, drop_first=True)
+    uu = u.float().requires_grad_(True)
+    (torch.nn.functional.gelu(uu) * keep / (1 - p)).backward(G.float() @ W.float().t())
+    assert rel(du.float(), uu.grad) < 5e-3
+
+
+def test_backproj_dropout_pairing_layernorm_fwd_bwd_against_exported_mask():
+    torch.manual_seed(3)
+    Bt, n, S, D, p, seed, site = 2, 70, 90, 256, 0.1, 31, SITE_BACKPROJ
+    keep = ops.debug_dropout_mask(p, seed, site, 0, Bt * n, D).bool()
+    x = torch.randn(Bt * S, D, device=DEV).bfloat16()
+    gamma = torch.rand(D, device=DEV) + 0.5
+    beta = torch.randn(D, device=DEV)
+    y = torch.empty(Bt * n, D, device=DEV, dtype=torch.bfloat16)
+    mean = torch.empty(Bt * n, device=DEV); rstd = torch.empty(Bt * n, device=DEV)
+    ops.layernorm_fwd(x, y, gamma, beta, mean, rstd, Bt * n, D, in_map=(n, S, 0), drop_p=p, drop_seed=seed, drop_stream=site)
+    xv = x.float().view(Bt, S, D)[:, :n].reshape(Bt * n, D)
+    ref = torch.nn.functional.layer_norm(xv, (D,), gamma, beta) * keep / (1 - p)
+    assert rel(y.float(), ref) < 4e-3
+    assert torch.equal(y != 0, keep & (ref.bfloat16() != 0))
+
+
+def test_mask_hash_pairwise_independence():
+    """The product hash keep(row, col) = rowhash * colhash >= t: marginal rate, column-column correlations and 2 x 2
+    minors (joint keep probability of a (row pair, column pair)) must look like iid Bernoulli(1 - p)."""
+    p, rows, cols = 0.15, 8192, 896
+    k = ops.debug_dropout_mask(p, 12345, 77, 0, rows, cols).float()
+    assert abs(float(k.mean()) - (1 - p)) < 3 * math.sqrt(p * (1 - p) / (rows * cols)) + 2e-5
+    z = (k - k.mean(0)) / k.std(0).clamp_min(1e-6)
+    corr = (z.t() @ z) / rows
+    corr.fill_diagonal_(0)
+    assert float(corr.abs().max()) < 0.075   # iid: max over 4e5 pairs of N(0, 1/8192) ~ 0.05
+    zr = (k - k.mean(1, keepdim=True)) / k.std(1, keepdim=True).clamp_min(1e-6)
+    cr = (zr[:2048] @ zr[:2048].t()) / cols
+    cr.fill_diagonal_(0)
+    assert float(cr.abs().max()) < 0.25      # iid: max over 2e6 pairs of N(0, 1/896) ~ 0.17
+    # 2 x 2 minors: P(all four kept) = (1 - p)^4
+    a = k[0::2][:, 0::2] * k[0::2][:, 1::2] * k[1::2][:, 0::2] * k[1::2][:, 1::2]
+    assert abs(float(a.mean()) - (1 - p) ** 4) < 2e-3
+    # attention site: same checks on the symmetric (query hash x odd key hash) form
+    ka = ops.debug_attn_dropout_mask(p, 999, 5, 4, 1024, 1024).float()
+    assert abs(float(ka.mean()) - (1 - p)) < 1e-3
+    a = ka[:, 0::2, 0::2] * ka[:, 0::2, 1::2] * ka[:, 1::2, 0::2] * ka[:, 1::2, 1::2]
+    assert abs(float(a.mean()) - (1 - p) ** 4) < 2e-3

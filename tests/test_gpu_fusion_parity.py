@@ -4,7 +4,8 @@
 
 Tolerances (bf16 compute, fp32 accumulate; SURVEY §8c "observed error budget"): the reference's own
 autocast-bf16 run deviates from its fp32 run by rel-Frobenius 4.2e-3 on fused features and 5.0e-3 on
-weight grads; we require rel-Frobenius <= 1e-2 on fused features / LM logits, <= 2e-2 on gradients, and
+weight grads; we require rel-Frobenius <= 1e-2 on fused features / LM logits and on gradients (2x the reference's own
+bf16 error), and
 max-abs <= 5e-2 * max(1, rms(ref)) on fused features."""
 import pytest
 import torch
@@ -15,7 +16,7 @@ from tests.golden_utils import CASES, load_golden, rel_fro
 
 pytestmark = pytest.mark.gpu
 
-REL_OUT, REL_GRAD, MAXABS = 1e-2, 2e-2, 5e-2
+REL_OUT, REL_GRAD, MAXABS = 1e-2, 1e-2, 5e-2
 
 
 def _check_out(got, ref, name):
@@ -36,14 +37,16 @@ def test_golden_forward_backward(name):
     shapes = [tuple(feats[k].shape[2:]) for k in sorted(feats, key=int)]
     channels = [feats[k].shape[1] for k in sorted(feats, key=int)]
     D = g["lang"].shape[-1]
-    m = build_module(D, shapes, channels, g["patch"], g["layers"], g["heads"], lm=g["lm_on"])
+    m = build_module(D, shapes, channels, g["patch"], g["layers"], g["heads"], lm=g["lm_on"], use_lm_f=g["use_lm_f"],
+                     forward_language_f=g["fwd_lang"])
     missing, unexpected = m.load_state_dict(g["params"], strict=False)
     assert not unexpected
     assert all(("pos_embedding" in k or "padding_mask" in k) for k in missing), missing
     m.train()
     f_in = {k: v.cuda().requires_grad_(True) for k, v in feats.items()}
     lang = g["lang"].cuda().requires_grad_(True)
-    out, lm = run_module(m, f_in, lang, g["att_mask"].cuda())
+    # forward_language_f == "sum" adds in place in the reference (:206); hand the module a non-leaf alias like make_golden does
+    out, lm = run_module(m, f_in, lang * 1.0 if g["fwd_lang"] else lang, g["att_mask"].cuda())
     for k in out:
         _check_out(out[k], g["out"][k], f"{name}/features.{k}")
     loss = sum((out[k].float() * g["cot"][k].cuda()).sum() for k in out)

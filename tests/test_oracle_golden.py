@@ -5,19 +5,22 @@ import pytest
 import torch
 
 from oracle import ref_math
-from tests.golden_utils import CASES, load_golden, rel_fro
+from tests.golden_utils import CASES, DROPOUT_CASES, load_golden, rel_fro
 
 FP32_REL = 1e-5
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", CASES + DROPOUT_CASES)
 def test_oracle_forward_backward_matches_golden(name):
     g = load_golden(name)
     sd = {k: v.clone().requires_grad_(True) for k, v in g["params"].items()}
     feats = {k: v.clone().requires_grad_(True) for k, v in g["features"].items()}
     lang = g["lang"].clone().requires_grad_(True)
     out, lm = ref_math.cross_fusion_forward(feats, lang, g["att_mask"], sd, g["patch"], g["heads"],
-                                            g["layers"], lm=g["lm_on"])
+                                            g["layers"], lm=g["lm_on"], use_lm_f=g["use_lm_f"],
+                                            forward_language_f=g["fwd_lang"], masks=g["masks"] or None, drop=g["drop"])
+    if name in DROPOUT_CASES:
+        assert g["masks"] and g["drop"][1] > 0
     for k in out:
         assert out[k].shape == g["out"][k].shape
         assert rel_fro(out[k], g["out"][k]) < FP32_REL, k

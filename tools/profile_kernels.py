@@ -9,7 +9,7 @@ import torch
 
 from transfusion_b200 import ops
 
-B, S, D, H = int(os.environ.get("XF_B", 13)), 3136, 896, 4
+B, S, D, H = int(os.environ.get("XF_B", 13)), int(os.environ.get("XF_S", 3136)), 896, 4
 d = D // H
 M = B * S
 dev = "cuda"

@@ -140,6 +140,7 @@ EXPORTS = [
     "xf_layernorm_fwd", "xf_layernorm_bwd", "xf_colsum", "xf_cast_pad", "xf_cast_pad_multi", "xf_unpad_add",
     "xf_attn_delta", "xf_attn_fwd", "xf_attn_bwd", "xf_rows_gather",
     "xf_lm_pool_fwd", "xf_lm_pool_bwd", "xf_rowln_fwd", "xf_rowln_bwd", "xf_small_linear_fwd", "xf_small_linear_bwd",
+    "xf_debug_dropout_mask", "xf_debug_attn_dropout_mask",
 ]
 
 

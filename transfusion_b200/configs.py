@@ -11,7 +11,8 @@ import copy
 
 
 def default_fusion_cfg(token_dim: int, n_levels: int = 4, num_layers=None, num_heads: int = 4, patch=None,
-                       patch_dropout: float = 0.1, token_dropout: float = 0.15, backproj_dropout: float = 0.1) -> dict:
+                       patch_dropout: float = 0.1, token_dropout: float = 0.15, backproj_dropout: float = 0.1,
+                       use_lm_f: bool = True, forward_language_f=False) -> dict:
     patch = list(patch) if patch is not None else [4, 4, 2, 1][:n_levels]
     cfg = {
         "model": "cross_f",
@@ -24,7 +25,7 @@ def default_fusion_cfg(token_dim: int, n_levels: int = 4, num_layers=None, num_h
         "backproj_activ_f": None,
         "patch_norm": {"visual": None, "language": None},
         "pos_embedding": "sin1d",
-        "forward_language_f": False,
+        "forward_language_f": forward_language_f,
         "vis_mask_type": "global",
         "args": {
             "patch_dropout": patch_dropout,
@@ -37,7 +38,7 @@ def default_fusion_cfg(token_dim: int, n_levels: int = 4, num_layers=None, num_h
             "final_norm": "ln",
             "input_f_size": token_dim,
         },
-        "lm_args": {"pooling": {"type": "mean", "ln": True, "repr_size": 0}, "multi": False, "use_lm_f": True},
+        "lm_args": {"pooling": {"type": "mean", "ln": True, "repr_size": 0}, "multi": False, "use_lm_f": bool(use_lm_f)},
         "fpn_features": list(range(n_levels)),
         "replace_fpn_features": True,
     }

@@ -130,6 +130,9 @@ class CrossFusionBoxWrapper(nn.Module):
         seed = 0
         if self.training:
             seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item())
+        # the dropout seed of the last forward per level: with the site ids of LevelConfig.stream() it reproduces every
+        # keep mask of the step (xf_debug_dropout_mask; tests/test_gpu_dropout_parity.py)
+        self.__dict__.setdefault("_xf_last_seeds", {})[i] = seed
         cfg = LevelConfig(level=i, patch=p, num_heads=enc.num_heads, num_layers=enc.num_layers, training=self.training,
                           patch_dropout=float(enc.patch_dropout), token_dropout=float(enc.token_dropout),
                           backproj_dropout=float(t2f.back_dropout.p), seed=seed, need_lang_out=need_lang_out,
@@ -160,9 +163,12 @@ class CrossFusionBoxWrapper(nn.Module):
         features_dict = self.rcnn_model.forward_features(visual_data, targets)
         language_f, att_w, att_mask = self.narr_pooling_layer(x["language_f"], pad_mask=True)
         lang_pad = None if att_mask is None else ~(att_mask.type(torch.bool))  # reference :196
-        need_lang_out = bool(self.multi_lm or self.forward_language_f or (self.lm_on and not self.use_lm_f))
+        lm_from_fused = bool(self.lm_on and not self.use_lm_f)
+        need_all_lang = bool(self.multi_lm or self.forward_language_f)
         mscale_l_features = []
         fused_l_features = None
+        lm_tokens = None   # what the reference's `fused_l_features` holds after its loop: the LAST level's tokens (:177-222)
+        last_level = len(self.fpn_features_idx) - 1
         # Levels are independent given the shared language input (forward_language_f: False, fusion yml :27),
         # so they are visited coarsest-first: autograd then runs the largest level's backward FIRST and its
         # gradient all-reduce overlaps the remaining levels.  With forward_language_f the reference order holds.
@@ -190,6 +196,7 @@ class CrossFusionBoxWrapper(nn.Module):
         for i, key in level_order:
             key = str(key)
             feat = features_dict["features"][key]
+            need_lang_out = need_all_lang or (lm_from_fused and i == last_level)
             self.tokens_to_features[i].init_h = feat.shape[2]
             self.tokens_to_features[i].init_w = feat.shape[3]
             if side is not None:
@@ -204,6 +211,8 @@ class CrossFusionBoxWrapper(nn.Module):
                 keep_alive.append((feat, language_f, lang_pad))
             else:
                 fused, fused_l_features = self.run_level(i, feat, language_f, lang_pad, need_lang_out)
+            if i == last_level:
+                lm_tokens = fused_l_features   # independent of the visiting order
             if self.multi_lm:
                 mscale_l_features.append(fused_l_features)
             if self.forward_language_f:
@@ -229,7 +238,7 @@ class CrossFusionBoxWrapper(nn.Module):
         rcnn_outs = self.rcnn_model.apply_rpn_roi_on_features(features_dict)
         if self.lm_on:
             rcnn_outs["lm"] = self.lm_layer(
-                mscale_l_features if self.multi_lm else fused_l_features if not self.use_lm_f else language_f,
+                mscale_l_features if self.multi_lm else lm_tokens if not self.use_lm_f else language_f,
                 None if att_mask is None else att_mask.type(torch.bool))
         return rcnn_outs
 

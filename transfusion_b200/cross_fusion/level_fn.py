@@ -270,6 +270,8 @@ class FusionLevelFunction(torch.autograd.Function):
         # views as .grad without copying.
         arena = {"buf": None, "off": 0}
         arena_cap = sum(int(q.numel()) for q in params if q is not None and q.requires_grad) + 8 * len(params) * 64 + (1 << 16)
+        if dp != d:   # head-padded scratch gradients (g_win_p, g_bin_p, g_wo_p) live in the arena as well
+            arena_cap += nl * (3 * Dp * D + D * Dp + 3 * Dp + 3 * 64)
 
         def zeros(*shape, dtype=f32):
             if dtype != f32:
@@ -279,7 +281,10 @@ class FusionLevelFunction(torch.autograd.Function):
                 numel *= int(s_)
             need = (numel + 63) // 64 * 64   # 256-byte aligned slices
             if arena["buf"] is None or arena["off"] + need > arena["buf"].numel():
-                arena["buf"] = torch.zeros(max(need, arena_cap if arena["buf"] is None else 1 << 24), device=dev, dtype=f32)
+                # one buffer per level by construction (arena_cap): a second one would silently break the in-place
+                # data-parallel reduction of the arena (parallel.BucketedGradAllReduce)
+                assert arena["buf"] is None, "gradient arena overflow: arena_cap underestimates the level's gradients"
+                arena["buf"] = torch.zeros(max(need, arena_cap), device=dev, dtype=f32)
                 arena["off"] = 0
             out = arena["buf"][arena["off"]:arena["off"] + numel].view(*shape)
             arena["off"] += need

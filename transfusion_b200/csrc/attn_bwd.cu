@@ -374,13 +374,15 @@ attn_bwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gr
 template <int MODE>
 static int launch_bwd2(bool drop, int grid, int smem_bytes, cudaStream_t stream, const CUtensorMap& r1, const CUtensorMap& r2,
                        const CUtensorMap& t1, const CUtensorMap& t2, const AttnBwd2Params& p) {
-  if (drop) {
-    XF_CUDA(cudaFuncSetAttribute(attn_bwd2_tcgen05_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attn_bwd2_tcgen05_kernel<MODE, true><<<grid, NB_THREADS, smem_bytes, stream>>>(r1, r2, t1, t2, p);
-  } else {
-    XF_CUDA(cudaFuncSetAttribute(attn_bwd2_tcgen05_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attn_bwd2_tcgen05_kernel<MODE, false><<<grid, NB_THREADS, smem_bytes, stream>>>(r1, r2, t1, t2, p);
-  }
+  static DeviceOnce once;
+  if (int rc = once.run([] {
+        XF_CUDA(cudaFuncSetAttribute(attn_bwd2_tcgen05_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        XF_CUDA(cudaFuncSetAttribute(attn_bwd2_tcgen05_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        return 0;
+      }))
+    return rc;
+  if (drop) attn_bwd2_tcgen05_kernel<MODE, true><<<grid, NB_THREADS, smem_bytes, stream>>>(r1, r2, t1, t2, p);
+  else attn_bwd2_tcgen05_kernel<MODE, false><<<grid, NB_THREADS, smem_bytes, stream>>>(r1, r2, t1, t2, p);
   g_launches.fetch_add(1);
   XF_CUDA(cudaGetLastError());
   return 0;

@@ -387,12 +387,13 @@ extern "C" int xf_attn_fwd(const XfAttnFwd* a, xf_stream_t stream_) {
   const int ring = (AF_KST + AF_VST) * p.nch * 4096;
   const int stage = ((a->dp + 63) / 64) * 16384;   // Q staging aliases the rings
   const int smem_bytes = 1024 + 4096 + (ring > stage ? ring : stage);
-  static bool attr_set = false;
-  if (!attr_set) {
-    XF_CUDA(cudaFuncSetAttribute(attn_fwd_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    XF_CUDA(cudaFuncSetAttribute(attn_fwd_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  static DeviceOnce once;
+  if (int rc1 = once.run([] {
+        XF_CUDA(cudaFuncSetAttribute(attn_fwd_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        XF_CUDA(cudaFuncSetAttribute(attn_fwd_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        return 0;
+      }))
+    return rc1;
   const int grid = a->B * a->H * p.q_tiles;
   if (a->drop_p > 0.f) attn_fwd_tcgen05_kernel<true><<<grid, AF_THREADS, smem_bytes, stream>>>(tq, tk, tv, p);
   else attn_fwd_tcgen05_kernel<false><<<grid, AF_THREADS, smem_bytes, stream>>>(tq, tk, tv, p);

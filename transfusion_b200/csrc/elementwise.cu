@@ -766,11 +766,9 @@ static int launch_ln_bwd_tma(const LnBwdParams& p, int bc, cudaStream_t st) {
   if ((rc = make_tmap_rowblock_bf16(&tx, p.x, p.rows, p.D, p.ldx, bc, LNT_ROWS))) return rc;
   if ((rc = make_tmap_rowblock_bf16(&td, p.dy, p.rows, p.D, p.lddy, bc, LNT_ROWS))) return rc;
   const int smem = 128 + 128 + (2 * LNT_STAGES + 1) * LNT_ROWS * p.D * 2;
-  static bool attr_set = false;
-  if (!attr_set) {
-    XF_CUDA(cudaFuncSetAttribute(layernorm_bwd_tma_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
-    attr_set = true;
-  }
+  static DeviceOnce once;
+  if (int rc = once.run([] { XF_CUDA(cudaFuncSetAttribute(layernorm_bwd_tma_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024)); return 0; }))
+    return rc;
   const int nblk = (p.rows + LNT_ROWS - 1) / LNT_ROWS;
   int ctas = 2 * sm_count();
   if (ctas > nblk) ctas = nblk;
@@ -1271,6 +1269,51 @@ extern "C" int xf_rows_gather(const void* in, int64_t ldi, void* out, int64_t ld
       reinterpret_cast<const __nv_bfloat16*>(in), ldi, reinterpret_cast<__nv_bfloat16*>(out), ldo, rows, D, rin, rout, roff,
       rows_per_cta, colsum, drop_p, drop_key(seed, stream_id), stream_id, drop_thresh32(drop_p),
       drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f, coltab);
+  g_launches.fetch_add(1);
+  XF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Test aid: materialise the counter-based dropout keep masks (ptx.cuh) so a CPU checker can apply the SAME masks.
+// These are the canonical definitions every kernel of the library recomputes on the fly.
+// ------------------------------------------------------------------------------------------
+namespace xf {
+__global__ void debug_drop_mask_kernel(uint8_t* __restrict__ out, long long row0, int rows, int cols, uint32_t key, uint32_t t32) {
+  const long long total = static_cast<long long>(rows) * cols;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / cols;
+    const uint32_t c = static_cast<uint32_t>(i - r * cols);
+    out[i] = drop_keep_rc(drop_rowhash(key, static_cast<uint64_t>(row0 + r)), drop_colodd(c), t32) ? 1 : 0;
+  }
+}
+__global__ void debug_attn_drop_mask_kernel(uint8_t* __restrict__ out, int BH, int Sq, int Sk, uint32_t key, uint32_t t32) {
+  const long long total = static_cast<long long>(BH) * Sq * Sk;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long rq = i / Sk;   // bh * Sq + q: the row index the attention kernels hash
+    const uint32_t k = static_cast<uint32_t>(i - rq * Sk);
+    out[i] = drop_keep_rc(drop_rowhash(key, static_cast<uint64_t>(rq)), drop_colhash(key, k), t32) ? 1 : 0;
+  }
+}
+}  // namespace xf
+
+extern "C" int xf_debug_dropout_mask(float p, uint32_t seed, uint32_t stream_id, int64_t row0, int rows, int cols, uint8_t* out,
+                                     xf_stream_t s) {
+  if (!out) return fail(-1, "xf_debug_dropout_mask: null pointer");
+  if (rows <= 0 || cols <= 0) return 0;
+  debug_drop_mask_kernel<<<grid_for(static_cast<long long>(rows) * cols, 256), 256, 0, reinterpret_cast<cudaStream_t>(s)>>>(
+      out, row0, rows, cols, drop_key(seed, stream_id), drop_thresh32(p));
+  g_launches.fetch_add(1);
+  XF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int xf_debug_attn_dropout_mask(float p, uint32_t seed, uint32_t stream_id, int BH, int Sq, int Sk, uint8_t* out,
+                                          xf_stream_t s) {
+  if (!out) return fail(-1, "xf_debug_attn_dropout_mask: null pointer");
+  if (BH <= 0 || Sq <= 0 || Sk <= 0) return 0;
+  debug_attn_drop_mask_kernel<<<grid_for(static_cast<long long>(BH) * Sq * Sk, 256), 256, 0, reinterpret_cast<cudaStream_t>(s)>>>(
+      out, BH, Sq, Sk, drop_key(seed, stream_id), drop_thresh32(p));
   g_launches.fetch_add(1);
   XF_CUDA(cudaGetLastError());
   return 0;

@@ -602,11 +602,9 @@ static int pick_tile_n(long long N) {
 template <int CG, int EPI>
 static int launch_gemm(int ctas, int smem_bytes, cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
                        const CUtensorMap& td, const GemmParams& p) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    XF_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<CG, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  static DeviceOnce once;   // the attribute is per device: one opt-in per (kernel instantiation, device)
+  if (int rc = once.run([] { XF_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<CG, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); return 0; }))
+    return rc;
   if (CG == 1) {
     gemm_bf16_tcgen05_kernel<CG, EPI><<<ctas, GEMM_THREADS, smem_bytes, stream>>>(ta, tb, tc, td, p);
     return 0;

@@ -102,15 +102,15 @@ int make_tmap_rowblock_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, ui
 }
 
 int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    cudaDeviceProp p;
-    if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 148;
-    n = p.multiProcessorCount;
+  static std::atomic<int> n[64];   // zero-initialised; one slot per device
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  int v = n[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
+    n[dev].store(v, std::memory_order_relaxed);
   }
-  return n;
+  return v;
 }
 
 // Odd column hashes of the GEMM / LayerNorm dropout sites (ptx.cuh:drop_colodd), one table per device, filled

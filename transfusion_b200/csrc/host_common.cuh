@@ -9,6 +9,7 @@
 #include <stdio.h>
 
 #include <atomic>
+#include <mutex>
 
 namespace xf {
 
@@ -59,7 +60,27 @@ int make_tmap_rowblock_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, ui
 int make_tmap_chunks_bf16(CUtensorMap* out, const void* ptr, uint64_t batch, uint64_t rows, uint64_t cols, uint64_t ld,
                           uint32_t box_rows, uint32_t box_chunks);
 
-int sm_count();
+int sm_count();   // of the CURRENT device (cached per device)
+
+// Per-device one-time setup (cudaFuncSetAttribute is per device / context): runs f() the first time it is reached
+// on each device, under a mutex, and only marks the device done when f() returned 0.  Usage:
+//   static DeviceOnce once;  if (int rc = once.run([&] { XF_CUDA(cudaFuncSetAttribute(...)); return 0; })) return rc;
+struct DeviceOnce {
+  std::atomic<uint64_t> done{0};
+  template <typename F>
+  int run(F&& f) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    const uint64_t bit = 1ull << (dev & 63);
+    if (done.load(std::memory_order_acquire) & bit) return 0;
+    std::lock_guard<std::mutex> lock(mu);
+    if (done.load(std::memory_order_relaxed) & bit) return 0;
+    const int rc = f();
+    if (rc == 0) done.fetch_or(bit, std::memory_order_release);
+    return rc;
+  }
+  std::mutex mu;
+};
 
 // device table of drop_colodd(0 .. XF_DROP_TABLE_COLS-1) for the current device (nullptr on failure)
 constexpr uint32_t XF_DROP_TABLE_COLS = 16384;

@@ -374,3 +374,18 @@ def small_linear_bwd(dy: torch.Tensor, x: torch.Tensor, W: torch.Tensor, act: in
         check(lib().xf_small_linear_bwd(_ptr(dy), _ptr(x), _ptr(W), R, Cn, D, act, _ptr(dx), _ptr(dW), _ptr(db), _stream()),
               "xf_small_linear_bwd")
     return dx, dW, db
+
+
+# ---- test aids: the dropout keep masks the kernels recompute on the fly (include/xfusion.h) ------------------------
+def debug_dropout_mask(p: float, seed: int, stream: int, row0: int, rows: int, cols: int, device="cuda") -> torch.Tensor:
+    out = torch.empty(rows, cols, device=device, dtype=torch.uint8)
+    check(lib().xf_debug_dropout_mask(C.c_float(p), C.c_uint32(seed), C.c_uint32(stream), C.c_int64(row0), rows, cols, _ptr(out),
+                                      _stream()), "xf_debug_dropout_mask")
+    return out
+
+
+def debug_attn_dropout_mask(p: float, seed: int, stream: int, BH: int, Sq: int, Sk: int, device="cuda") -> torch.Tensor:
+    out = torch.empty(BH, Sq, Sk, device=device, dtype=torch.uint8)
+    check(lib().xf_debug_attn_dropout_mask(C.c_float(p), C.c_uint32(seed), C.c_uint32(stream), BH, Sq, Sk, _ptr(out), _stream()),
+          "xf_debug_attn_dropout_mask")
+    return out
