@@ -24,7 +24,7 @@ extern "C" {
 
 typedef void* xf_stream_t; /* cudaStream_t */
 
-#define XF_ABI_VERSION 1
+#define XF_ABI_VERSION 2
 
 int xf_version(void);
 const char* xf_last_error(void);
@@ -78,6 +78,13 @@ typedef struct XfGemm {
   int32_t drop_first;
   int32_t max_ctas;         /* 0 = one per SM */
   int32_t cta_group;        /* 0 = auto (CTA pairs, 256 x tile_n tiles via cta_group::2), 1 = single-CTA 128 x tile_n tiles, 2 = force pairs */
+  /* Batched GEMM (batch1 > 0): batch1 x max(batch2, 1) independent problems of the same M, N, K; entry (i, j) reads A at
+   * a + i * a_bs1 + j * a_bs2 (elements), B and out likewise (residual / preact_out / dact_in use the out strides).
+   * The two-level index lets a per-(sample, head) problem address token-major [B*S, H*dp] tensors: bs1 = S * ld,
+   * bs2 = dp.  Rows / columns outside M, N, K are zero-filled per entry (TMA bounds), so neighbouring entries may
+   * overlap in memory.  Specialised epilogues only; no split_k. */
+  int32_t batch1, batch2;
+  int64_t a_bs1, a_bs2, b_bs1, b_bs2, out_bs1, out_bs2;
 } XfGemm;
 
 int xf_gemm(const XfGemm* g, xf_stream_t stream);
@@ -227,8 +234,15 @@ typedef struct XfAttnBwd {
   float scale;
   float drop_p; uint32_t drop_seed, drop_stream;   /* must equal the forward's */
   void* debug_timeline;                            /* dev aid: NULL, or int64[2][2][64][8] device buffer of clock64 stamps */
+  /* Optional scratch of >= xf_attn_bwd_workspace_bytes(B, H, Sq, Sk) bytes (16-byte aligned, contents undefined on
+   * entry and exit).  With it the backward computes the score tiles ONCE: a key-stationary tcgen05 pass produces dK and
+   * streams E = scale * dS^T and P_d^T / (1 - p) as bf16 [B, H, Sk, Sq] tiles to the scratch, and dQ = E^T K, dV = P_d^T dO
+   * run as two batched GEMMs (5 GEMM units in total, the algorithmic minimum).  Without it (NULL): three tcgen05
+   * passes that recompute the scores (8 units) and never leave the chip: no S x S bytes in HBM. */
+  void* workspace; int64_t workspace_bytes;
 } XfAttnBwd;
 int xf_attn_bwd(const XfAttnBwd* a, xf_stream_t stream);
+int64_t xf_attn_bwd_workspace_bytes(int B, int H, int Sq, int Sk);
 
 /* out[r,:] = in[(r / rin) * rout + r % rin + roff, :] with the dropout mask of the forward write at
  * the source position, colsum += column sums of out (may be NULL).  Patch-embed backward: gathers the

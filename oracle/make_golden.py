@@ -87,7 +87,39 @@ def run_case(name, case):
         loss = loss + lm["noun_logits"].sum() * 0.5 + (lm["verb_logits"] ** 2).sum() * 0.25
     loss.backward()
 
+    # The reference's OWN bf16 error on these inputs (torch.autocast on CPU, same weights / masks): the anchor of the
+    # GPU tolerances ("no worse than 2x the reference's own autocast-bf16 error").
+    def rel(a, b):
+        return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+
+    fp32_pg = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+    fp32_out = {k: v.detach().clone() for k, v in out.items()}
+    fp32_gl = lang_in.grad.clone()
+    m.zero_grad(set_to_none=True)
+    feats_b = {k: v.clone().requires_grad_(True) for k, v in feats.items()}
+    lang_b = lang.clone().requires_grad_(True)
+    lang_barg = lang_b * 1.0 if case.get("fwd_lang") else lang_b
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        if case.get("dropout"):
+            with ref_loader.recorded_dropout(case["seed"] + 2000):
+                out_b, lm_b = ref_loader.run_reference(m, feats_b, lang_barg, mask)
+        else:
+            out_b, lm_b = ref_loader.run_reference(m, feats_b, lang_barg, mask)
+    loss_b = sum((out_b[k].float() * cot[k]).sum() for k in out_b)
+    if lm_b is not None:
+        loss_b = loss_b + lm_b["noun_logits"].float().sum() * 0.5 + (lm_b["verb_logits"].float() ** 2).sum() * 0.25
+    loss_b.backward()
+    ac_err = {f"out.{k}": rel(out_b[k].detach().float(), fp32_out[k]) for k in out_b}
+    ac_err["glang"] = rel(lang_b.grad, fp32_gl)
+    for k, p in m.named_parameters():
+        if p.grad is not None and k in fp32_pg:
+            ac_err[f"pgrad.{k}"] = rel(p.grad, fp32_pg[k])
+    for k, p in m.named_parameters():   # restore the fp32 gradients for the blob below
+        p.grad = fp32_pg.get(k)
+
     blob = {}
+    for k, v in ac_err.items():
+        blob[f"refbf16err.{k}"] = np.array(v, dtype=np.float64)
     for k, v in feats.items():
         blob[f"in.features.{k}"] = v.numpy()
         blob[f"in.cotangent.{k}"] = cot[k].numpy()
@@ -121,7 +153,9 @@ def run_case(name, case):
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     path = os.path.join(GOLDEN_DIR, name + ".npz")
     np.savez_compressed(path, **{k: (v.astype(np.float32) if v.dtype == np.float64 else v) for k, v in blob.items()})
-    print(f"{name}: wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB), loss={float(loss):.6f}")
+    worst = max(ac_err.items(), key=lambda kv: kv[1])
+    print(f"{name}: wrote {path} ({os.path.getsize(path) / 1e6:.2f} MB), loss={float(loss):.6f}; reference's own bf16-autocast "
+          f"error: worst {worst[0]} = {worst[1]:.3e}, out {max(v for k, v in ac_err.items() if k.startswith('out.')):.3e}")
 
 
 def main():

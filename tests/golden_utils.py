@@ -39,6 +39,8 @@ def load_golden(name):
     g["use_lm_f"] = bool(int(z["meta.use_lm_f"])) if "meta.use_lm_f" in z.files else True
     g["fwd_lang"] = (str(z["meta.fwd_lang"]) or False) if "meta.fwd_lang" in z.files else False
     g["drop"] = tuple(float(x) for x in z["meta.drop"]) if "meta.drop" in z.files else (0.0, 0.0, 0.0)
+    # the reference's own bf16-autocast error per tensor on these inputs (oracle/make_golden.py): anchors the GPU bounds
+    g["ref_bf16_err"] = {k[len("refbf16err."):]: float(z[k]) for k in z.files if k.startswith("refbf16err.")}
     g["masks"] = {}
     for k in z.files:
         if k.startswith("mask."):
@@ -54,3 +56,9 @@ def rel_fro(a, b):
     a = a.detach().double()
     b = b.detach().double()
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def grad_bound(g, key, floor=1e-2, cap=2e-2):
+    """"no worse than 2x the reference's own autocast-bf16 error on the same inputs", never tighter than
+    `floor` (the bound used at the shipped widths) and never looser than `cap`."""
+    return min(cap, max(floor, 2.0 * g["ref_bf16_err"].get(key, 0.0)))

@@ -29,7 +29,7 @@ def test_library_builds_and_exports_every_declared_symbol():
 
 def test_version_and_error_string():
     L = _lib.lib()
-    assert L.xf_version() == 1
+    assert L.xf_version() == 2
     assert isinstance(L.xf_last_error(), bytes)
     assert L.xf_launch_count() == 0
 

@@ -159,7 +159,7 @@ def test_pairing_patch_embed_dropout_with_rows_gather():
     ops.rows_gather(dz, dzv, Bt * n, N, in_map=(n, S, 0), colsum=cs, drop_p=p, drop_seed=seed, drop_stream=site)
     refg = dz.float().view(Bt, S, N)[:, :n] * keep / (1 - p)
     assert rel(dzv.float().view(Bt, n, N), refg) < 4e-3
-    assert rel(cs, dzv.float().sum(0)) < 1e-3
+    assert rel(cs, refg.sum((0, 1))) < 1e-3   # fp32 column sums of the unrounded masked rows (image_kind_embedding grad)
 
 
 def test_pairing_gelu_dropout_with_dgelu_drop_first():

@@ -190,15 +190,18 @@ def test_attention_forward_backward(B, H, S, d, mask):
     dout.view(B, S, H, dp)[..., :d] = dsrc
     delta = torch.zeros(B, H, Sp, device=DEV)
     ops.attn_delta(out, dout, delta, B, S, H, dp)
-    dqkv = torch.full((B * S, 3 * Dp), 7.0, device=DEV, dtype=torch.bfloat16)
-    ops.attn_bwd(qkv[:, :Dp], qkv[:, Dp:2 * Dp], qkv[:, 2 * Dp:], dout, lse, delta, dqkv[:, :Dp], dqkv[:, Dp:2 * Dp],
-                 dqkv[:, 2 * Dp:], B=B, H=H, Sq=S, Sk=S, dp=dp, scale=1 / math.sqrt(d), key_padding_mask=kpm)
     ref.backward(dsrc.float().reshape(B, S, D))
-    got = dqkv.view(B, S, 3, H, dp)
-    for i, g in enumerate((qf.grad, kf.grad, vf.grad)):
-        assert rel(got[:, :, i, :, :d].reshape(B, S, D).float(), g) < 8e-3
-    if dp != d:
-        assert float(got[..., d:].float().abs().max()) == 0.0
+    # both backward schedules: three on-chip passes (no workspace) and the 5-unit path (key-stationary pass + two batched
+    # GEMMs over a bf16 [B, H, Sk, Sq] scratch)
+    for ws in (None, torch.empty(ops.attn_bwd_workspace_bytes(B, H, S, S), device=DEV, dtype=torch.uint8)):
+        dqkv = torch.full((B * S, 3 * Dp), 7.0, device=DEV, dtype=torch.bfloat16)
+        ops.attn_bwd(qkv[:, :Dp], qkv[:, Dp:2 * Dp], qkv[:, 2 * Dp:], dout, lse, delta, dqkv[:, :Dp], dqkv[:, Dp:2 * Dp],
+                     dqkv[:, 2 * Dp:], B=B, H=H, Sq=S, Sk=S, dp=dp, scale=1 / math.sqrt(d), key_padding_mask=kpm, workspace=ws)
+        got = dqkv.view(B, S, 3, H, dp)
+        for i, g in enumerate((qf.grad, kf.grad, vf.grad)):
+            assert rel(got[:, :, i, :, :d].reshape(B, S, D).float(), g) < 8e-3, ("workspace" if ws is not None else "3-pass", i)
+        if dp != d:
+            assert float(got[..., d:].float().abs().max()) == 0.0
 
 
 def test_cross_attention_lq_ne_lk():
@@ -244,12 +247,13 @@ def test_attention_dropout_mask_consistent_between_forward_and_backward():
     dout = dsrc.reshape(B * S, Dp).contiguous()
     delta = torch.zeros(B, H, 128, device=DEV)
     ops.attn_delta(out, dout, delta, B, S, H, d)
-    dqkv = torch.zeros(B * S, 3 * Dp, device=DEV, dtype=torch.bfloat16)
-    ops.attn_bwd(qkv[:, :Dp], qkv[:, Dp:2 * Dp], qkv[:, 2 * Dp:], dout, lse, delta, dqkv[:, :Dp], dqkv[:, Dp:2 * Dp],
-                 dqkv[:, 2 * Dp:], key_padding_mask=None, **kw)
-    got = dqkv.view(B, S, 3, H, d)
-    for i, g in enumerate((qf.grad, kf.grad, vf.grad)):
-        assert rel(got[:, :, i].reshape(B, S, H * d).float(), g) < 1e-2
+    for ws in (None, torch.empty(ops.attn_bwd_workspace_bytes(B, H, S, S), device=DEV, dtype=torch.uint8)):
+        dqkv = torch.zeros(B * S, 3 * Dp, device=DEV, dtype=torch.bfloat16)
+        ops.attn_bwd(qkv[:, :Dp], qkv[:, Dp:2 * Dp], qkv[:, 2 * Dp:], dout, lse, delta, dqkv[:, :Dp], dqkv[:, Dp:2 * Dp],
+                     dqkv[:, 2 * Dp:], key_padding_mask=None, workspace=ws, **kw)
+        got = dqkv.view(B, S, 3, H, d)
+        for i, g in enumerate((qf.grad, kf.grad, vf.grad)):
+            assert rel(got[:, :, i].reshape(B, S, H * d).float(), g) < 1e-2, ("workspace" if ws is not None else "3-pass", i)
 
 
 # ------------------------------------------------------------------ LayerNorm / layout / misc
@@ -386,3 +390,31 @@ def test_lm_head_matches_reference_modules(kind, ln, repr_size):
     assert rel(gtok, tok2.grad) < 1e-5
     for k, p in head.named_parameters():
         assert rel(got[k], p.grad) < 1e-5, k
+
+
+# ------------------------------------------------------------------ batched GEMM (per (sample, head) problems)
+@pytest.mark.parametrize("Bt,H,Sq,Sk,dp", [(2, 4, 300, 300, 224), (3, 2, 200, 328, 192), (1, 4, 832, 832, 32)])
+def test_gemm_batched_head_addressing(Bt, H, Sq, Sk, dp):
+    """The two batched products of the attention backward: dQ[b, q, h*dp + e] = sum_k E[b, h, k, q] K[b, k, h*dp + e]
+    (A stored [K][M], B stored [K][N], token-major output with heads in columns) and
+    dV[b, k, h*dp + e] = sum_q P[b, h, k, q] dO[b, q, h*dp + e] (A stored [M][K]).  Rows / columns outside the per-entry
+    extents (the padded pitch of E, the next head's columns) must not leak into the result."""
+    torch.manual_seed(40)
+    Sqp = (Sq + 63) // 64 * 64
+    E = torch.randn(Bt, H, Sk, Sqp, device=DEV).bfloat16()     # garbage in the padded columns on purpose
+    kv = torch.randn(Bt * Sk, 3 * H * dp, device=DEV).bfloat16()
+    K = kv[:, H * dp:2 * H * dp]
+    dq = torch.zeros(Bt * Sq, 3 * H * dp, device=DEV, dtype=torch.bfloat16)
+    ld = 3 * H * dp
+    ops.gemm(E, K, dq, M=Sq, N=dp, K=Sk, a_mn_major=True, b_mn_major=True, a_ld=Sqp, b_ld=ld, ldc=ld,
+             batch=(Bt, H, (H * Sk * Sqp, Sk * Sqp), (Sk * ld, dp), (Sq * ld, dp)))
+    ref = torch.einsum("bhkq,bkhe->bqhe", E[..., :Sq].float(), K.float().reshape(Bt, Sk, H, dp)).reshape(Bt * Sq, H * dp)
+    assert rel(dq[:, :H * dp].float(), ref) < 3e-3
+    assert float(dq[:, H * dp:].abs().max()) == 0.0   # nothing written outside the addressed head columns
+    # dV-style: A K-major
+    do = torch.randn(Bt * Sq, H * dp, device=DEV).bfloat16()
+    dv = torch.zeros(Bt * Sk, H * dp, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(E, do, dv, M=Sk, N=dp, K=Sq, a_mn_major=False, b_mn_major=True, a_ld=Sqp, b_ld=H * dp, ldc=H * dp,
+             batch=(Bt, H, (H * Sk * Sqp, Sk * Sqp), (Sq * H * dp, dp), (Sk * H * dp, dp)))
+    ref = torch.einsum("bhkq,bqhe->bkhe", E[..., :Sq].float(), do.float().reshape(Bt, Sq, H, dp)).reshape(Bt * Sk, H * dp)
+    assert rel(dv.float(), ref) < 3e-3

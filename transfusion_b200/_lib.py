@@ -31,6 +31,9 @@ class XfGemm(C.Structure):
         ("out_dtype", C.c_int32), ("accumulate", C.c_int32),
         ("drop_p", C.c_float), ("drop_seed", C.c_uint32), ("drop_stream", C.c_uint32),
         ("drop_first", C.c_int32), ("max_ctas", C.c_int32), ("cta_group", C.c_int32),
+        ("batch1", C.c_int32), ("batch2", C.c_int32),
+        ("a_bs1", C.c_int64), ("a_bs2", C.c_int64), ("b_bs1", C.c_int64), ("b_bs2", C.c_int64),
+        ("out_bs1", C.c_int64), ("out_bs2", C.c_int64),
     ]
 
 
@@ -108,6 +111,7 @@ class XfAttnBwd(C.Structure):
         ("scale", C.c_float),
         ("drop_p", C.c_float), ("drop_seed", C.c_uint32), ("drop_stream", C.c_uint32),
         ("debug_timeline", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64),
     ]
 
 
@@ -127,6 +131,9 @@ def lib():
         for name in EXPORTS:
             if name in ("xf_version", "xf_last_error", "xf_launch_count"):
                 continue
+            if name == "xf_attn_bwd_workspace_bytes":
+                getattr(L, name).restype = C.c_int64
+                continue
             fn = getattr(L, name)
             fn.restype = C.c_int
         _lib = L
@@ -138,7 +145,7 @@ EXPORTS = [
     "xf_version", "xf_last_error", "xf_launch_count", "xf_gemm",
     "xf_patchify", "xf_fold", "xf_lang_rows_fwd", "xf_lang_rows_bwd",
     "xf_layernorm_fwd", "xf_layernorm_bwd", "xf_colsum", "xf_cast_pad", "xf_cast_pad_multi", "xf_unpad_add",
-    "xf_attn_delta", "xf_attn_fwd", "xf_attn_bwd", "xf_rows_gather",
+    "xf_attn_delta", "xf_attn_fwd", "xf_attn_bwd", "xf_attn_bwd_workspace_bytes", "xf_rows_gather",
     "xf_lm_pool_fwd", "xf_lm_pool_bwd", "xf_rowln_fwd", "xf_rowln_bwd", "xf_small_linear_fwd", "xf_small_linear_bwd",
     "xf_debug_dropout_mask", "xf_debug_attn_dropout_mask",
 ]

@@ -24,6 +24,11 @@ from .. import ops
 
 LN_EPS = 1e-5
 
+# Attention backward schedule: 1 = score tiles computed once, dQ / dV as batched GEMMs over a transient bf16 [B, H, S, S]
+# scratch (5 GEMM units); 0 = three on-chip passes that recompute the scores (8 units, no S x S bytes in HBM)
+import os as _os
+ATTN_BWD_WORKSPACE = bool(int(_os.environ.get("XF_ATTN_BWD_WS", "1")))
+
 # dropout sites inside one encoder layer (stream ids for the counter-based RNG)
 SITE_ATTN, SITE_DROP1, SITE_FFN, SITE_DROP2 = 0, 1, 2, 3
 SITE_PATCH, SITE_BACKPROJ = 60, 61
@@ -326,6 +331,10 @@ class FusionLevelFunction(torch.autograd.Function):
         grads[base_tail + 2], grads[base_tail + 3] = g_wbp, g_bbp
         del dvis
 
+        # scratch of the 5-unit attention backward (E = scale dS^T and P_d^T as bf16 [B, H, S, S]); one buffer for all layers
+        attn_ws = None
+        if ATTN_BWD_WORKSPACE:
+            attn_ws = torch.empty(ops.attn_bwd_workspace_bytes(B, H, S, S), device=dev, dtype=torch.uint8)
         dcur = dxf  # gradient w.r.t. the layer output x2
         for l in reversed(range(nl)):
             (in_w, in_b, out_w, out_b, w1, b1, w2, b2, n1w, n1b, n2w, n2b) = layer_params[l]
@@ -367,7 +376,8 @@ class FusionLevelFunction(torch.autograd.Function):
             dqkv = empty(M, 3 * Dp)
             ops.attn_bwd(qkv[:, :Dp], qkv[:, Dp:2 * Dp], qkv[:, 2 * Dp:], datt, lse, delta,
                          dqkv[:, :Dp], dqkv[:, Dp:2 * Dp], dqkv[:, 2 * Dp:], B=B, H=H, Sq=S, Sk=S, dp=dp, scale=scale,
-                         key_padding_mask=kpm, kpm_start=n, drop_p=pd_tok, drop_seed=seed, drop_stream=cfg.stream(l, SITE_ATTN))
+                         key_padding_mask=kpm, kpm_start=n, drop_p=pd_tok, drop_seed=seed, drop_stream=cfg.stream(l, SITE_ATTN),
+                         workspace=attn_ws)
             del datt
             # in_proj
             g_bin_p = zeros(3 * Dp); ops.colsum(dqkv, g_bin_p, M, 3 * Dp)

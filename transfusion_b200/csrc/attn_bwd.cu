@@ -38,7 +38,10 @@ constexpr int NB_LONG = 3, NB_SHORT = 2;
 constexpr int NB_EW_WARPS = 8;   // element-wise warps: two per TMEM lane quadrant, each owns 32 of the 64 streamed columns
 constexpr int NB_THREADS = 32 * (NB_EW_WARPS + 2);
 constexpr uint32_t NB_SW64 = 4;
-enum { MODE_DQ = 0, MODE_DK = 1, MODE_DV = 2 };
+// MODE_DKS = MODE_DK that also writes E = scale * dS^T and P_d^T / (1 - p) (bf16, [b, h, key, query]) to a caller-provided
+// workspace: dQ = E^T K and dV = P_d^T dO then run as two batched GEMMs on the GEMM kernel (5 GEMM units for the whole
+// backward instead of 8: S^T and dP^T are computed once)
+enum { MODE_DQ = 0, MODE_DK = 1, MODE_DV = 2, MODE_DKS = 3 };
 
 struct AttnBwd2Params {
   int B, H, Sq, Sk, dp, nch, r_tiles, n_stream;
@@ -51,6 +54,7 @@ struct AttnBwd2Params {
   __nv_bfloat16* out;
   long long ldo;
   float drop_p, drop_scale;
+  float pd_mul;   // MODE_DKS: P_d / (1 - p) = (P * scale) * pd_mul
   uint32_t drop_key, drop_thresh;
   long long* dbg;  // dev aid: clock64 stamps of CTA 0 (null in production)
 };
@@ -61,9 +65,11 @@ template <int MODE, bool DROP>
 __global__ void __launch_bounds__(NB_THREADS, 1)
 attn_bwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __grid_constant__ CUtensorMap tmap_r2,
                          const __grid_constant__ CUtensorMap tmap_t1, const __grid_constant__ CUtensorMap tmap_t2,
+                         const __grid_constant__ CUtensorMap tmap_s1, const __grid_constant__ CUtensorMap tmap_s2,
                          const __grid_constant__ AttnBwd2Params p) {
   constexpr bool ROWQ = MODE == MODE_DQ;   // resident rows are queries (else keys)
   constexpr bool HAS2 = MODE != MODE_DV;   // second score product C2 = R2 T2^T
+  constexpr bool STORE = MODE == MODE_DKS; // E and P_d^T also go to the workspace (tmap_s1 / tmap_s2), one 32 x 32 box per warp
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
@@ -75,6 +81,7 @@ attn_bwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gr
   sR2 = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sR2) + 1023) & ~uintptr_t(1023));
   uint8_t* sL = sR2 + r2_bytes;                            // long ring (tile also read MN-major by the accumulate MMA)
   uint8_t* sS = sL + NB_LONG * t_bytes;                    // short ring (tile only feeds a score MMA)
+  uint8_t* sBox = sS + NB_SHORT * t_bytes;                 // MODE_DKS: [8 warps][32 rows x 64 B] SWIZZLE_64B store boxes
   uint8_t* sStage = sL;                                    // R1 staging (SWIZZLE_128B, 64-column chunks) aliases the rings
   const int nck = (p.dp + 63) / 64;
 
@@ -99,6 +106,7 @@ attn_bwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gr
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_r1); tma_prefetch_desc(&tmap_r2);
     tma_prefetch_desc(&tmap_t1); tma_prefetch_desc(&tmap_t2);
+    if (STORE) { tma_prefetch_desc(&tmap_s1); tma_prefetch_desc(&tmap_s2); }
     mbar_init(R_FULL, 1);
     mbar_init(R1_COPIED, 1);
     for (int s = 0; s < NB_LONG; ++s) { mbar_init(L_FULL(s), 1); mbar_init(L_EMPTY(s), 1); }
@@ -290,6 +298,8 @@ attn_bwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gr
       if (lane == 0) mbar_arrive(C_EMPTY(cb));   // this warp's share of the score tile is in registers
       if (warp == 0 && lane == 0) NB_STAMP(1, i, 2);
       uint32_t pk[16];
+      uint32_t ppk[STORE ? 16 : 1];   // MODE_DKS: P_d^T / (1 - p) of the same elements
+      const float2 pdm_2 = make_float2(p.pd_mul, p.pd_mul);
 #pragma unroll
       for (int c = 0; c < 32; c += 4) {
         float4 st_l, st_d;
@@ -315,6 +325,10 @@ attn_bwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gr
             const float2 dpv = make_float2(k0 ? __uint_as_float(c2[cc]) : 0.f, k1 ? __uint_as_float(c2[cc + 1]) : 0.f);
             const float2 nd = ROWQ ? ndelta_2 : (h2 ? make_float2(-st_d.z, -st_d.w) : make_float2(-st_d.x, -st_d.y));
             e2 = __fmul2_rn(pr, __ffma2_rn(dpv, ds_2, nd));   // P * scale * (dP_dropped / (1 - p) - delta)
+            if constexpr (STORE) {
+              const float2 pd = __fmul2_rn(make_float2(k0 ? pr.x : 0.f, k1 ? pr.y : 0.f), pdm_2);
+              ppk[cc >> 1] = pack_bf16(pd.x, pd.y);
+            }
           }
           pk[cc >> 1] = pack_bf16(e2.x, e2.y);
         }
@@ -323,6 +337,10 @@ attn_bwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gr
 #pragma unroll
         for (int j = 0; j < 16; ++j)
           pk[j] &= (((bad >> (2 * j)) & 1u) ? 0u : 0x0000FFFFu) | (((bad >> (2 * j + 1)) & 1u) ? 0u : 0xFFFF0000u);
+      }
+      if constexpr (STORE) if (!row_valid) {   // padded / out-of-range key: its rows of E and P_d^T are exactly 0 (dQ and dV sum over them)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { pk[j] = 0u; ppk[j] = 0u; }
       }
       if (warp == 0 && lane == 0) NB_STAMP(1, i, 3);
       // acc_{i-1} has consumed the previous E (for i = 0 the wait on the fresh barrier's opposite parity passes at
@@ -336,7 +354,37 @@ attn_bwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gr
       __syncwarp();
       if (lane == 0) mbar_arrive(E_FULL);
       if (warp == 0 && lane == 0) NB_STAMP(1, i, 5);
+      if constexpr (STORE) if (t0 < p.Sq) {
+        // this warp's [32 keys x 32 queries] blocks of E and P_d^T -> workspace through one SWIZZLE_64B box (row-per-thread
+        // global stores would cost 32 LSU wavefronts per instruction).  Off the MMA critical path: E is already in TMEM.
+        const uint32_t box = smem_u32(sBox) + warp * 2048u;
+        const uint32_t row = box + lane * 64, sw = (lane >> 1) & 3;
+        const int key0 = r0 + quad * 32;
+        if (lane == 0) tma_store_wait_read<0>();   // the previous tile's second store has read the box (issued a tile ago)
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + ((j ^ sw) << 4)), "r"(pk[4 * j]), "r"(pk[4 * j + 1]), "r"(pk[4 * j + 2]), "r"(pk[4 * j + 3]) : "memory");
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_4d(&tmap_s1, box, t0, key0, 0, static_cast<int>(bh));
+          tma_store_commit();
+          tma_store_wait_read<0>();
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + ((j ^ sw) << 4)), "r"(ppk[4 * j]), "r"(ppk[4 * j + 1]), "r"(ppk[4 * j + 2]), "r"(ppk[4 * j + 3]) : "memory");
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_4d(&tmap_s2, box, t0, key0, 0, static_cast<int>(bh));
+          tma_store_commit();
+        }
+      }
     }
+    if (STORE && lane == 0) tma_store_wait_all<0>();   // workspace writes complete before the CTA retires
 
     // ---- epilogue: accumulator -> bf16 -> global (token-major, heads merged); the two warps of a quadrant
     //      alternate 32-column chunks
@@ -373,7 +421,8 @@ attn_bwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gr
 
 template <int MODE>
 static int launch_bwd2(bool drop, int grid, int smem_bytes, cudaStream_t stream, const CUtensorMap& r1, const CUtensorMap& r2,
-                       const CUtensorMap& t1, const CUtensorMap& t2, const AttnBwd2Params& p) {
+                       const CUtensorMap& t1, const CUtensorMap& t2, const CUtensorMap& s1, const CUtensorMap& s2,
+                       const AttnBwd2Params& p) {
   static DeviceOnce once;
   if (int rc = once.run([] {
         XF_CUDA(cudaFuncSetAttribute(attn_bwd2_tcgen05_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -381,14 +430,20 @@ static int launch_bwd2(bool drop, int grid, int smem_bytes, cudaStream_t stream,
         return 0;
       }))
     return rc;
-  if (drop) attn_bwd2_tcgen05_kernel<MODE, true><<<grid, NB_THREADS, smem_bytes, stream>>>(r1, r2, t1, t2, p);
-  else attn_bwd2_tcgen05_kernel<MODE, false><<<grid, NB_THREADS, smem_bytes, stream>>>(r1, r2, t1, t2, p);
+  if (drop) attn_bwd2_tcgen05_kernel<MODE, true><<<grid, NB_THREADS, smem_bytes, stream>>>(r1, r2, t1, t2, s1, s2, p);
+  else attn_bwd2_tcgen05_kernel<MODE, false><<<grid, NB_THREADS, smem_bytes, stream>>>(r1, r2, t1, t2, s1, s2, p);
   g_launches.fetch_add(1);
   XF_CUDA(cudaGetLastError());
   return 0;
 }
 
 }  // namespace xf
+
+extern "C" int64_t xf_attn_bwd_workspace_bytes(int B, int H, int Sq, int Sk) {
+  if (B <= 0 || H <= 0 || Sq <= 0 || Sk <= 0) return 0;
+  const int64_t pitch = ((Sq + 63) / 64) * 64;
+  return 2 * static_cast<int64_t>(B) * H * Sk * pitch * 2;   // E and P_d^T, bf16 [B, H, Sk, pitch]
+}
 
 extern "C" int xf_attn_bwd(const XfAttnBwd* a, xf_stream_t stream_) {
   using namespace xf;
@@ -432,21 +487,63 @@ extern "C" int xf_attn_bwd(const XfAttnBwd* a, xf_stream_t stream_) {
   const int smem2 = 1024 + 4096 + p.nch * 8192 + ring;   // align slack + control/stats + R2 + rings
   const int smem1 = 1024 + 4096 + ring;
   const int q_tiles = (a->Sq + NB_BM - 1) / NB_BM, k_tiles = (a->Sk + NB_BM - 1) / NB_BM;
+  CUtensorMap none;
+  memset(&none, 0, sizeof(none));
+
+  // ---- 5-unit path: one key-stationary pass (dK + E + P_d^T to the workspace), then dQ = E^T K and dV = P_d^T dO as
+  //      batched GEMMs over (sample, head)
+  const int64_t ws_need = xf_attn_bwd_workspace_bytes(a->B, a->H, a->Sq, a->Sk);
+  if (a->workspace && a->workspace_bytes >= ws_need) {
+    if (reinterpret_cast<uintptr_t>(a->workspace) & 15) return fail(-7, "xf_attn_bwd: workspace must be 16-byte aligned");
+    const int64_t pitch = ((a->Sq + 63) / 64) * 64;
+    __nv_bfloat16* ws_e = reinterpret_cast<__nv_bfloat16*>(a->workspace);
+    __nv_bfloat16* ws_p = ws_e + static_cast<int64_t>(a->B) * a->H * a->Sk * pitch;
+    CUtensorMap se, sp;
+    const uint64_t bh_n = static_cast<uint64_t>(a->B) * a->H;
+    if ((rc = make_tmap_4d_bf16(&se, ws_e, bh_n, 1, a->Sk, a->Sq, pitch, a->Sk * pitch, 0, 32, 32, 64))) return rc;
+    if ((rc = make_tmap_4d_bf16(&sp, ws_p, bh_n, 1, a->Sk, a->Sq, pitch, a->Sk * pitch, 0, 32, 32, 64))) return rc;
+    AttnBwd2Params pk = p;
+    pk.r_tiles = k_tiles; pk.n_stream = (a->Sq + NB_BN - 1) / NB_BN;
+    pk.out = reinterpret_cast<__nv_bfloat16*>(a->dk); pk.ldo = a->lddk;
+    pk.pd_mul = p.drop_scale / a->scale;
+    if ((rc = launch_bwd2<MODE_DKS>(drop, a->B * a->H * k_tiles, smem2 + NB_EW_WARPS * 2048, stream, k_stage, v_res, q64, do64, se, sp, pk)))
+      return rc;
+    XfGemm g;
+    memset(&g, 0, sizeof(g));
+    g.batch1 = a->B; g.batch2 = a->H;
+    g.a_bs1 = static_cast<int64_t>(a->H) * a->Sk * pitch; g.a_bs2 = a->Sk * pitch;
+    g.a_ld = pitch;
+    g.b_mn_major = 1;
+    g.b_bs2 = a->dp; g.out_bs2 = a->dp;
+    g.N = a->dp;
+    // dQ[b, q, h, :] = sum_k E[b, h, k, q] K[b, k, h, :]
+    g.a = ws_e; g.a_mn_major = 1;
+    g.b = a->k; g.b_ld = a->ldk; g.b_bs1 = static_cast<int64_t>(a->Sk) * a->ldk;
+    g.M = a->Sq; g.K = a->Sk;
+    g.out = a->dq; g.ldc = a->lddq; g.out_bs1 = static_cast<int64_t>(a->Sq) * a->lddq;
+    if ((rc = xf_gemm(&g, stream_))) return rc;
+    // dV[b, k, h, :] = sum_q P_d[b, h, k, q] dO[b, q, h, :]
+    g.a = ws_p; g.a_mn_major = 0;
+    g.b = a->d_out; g.b_ld = a->lddo; g.b_bs1 = static_cast<int64_t>(a->Sq) * a->lddo;
+    g.M = a->Sk; g.K = a->Sq;
+    g.out = a->dv; g.ldc = a->lddv; g.out_bs1 = static_cast<int64_t>(a->Sk) * a->lddv;
+    return xf_gemm(&g, stream_);
+  }
   {
     AttnBwd2Params pq = p;
     pq.r_tiles = q_tiles; pq.n_stream = (a->Sk + NB_BN - 1) / NB_BN;
     pq.out = reinterpret_cast<__nv_bfloat16*>(a->dq); pq.ldo = a->lddq;
-    if ((rc = launch_bwd2<MODE_DQ>(drop, a->B * a->H * q_tiles, smem2, stream, q_stage, do_res, k64, v64, pq))) return rc;
+    if ((rc = launch_bwd2<MODE_DQ>(drop, a->B * a->H * q_tiles, smem2, stream, q_stage, do_res, k64, v64, none, none, pq))) return rc;
   }
   {
     AttnBwd2Params pk = p;
     pk.r_tiles = k_tiles; pk.n_stream = (a->Sq + NB_BN - 1) / NB_BN;
     pk.out = reinterpret_cast<__nv_bfloat16*>(a->dk); pk.ldo = a->lddk;
     if (pk.dbg) pk.dbg += 2 * 64 * 8;
-    if ((rc = launch_bwd2<MODE_DK>(drop, a->B * a->H * k_tiles, smem2, stream, k_stage, v_res, q64, do64, pk))) return rc;
+    if ((rc = launch_bwd2<MODE_DK>(drop, a->B * a->H * k_tiles, smem2, stream, k_stage, v_res, q64, do64, none, none, pk))) return rc;
     pk.out = reinterpret_cast<__nv_bfloat16*>(a->dv); pk.ldo = a->lddv;
     if (pk.dbg) pk.dbg += 2 * 64 * 8;
-    if ((rc = launch_bwd2<MODE_DV>(drop, a->B * a->H * k_tiles, smem1, stream, k_stage, v_res, q64, do64, pk))) return rc;
+    if ((rc = launch_bwd2<MODE_DV>(drop, a->B * a->H * k_tiles, smem1, stream, k_stage, v_res, q64, do64, none, none, pk))) return rc;
   }
   return 0;
 }

@@ -38,6 +38,10 @@ struct GemmParams {
   int a_mn, b_mn;
   int num_m_tiles, num_n_tiles, split_k, kb_per_split, total_kb;
   int stages, b_bytes, stage_bytes;
+  // batching: items enumerate (batch, m-tile, k-split, n-tile); batch = b1 * nb2 + b2 addresses the operands through the
+  // two outer dimensions of 4-D tensor maps (A, B, out, aux) -- M, N, K are per batch entry
+  int batched, nb2, items_per_batch;
+  long long out_bs1, out_bs2;   // element offsets of the output per batch index (fp32 reduction epilogue)
   // epilogue
   const float* bias;
   const float* pos_table;
@@ -56,7 +60,14 @@ struct GemmParams {
   int drop_first;
 };
 
-__device__ __forceinline__ void decode_item(const GemmParams& p, int item, int& mt, int& nt, int& kb0, int& nkb) {
+__device__ __forceinline__ void decode_item(const GemmParams& p, int item, int& mt, int& nt, int& kb0, int& nkb, int& b1, int& b2) {
+  b1 = b2 = 0;
+  if (p.batched) {
+    const int batch = item / p.items_per_batch;
+    item -= batch * p.items_per_batch;
+    b1 = batch / p.nb2;
+    b2 = batch - b1 * p.nb2;
+  }
   nt = item % p.num_n_tiles;
   int r = item / p.num_n_tiles;
   int ks = r % p.split_k;
@@ -251,13 +262,19 @@ __device__ __forceinline__ void box_store_begin(int lane) {
   if (lane == 0) tma_store_wait_read<PENDING>();
   __syncwarp();
 }
-__device__ __forceinline__ void box_store_issue(const CUtensorMap* tmap, uint32_t box, int lane, int n0, int m0) {
+// bt < 0: 2-D tensor map; else 4-D (n, m, b2 = bt & 0xFFFF, b1 = bt >> 16)
+__device__ __forceinline__ void box_store_issue(const CUtensorMap* tmap, uint32_t box, int lane, int n0, int m0, int bt) {
   fence_proxy_async_smem();
   __syncwarp();
   if (lane == 0) {
-    tma_store_2d(tmap, box, n0, m0);
+    if (bt < 0) tma_store_2d(tmap, box, n0, m0);
+    else tma_store_4d(tmap, box, n0, m0, bt & 0xFFFF, bt >> 16);
     tma_store_commit();
   }
+}
+__device__ __forceinline__ void box_load_issue(const CUtensorMap* tmap, uint32_t box, uint32_t bar, int n0, int m0, int bt) {
+  if (bt < 0) tma_load_2d(box, tmap, bar, n0, m0);
+  else tma_load_4d(box, tmap, bar, n0, m0, bt & 0xFFFF, bt >> 16);
 }
 // dropout mask of row hash rh on 32 columns whose odd column hashes sit at shared address col_addr (no scaling)
 __device__ __forceinline__ void drop32(float2 (&v)[16], uint32_t rh, uint32_t col_addr, uint32_t t32) {
@@ -280,9 +297,10 @@ __device__ __forceinline__ void drop32(float2 (&v)[16], uint32_t rh, uint32_t co
 template <int EPI>
 __device__ __forceinline__ void epilogue_fast(const GemmParams& p, const CUtensorMap* tmap_out, const CUtensorMap* tmap_aux, int lane,
                                               int m0, int n0, const uint32_t (&acc)[32], const uint4 (&aux)[4], uint32_t box0,
-                                              uint32_t box1, uint32_t bias_addr, uint32_t col_addr, uint32_t rh) {
+                                              uint32_t box1, uint32_t bias_addr, uint32_t col_addr, uint32_t rh, int bt) {
   if constexpr (EPI == EPI_RED) {
     float* o = reinterpret_cast<float*>(p.out) + static_cast<long long>(m0 + lane) * p.ldc + n0;
+    if (bt >= 0) o += (bt >> 16) * p.out_bs1 + (bt & 0xFFFF) * p.out_bs2;
     if (m0 + lane < p.M) {
 #pragma unroll
       for (int i = 0; i < 32; i += 4)   // 128-bit vector reductions: 8 L2 transactions per chunk instead of 32
@@ -307,7 +325,7 @@ __device__ __forceinline__ void epilogue_fast(const GemmParams& p, const CUtenso
       if (p.preact_out) {
         box_store_begin<1>(lane);   // the output store of the previous chunk may still be reading box1
         box_store_row(box0, lane, v);
-        box_store_issue(tmap_aux, box0, lane, n0, m0);
+        box_store_issue(tmap_aux, box0, lane, n0, m0, bt);
       }
 #pragma unroll
       for (int i = 0; i < 16; ++i) v[i] = gelu2(v[i]);
@@ -342,7 +360,7 @@ __device__ __forceinline__ void epilogue_fast(const GemmParams& p, const CUtenso
       box_store_begin<0>(lane);
     }
     box_store_row(box1, lane, v);
-    box_store_issue(tmap_out, box1, lane, n0, m0);
+    box_store_issue(tmap_out, box1, lane, n0, m0, bt);
   }
 }
 
@@ -398,7 +416,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);   // warp-uniform for the compiler
 
-  const int num_items = p.num_m_tiles * p.num_n_tiles * p.split_k;   // m-tiles are 128*CG rows tall
+  const int num_items = p.num_m_tiles * p.num_n_tiles * p.split_k * (p.batched ? p.batched : 1);   // m-tiles are 128*CG rows tall
   const int first_item = blockIdx.x / CG, item_stride = gridDim.x / CG;
   const int cta_b_rows = p.tile_n / CG;                              // B rows (D columns) staged by this CTA
 
@@ -412,8 +430,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       int stage = 0;
       uint32_t phase = 0;
       for (int item = first_item; item < num_items; item += item_stride) {
-        int mt, nt, kb0, nkb;
-        decode_item(p, item, mt, nt, kb0, nkb);
+        int mt, nt, kb0, nkb, b1, b2;
+        decode_item(p, item, mt, nt, kb0, nkb, b1, b2);
         const int m0 = mt * GEMM_BM * CG + rank * GEMM_BM;
         const int n0 = nt * p.tile_n + rank * cta_b_rows;
         for (int kb = 0; kb < nkb; ++kb) {
@@ -423,7 +441,33 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           const uint32_t sb = sa + GEMM_A_BYTES;
           const uint32_t fb = full_bar(stage);
           if (leader) mbar_expect_tx(fb, CG * (GEMM_A_BYTES + p.b_bytes));
-          if (CG == 2) {
+          if (p.batched) {   // 4-D tensor maps: (column, row, b2, b1)
+            if (CG == 2) {
+              if (!p.a_mn) {
+                tma_load_4d_cg2(sa, &tmap_a, fb, k0, m0, b2, b1);
+              } else {
+                tma_load_4d_cg2(sa, &tmap_a, fb, m0, k0, b2, b1);
+                tma_load_4d_cg2(sa + 8192, &tmap_a, fb, m0 + 64, k0, b2, b1);
+              }
+              if (!p.b_mn) {
+                tma_load_4d_cg2(sb, &tmap_b, fb, k0, n0, b2, b1);
+              } else {
+                for (int c = 0; c * 64 < cta_b_rows; ++c) tma_load_4d_cg2(sb + c * 8192, &tmap_b, fb, n0 + c * 64, k0, b2, b1);
+              }
+            } else {
+              if (!p.a_mn) {
+                tma_load_4d(sa, &tmap_a, fb, k0, m0, b2, b1);
+              } else {
+                tma_load_4d(sa, &tmap_a, fb, m0, k0, b2, b1);
+                tma_load_4d(sa + 8192, &tmap_a, fb, m0 + 64, k0, b2, b1);
+              }
+              if (!p.b_mn) {
+                tma_load_4d(sb, &tmap_b, fb, k0, n0, b2, b1);
+              } else {
+                for (int c = 0; c * 64 < cta_b_rows; ++c) tma_load_4d(sb + c * 8192, &tmap_b, fb, n0 + c * 64, k0, b2, b1);
+              }
+            }
+          } else if (CG == 2) {
             if (!p.a_mn) {
               tma_load_2d_cg2(sa, &tmap_a, fb, k0, m0);
             } else {
@@ -467,8 +511,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int item = first_item; item < num_items; item += item_stride) {
-        int mt, nt, kb0, nkb;
-        decode_item(p, item, mt, nt, kb0, nkb);
+        int mt, nt, kb0, nkb, b1, b2;
+        decode_item(p, item, mt, nt, kb0, nkb, b1, b2);
         if (nkb == 0) continue;
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);
         tc_fence_after();
@@ -498,9 +542,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     int acc = 0;
     uint32_t acc_phase = 0, aux_phase = 0;
     for (int item = first_item; item < num_items; item += item_stride) {
-      int mt, nt, kb0, nkb;
-      decode_item(p, item, mt, nt, kb0, nkb);
+      int mt, nt, kb0, nkb, b1, b2;
+      decode_item(p, item, mt, nt, kb0, nkb, b1, b2);
       if (nkb == 0) continue;
+      const int bt = p.batched ? ((b1 << 16) | b2) : -1;   // batch coordinates of the 4-D output / operand boxes
       constexpr bool FAST = EPI != EPI_GENERIC;
       constexpr bool STAGED = EPI == EPI_LINEAR || EPI == EPI_GELU || EPI == EPI_DGELU;
       constexpr bool AUX_IN = EPI == EPI_LINEAR || EPI == EPI_DGELU;   // residual / saved pre-activation arrive by TMA
@@ -521,7 +566,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         if (p.drop_p > 0.f) rh = drop_rowhash(p.drop_seed, static_cast<uint64_t>(m));
         if (has_aux && lane == 0 && half * 32 < p.tile_n && nt * p.tile_n + half * 32 < p.N) {   // first chunk's operand box, before the MMAs finish
           mbar_expect_tx(aux_bar(warp), 2048);
-          tma_load_2d(box0, &tmap_aux, aux_bar(warp), nt * p.tile_n + half * 32, m0);
+          box_load_issue(&tmap_aux, box0, aux_bar(warp), nt * p.tile_n + half * 32, m0, bt);
         }
         asm volatile("bar.sync 1, %0;" ::"n"(32 * GEMM_EPI_WARPS) : "memory");
       }
@@ -542,7 +587,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           if (lane == 0 && cn < p.tile_n && nt * p.tile_n + cn < p.N) {
             fence_proxy_async_smem();
             mbar_expect_tx(aux_bar(warp), 2048);
-            tma_load_2d(box0, &tmap_aux, aux_bar(warp), nt * p.tile_n + cn, m0);
+            box_load_issue(&tmap_aux, box0, aux_bar(warp), nt * p.tile_n + cn, m0, bt);
           }
         }
         uint32_t r[32];
@@ -559,7 +604,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
         if (FAST) {
           if (live) epilogue_fast<EPI>(p, &tmap_out, &tmap_aux, lane, m0, n0, r, aux, box0, box1, smem_u32(s_bias + acc * 256 + c),
-                                       smem_u32(s_col + acc * 256 + c), rh);
+                                       smem_u32(s_col + acc * 256 + c), rh, bt);
         } else if (n0 < p.N) {
           epilogue_chunk(p, m, n0, r);
         }
@@ -638,6 +683,11 @@ extern "C" int xf_gemm(const XfGemm* g, xf_stream_t stream_) {
   if (g->accumulate && g->out_dtype != 1) return fail(-5, "xf_gemm: accumulate needs fp32 output");
   if (g->drop_p < 0.f || g->drop_p >= 1.f) return fail(-6, "xf_gemm: drop_p out of range");
 
+  const int nb1 = g->batch1 > 0 ? g->batch1 : 0, nb2 = g->batch2 > 0 ? g->batch2 : (nb1 > 0 ? 1 : 0);
+  const bool batched = nb1 > 0;
+  if (batched && (nb1 > 32767 || nb2 > 65535)) return fail(-9, "xf_gemm: batch counts out of range");
+  if (batched && split_k > 1) return fail(-9, "xf_gemm: batched GEMM does not combine with split_k");
+
   // CTA pairs (cta_group::2) unless disabled or the problem is a single small tile
   int cg = g->cta_group == 1 ? 1 : 2;
   if (g->cta_group == 0 && g->M <= 128) cg = 1;
@@ -656,6 +706,10 @@ extern "C" int xf_gemm(const XfGemm* g, xf_stream_t stream_) {
   p.kb_per_split = (p.total_kb + split_k - 1) / split_k;
   split_k = (p.total_kb + p.kb_per_split - 1) / p.kb_per_split;  // no empty splits
   p.split_k = split_k;
+  p.batched = batched ? nb1 * nb2 : 0;
+  p.nb2 = batched ? nb2 : 1;
+  p.items_per_batch = p.num_m_tiles * p.num_n_tiles * p.split_k;
+  p.out_bs1 = g->out_bs1; p.out_bs2 = g->out_bs2;
   const int cta_b_rows = tile_n / cg;
   p.b_bytes = p.b_mn ? ((cta_b_rows + 63) / 64) * 8192 : cta_b_rows * 128;   // per CTA
   p.stage_bytes = GEMM_A_BYTES + ((p.b_bytes + 1023) / 1024) * 1024;
@@ -691,12 +745,21 @@ extern "C" int xf_gemm(const XfGemm* g, xf_stream_t stream_) {
 
   CUtensorMap ta, tb;
   int rc;
-  if (!p.a_mn) rc = make_tmap_2d_bf16(&ta, g->a, p.M, p.K, g->a_ld, 64, 128);
-  else         rc = make_tmap_2d_bf16(&ta, g->a, p.K, p.M, g->a_ld, 64, 64);
-  if (rc) return rc;
-  if (!p.b_mn) rc = make_tmap_2d_bf16(&tb, g->b, p.N, p.K, g->b_ld, 64, cta_b_rows);
-  else         rc = make_tmap_2d_bf16(&tb, g->b, p.K, p.N, g->b_ld, 64, 64);
-  if (rc) return rc;
+  if (batched) {
+    if (!p.a_mn) rc = make_tmap_4d_bf16(&ta, g->a, nb1, nb2, p.M, p.K, g->a_ld, g->a_bs1, g->a_bs2, 64, 128);
+    else         rc = make_tmap_4d_bf16(&ta, g->a, nb1, nb2, p.K, p.M, g->a_ld, g->a_bs1, g->a_bs2, 64, 64);
+    if (rc) return rc;
+    if (!p.b_mn) rc = make_tmap_4d_bf16(&tb, g->b, nb1, nb2, p.N, p.K, g->b_ld, g->b_bs1, g->b_bs2, 64, cta_b_rows);
+    else         rc = make_tmap_4d_bf16(&tb, g->b, nb1, nb2, p.K, p.N, g->b_ld, g->b_bs1, g->b_bs2, 64, 64);
+    if (rc) return rc;
+  } else {
+    if (!p.a_mn) rc = make_tmap_2d_bf16(&ta, g->a, p.M, p.K, g->a_ld, 64, 128);
+    else         rc = make_tmap_2d_bf16(&ta, g->a, p.K, p.M, g->a_ld, 64, 64);
+    if (rc) return rc;
+    if (!p.b_mn) rc = make_tmap_2d_bf16(&tb, g->b, p.N, p.K, g->b_ld, 64, cta_b_rows);
+    else         rc = make_tmap_2d_bf16(&tb, g->b, p.K, p.N, g->b_ld, 64, 64);
+    if (rc) return rc;
+  }
 
   // epilogue kind: the specialised epilogues need full, 16-byte aligned 32-column chunks and no row remap
   // (a last chunk that sticks out of N is clipped by the TMA boxes; bias / hash staging stops at N)
@@ -715,14 +778,21 @@ extern "C" int xf_gemm(const XfGemm* g, xf_stream_t stream_) {
   CUtensorMap tc, td;
   memset(&tc, 0, sizeof(tc));
   memset(&td, 0, sizeof(td));
+  if (batched && epi == EPI_GENERIC)
+    return fail(-9, "xf_gemm: batched GEMM needs a specialised epilogue (no pos_table / row remap, N %% 8 == 0, aligned operands)");
   if (epi == EPI_LINEAR || epi == EPI_GELU || epi == EPI_DGELU) {
-    if ((rc = make_tmap_2d_bf16(&tc, g->out, p.M, p.N, g->ldc, 32, 32, 64))) return rc;
     const void* auxp = epi == EPI_GELU ? g->preact_out : epi == EPI_DGELU ? g->dact_in : g->residual;
     const long long auxld = epi == EPI_LINEAR ? g->ldr : g->ldc;
-    if (auxp && (rc = make_tmap_2d_bf16(&td, auxp, p.M, p.N, auxld, 32, 32, 64))) return rc;
+    if (batched) {   // aux operands share the output's batch strides
+      if ((rc = make_tmap_4d_bf16(&tc, g->out, nb1, nb2, p.M, p.N, g->ldc, g->out_bs1, g->out_bs2, 32, 32, 64))) return rc;
+      if (auxp && (rc = make_tmap_4d_bf16(&td, auxp, nb1, nb2, p.M, p.N, auxld, g->out_bs1, g->out_bs2, 32, 32, 64))) return rc;
+    } else {
+      if ((rc = make_tmap_2d_bf16(&tc, g->out, p.M, p.N, g->ldc, 32, 32, 64))) return rc;
+      if (auxp && (rc = make_tmap_2d_bf16(&td, auxp, p.M, p.N, auxld, 32, 32, 64))) return rc;
+    }
   }
   const int smem_bytes = 1024 /*align slack*/ + GEMM_CTRL_BYTES + GEMM_IO_BYTES + p.stages * p.stage_bytes;
-  const int items = p.num_m_tiles * p.num_n_tiles * p.split_k;
+  const int items = p.num_m_tiles * p.num_n_tiles * p.split_k * (batched ? nb1 * nb2 : 1);
   int sms = g->max_ctas > 0 ? g->max_ctas : sm_count();
   if (cg == 1) {
     int ctas = sms < items ? sms : items;

@@ -65,6 +65,32 @@ int make_tmap_3d_bf16(CUtensorMap* out, const void* ptr, uint64_t batch, uint64_
   return 0;
 }
 
+int make_tmap_4d_bf16(CUtensorMap* out, const void* ptr, uint64_t nb1, uint64_t nb2, uint64_t rows, uint64_t cols, uint64_t ld,
+                      uint64_t bs1, uint64_t bs2, uint32_t box_cols, uint32_t box_rows, int swizzle_bytes) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return fail(-10, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return fail(-11, "TMA base pointer not 16-byte aligned");
+  if (nb1 == 0) nb1 = 1;
+  if (nb2 == 0) nb2 = 1;
+  if (nb1 == 1 && bs1 == 0) bs1 = 8;   // a stride of an extent-1 dimension is never used but must be valid
+  if (nb2 == 1 && bs2 == 0) bs2 = 8;
+  if ((ld * 2) % 16 != 0 || (bs1 * 2) % 16 != 0 || (bs2 * 2) % 16 != 0)
+    return fail(-12, "TMA pitches (row %llu, batch %llu / %llu elements) must be multiples of 8 elements", (unsigned long long)ld,
+                (unsigned long long)bs1, (unsigned long long)bs2);
+  if ((swizzle_bytes > 0 && static_cast<int>(box_cols * 2) > swizzle_bytes) || box_cols > 256 || box_rows > 256)
+    return fail(-13, "bad TMA box %u x %u", box_cols, box_rows);
+  const CUtensorMapSwizzle swz = swizzle_bytes == 0 ? CU_TENSOR_MAP_SWIZZLE_NONE
+                               : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;
+  cuuint64_t gdim[4] = {cols, rows, nb2, nb1};
+  cuuint64_t gstr[3] = {ld * 2, bs2 * 2, bs1 * 2};
+  cuuint32_t box[4] = {box_cols, box_rows, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(-14, "cuTensorMapEncodeTiled(4d batched) failed: %d", (int)r);
+  return 0;
+}
+
 int make_tmap_chunks_bf16(CUtensorMap* out, const void* ptr, uint64_t batch, uint64_t rows, uint64_t cols, uint64_t ld,
                           uint32_t box_rows, uint32_t box_chunks) {
   EncodeTiledFn enc = get_encode_tiled();

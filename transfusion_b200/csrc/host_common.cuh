@@ -60,6 +60,12 @@ int make_tmap_rowblock_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, ui
 int make_tmap_chunks_bf16(CUtensorMap* out, const void* ptr, uint64_t batch, uint64_t rows, uint64_t cols, uint64_t ld,
                           uint32_t box_rows, uint32_t box_chunks);
 
+// Batched 4-D view (inner columns, rows, batch2, batch1) of bf16 matrices [rows, cols] that sit at element offsets
+// b1 * bs1 + b2 * bs2 from ptr (row pitch ld); box = box_cols x box_rows x 1 x 1.  Out-of-bounds rows / columns are
+// zero-filled on loads and clipped on stores PER BATCH ENTRY.  bs1, bs2, ld must be multiples of 8 elements.
+int make_tmap_4d_bf16(CUtensorMap* out, const void* ptr, uint64_t nb1, uint64_t nb2, uint64_t rows, uint64_t cols, uint64_t ld,
+                      uint64_t bs1, uint64_t bs2, uint32_t box_cols, uint32_t box_rows, int swizzle_bytes = 128);
+
 int sm_count();   // of the CURRENT device (cached per device)
 
 // Per-device one-time setup (cudaFuncSetAttribute is per device / context): runs f() the first time it is reached

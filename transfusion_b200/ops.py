@@ -64,7 +64,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
          act: int = 0, preact_out: Optional[torch.Tensor] = None, dact_in: Optional[torch.Tensor] = None,
          residual: Optional[torch.Tensor] = None, accumulate: bool = False, split_k: int = 1,
          tile_n: int = 0, drop_p: float = 0.0, drop_seed: int = 0, drop_stream: int = 0,
-         drop_first: bool = False, max_ctas: int = 0, cta_group: int = 0) -> torch.Tensor:
+         drop_first: bool = False, max_ctas: int = 0, cta_group: int = 0,
+         batch=None, a_ld: int = 0, b_ld: int = 0, ldc: int = 0) -> torch.Tensor:
     """out[M,N] (+)= A(MxK) @ B(NxK)^T with the fused epilogue of include/xfusion.h:XfGemm.
     a / b / out / residual are 2-D row-major (last stride 1); leading dims come from stride(0)."""
     _req(a, torch.bfloat16, "a")
@@ -103,10 +104,23 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     g.drop_p, g.drop_seed, g.drop_stream, g.drop_first = drop_p, drop_seed, drop_stream, int(drop_first)
     g.max_ctas = max_ctas
     g.cta_group = cta_group if cta_group else DEFAULT_CTA_GROUP
+    nbatch = 1
+    if batch is not None:
+        # batch = (n1, n2, (a_bs1, a_bs2), (b_bs1, b_bs2), (out_bs1, out_bs2)): element strides per batch index; a / b / out
+        # are then only base pointers and the leading dimensions come from a_ld / b_ld / ldc
+        g.batch1, g.batch2 = batch[0], batch[1]
+        (g.a_bs1, g.a_bs2), (g.b_bs1, g.b_bs2), (g.out_bs1, g.out_bs2) = batch[2], batch[3], batch[4]
+        nbatch = batch[0] * max(1, batch[1])
+    if a_ld:
+        g.a_ld = a_ld
+    if b_ld:
+        g.b_ld = b_ld
+    if ldc:
+        g.ldc = ldc
     fam = "gemm_wgrad" if a_mn_major else ("gemm_dgrad" if b_mn_major else "gemm_fwd")
     if PROFILE_DETAIL:
         fam += f"[M={M},N={N},K={K},split={split_k},act={act},drop={int(drop_p > 0)},res={int(residual is not None)}]"
-    with _Prof(fam, 2.0 * M * N * K):
+    with _Prof(fam, 2.0 * M * N * K * nbatch):
         check(lib().xf_gemm(C.byref(g), _stream()), "xf_gemm")
     return out
 
@@ -267,7 +281,9 @@ def attn_fwd(q, k, v, out, lse, *, B: int, H: int, Sq: int, Sk: int, dp: int, sc
 
 def attn_bwd(q, k, v, d_out, lse, delta, dq, dk, dv, *, B: int, H: int, Sq: int, Sk: int, dp: int, scale: float,
              key_padding_mask: Optional[torch.Tensor] = None, kpm_start: int = 0, drop_p: float = 0.0,
-             drop_seed: int = 0, drop_stream: int = 0, debug_timeline: Optional[torch.Tensor] = None):
+             drop_seed: int = 0, drop_stream: int = 0, debug_timeline: Optional[torch.Tensor] = None,
+             workspace: Optional[torch.Tensor] = None):
+    """workspace: optional uint8 scratch of attn_bwd_workspace_bytes(...) bytes -> 5-unit backward (include/xfusion.h)."""
     a = XfAttnBwd()
     a.q, a.ldq = q.data_ptr(), q.stride(0)
     a.k, a.ldk = k.data_ptr(), k.stride(0)
@@ -286,9 +302,15 @@ def attn_bwd(q, k, v, d_out, lse, delta, dq, dk, dv, *, B: int, H: int, Sq: int,
     a.B, a.H, a.Sq, a.Sk, a.dp = B, H, Sq, Sk, dp
     a.scale = scale
     a.drop_p, a.drop_seed, a.drop_stream = drop_p, drop_seed, drop_stream
+    if workspace is not None:
+        a.workspace, a.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
     d_true = 1.0 / (scale * scale)
     with _Prof("attn_bwd", 8.0 * B * H * Sq * Sk * d_true):
         check(lib().xf_attn_bwd(C.byref(a), _stream()), "xf_attn_bwd")
+
+
+def attn_bwd_workspace_bytes(B: int, H: int, Sq: int, Sk: int) -> int:
+    return int(lib().xf_attn_bwd_workspace_bytes(B, H, Sq, Sk))
 
 
 def rows_gather(src: torch.Tensor, dst: torch.Tensor, rows: int, D: int, in_map=(0, 0, 0), colsum: Optional[torch.Tensor] = None,
