@@ -235,9 +235,9 @@ typedef struct XfAttnBwd {
   float drop_p; uint32_t drop_seed, drop_stream;   /* must equal the forward's */
   void* debug_timeline;                            /* dev aid: NULL, or int64[2][2][64][8] device buffer of clock64 stamps */
   /* Optional scratch of >= xf_attn_bwd_workspace_bytes(B, H, Sq, Sk) bytes (16-byte aligned, contents undefined on
-   * entry and exit).  With it the backward computes the score tiles ONCE: a key-stationary tcgen05 pass produces dK and
-   * streams E = scale * dS^T and P_d^T / (1 - p) as bf16 [B, H, Sk, Sq] tiles to the scratch, and dQ = E^T K, dV = P_d^T dO
-   * run as two batched GEMMs (5 GEMM units in total, the algorithmic minimum).  Without it (NULL): three tcgen05
+   * entry and exit).  With it the backward computes the score tiles ONCE: a key-stationary tcgen05 pass produces dV and
+   * streams E = scale * dS^T as bf16 [B, H, Sk, Sq] tiles to the scratch, and dQ = E^T K, dK = E Q run as two batched
+   * GEMMs (5 GEMM units in total, the algorithmic minimum).  Without it (NULL): three tcgen05
    * passes that recompute the scores (8 units) and never leave the chip: no S x S bytes in HBM. */
   void* workspace; int64_t workspace_bytes;
 } XfAttnBwd;

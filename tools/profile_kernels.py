@@ -52,8 +52,11 @@ for it in range(2):
     delta = torch.empty(B, H, Sp, device=dev)
     ops.attn_delta(att, datt, delta, B, S, H, d)
     dqkv = torch.empty(M, 3 * D, device=dev, dtype=torch.bfloat16)
+    ws = None
+    if int(os.environ.get("XF_ATTN_BWD_WS", "1")):
+        ws = torch.empty(ops.attn_bwd_workspace_bytes(B, H, S, S), device=dev, dtype=torch.uint8)
     ops.attn_bwd(qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:], datt, lse, delta, dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:],
-                 key_padding_mask=kpm, **kw)
+                 key_padding_mask=kpm, workspace=ws, **kw)
     # HBM-bound
     y = torch.empty_like(x)
     mean, rstd = torch.empty(M, device=dev), torch.empty(M, device=dev)

@@ -331,7 +331,7 @@ class FusionLevelFunction(torch.autograd.Function):
         grads[base_tail + 2], grads[base_tail + 3] = g_wbp, g_bbp
         del dvis
 
-        # scratch of the 5-unit attention backward (E = scale dS^T and P_d^T as bf16 [B, H, S, S]); one buffer for all layers
+        # scratch of the 5-unit attention backward (E = scale dS^T as bf16 [B, H, S, S]); one buffer for all layers
         attn_ws = None
         if ATTN_BWD_WORKSPACE:
             attn_ws = torch.empty(ops.attn_bwd_workspace_bytes(B, H, S, S), device=dev, dtype=torch.uint8)

@@ -38,10 +38,11 @@ constexpr int NB_LONG = 3, NB_SHORT = 2;
 constexpr int NB_EW_WARPS = 8;   // element-wise warps: two per TMEM lane quadrant, each owns 32 of the 64 streamed columns
 constexpr int NB_THREADS = 32 * (NB_EW_WARPS + 2);
 constexpr uint32_t NB_SW64 = 4;
-// MODE_DKS = MODE_DK that also writes E = scale * dS^T and P_d^T / (1 - p) (bf16, [b, h, key, query]) to a caller-provided
-// workspace: dQ = E^T K and dV = P_d^T dO then run as two batched GEMMs on the GEMM kernel (5 GEMM units for the whole
-// backward instead of 8: S^T and dP^T are computed once)
-enum { MODE_DQ = 0, MODE_DK = 1, MODE_DV = 2, MODE_DKS = 3 };
+// MODE_DVS (5-unit backward): key-stationary, BOTH score products (C1 = K Q_i^T, C2 = V dO_i^T), accumulates
+//   dV += P_d^T dO_i  in TMEM and streams  E = scale * dS^T  (bf16, [b, h, key, query]) to a caller-provided workspace;
+//   dQ = E^T K and dK = E Q then run as two batched GEMMs on the GEMM kernel: S^T and dP^T are computed once
+//   (5 GEMM units for the whole backward instead of 8).  One [32 keys x 32 queries] TMA store box per warp and tile.
+enum { MODE_DQ = 0, MODE_DK = 1, MODE_DV = 2, MODE_DVS = 3 };
 
 struct AttnBwd2Params {
   int B, H, Sq, Sk, dp, nch, r_tiles, n_stream;
@@ -54,7 +55,7 @@ struct AttnBwd2Params {
   __nv_bfloat16* out;
   long long ldo;
   float drop_p, drop_scale;
-  float pd_mul;   // MODE_DKS: P_d / (1 - p) = (P * scale) * pd_mul
+  float pd_mul;   // MODE_DVS: P_d / (1 - p) = (P * scale) * pd_mul
   uint32_t drop_key, drop_thresh;
   long long* dbg;  // dev aid: clock64 stamps of CTA 0 (null in production)
 };
@@ -69,7 +70,8 @@ attn_bwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gr
                          const __grid_constant__ AttnBwd2Params p) {
   constexpr bool ROWQ = MODE == MODE_DQ;   // resident rows are queries (else keys)
   constexpr bool HAS2 = MODE != MODE_DV;   // second score product C2 = R2 T2^T
-  constexpr bool STORE = MODE == MODE_DKS; // E and P_d^T also go to the workspace (tmap_s1 / tmap_s2), one 32 x 32 box per warp
+  constexpr bool STORE = MODE == MODE_DVS; // E also goes to the workspace (tmap_s1), one 32 x 32 box per warp
+  constexpr bool ACC_T2 = MODE == MODE_DV || MODE == MODE_DVS;   // the accumulate MMA's B operand is T2 (dO_i): T2 lives in the long ring
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
@@ -81,7 +83,7 @@ attn_bwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gr
   sR2 = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(sR2) + 1023) & ~uintptr_t(1023));
   uint8_t* sL = sR2 + r2_bytes;                            // long ring (tile also read MN-major by the accumulate MMA)
   uint8_t* sS = sL + NB_LONG * t_bytes;                    // short ring (tile only feeds a score MMA)
-  uint8_t* sBox = sS + NB_SHORT * t_bytes;                 // MODE_DKS: [8 warps][32 rows x 64 B] SWIZZLE_64B store boxes
+  uint8_t* sBox = sS + NB_SHORT * t_bytes;                 // MODE_DVS: [8 warps][32 rows x 64 B] SWIZZLE_64B store boxes
   uint8_t* sStage = sL;                                    // R1 staging (SWIZZLE_128B, 64-column chunks) aliases the rings
   const int nck = (p.dp + 63) / 64;
 
@@ -106,7 +108,7 @@ attn_bwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gr
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap_r1); tma_prefetch_desc(&tmap_r2);
     tma_prefetch_desc(&tmap_t1); tma_prefetch_desc(&tmap_t2);
-    if (STORE) { tma_prefetch_desc(&tmap_s1); tma_prefetch_desc(&tmap_s2); }
+    if (STORE) tma_prefetch_desc(&tmap_s1);
     mbar_init(R_FULL, 1);
     mbar_init(R1_COPIED, 1);
     for (int s = 0; s < NB_LONG; ++s) { mbar_init(L_FULL(s), 1); mbar_init(L_EMPTY(s), 1); }
@@ -145,7 +147,7 @@ attn_bwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gr
         const int ls = i % NB_LONG, ss = i % NB_SHORT;
         const uint32_t lpar = ((i / NB_LONG) & 1) ^ 1, spar = ((i / NB_SHORT) & 1) ^ 1;
         const uint32_t la = smem_u32(sL + ls * t_bytes), sa = smem_u32(sS + ss * t_bytes);
-        if (MODE != MODE_DV) {   // T1 -> long ring (score + accumulate), T2 -> short ring (score only)
+        if (!ACC_T2) {   // T1 -> long ring (score + accumulate), T2 -> short ring (score only)
           // the short-ring slot is released first (after the score MMAs of tile i-2, one accumulate MMA earlier than
           // the long-ring slot of tile i-3), so its load is requested first
           mbar_wait(S_EMPTY(ss), spar);
@@ -154,7 +156,7 @@ attn_bwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gr
           mbar_wait(L_EMPTY(ls), lpar);
           mbar_expect_tx(L_FULL(ls), t_bytes);
           tma_load_4d(la, &tmap_t1, L_FULL(ls), 0, i * NB_BN, hd * p.nch, b);
-        } else {                 // T1 -> short ring (score only), T2 -> long ring (accumulate only)
+        } else {                 // T1 -> short ring (score only), T2 -> long ring (accumulate; MODE_DVS: score too)
           mbar_wait(S_EMPTY(ss), spar);
           mbar_expect_tx(S_FULL(ss), t_bytes);
           tma_load_4d(sa, &tmap_t1, S_FULL(ss), 0, i * NB_BN, hd * p.nch, b);
@@ -200,7 +202,7 @@ attn_bwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gr
         const int cb = HAS2 ? 0 : (i & 1);
         const int cuse = HAS2 ? i : (i >> 1);
         NB_STAMP(0, i, 0);
-        if (MODE != MODE_DV) mbar_wait(L_FULL(ls), (i / NB_LONG) & 1);
+        if (MODE != MODE_DV) mbar_wait(L_FULL(ls), (i / NB_LONG) & 1);   // a score product reads the long-ring tile
         NB_STAMP(0, i, 6);
         mbar_wait(S_FULL(ss), (i / NB_SHORT) & 1);
         NB_STAMP(0, i, 1);
@@ -208,8 +210,8 @@ attn_bwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gr
         NB_STAMP(0, i, 2);
         tc_fence_after();
         const uint32_t c1 = tm_c + (HAS2 ? 0 : cb * 64), c2 = tm_c + 64;
-        const uint32_t t1lo = lo_k + (MODE != MODE_DV ? l_base + ls * t_lo : s_base + ss * t_lo);
-        const uint32_t t2lo = lo_k + s_base + ss * t_lo;
+        const uint32_t t1lo = lo_k + (!ACC_T2 ? l_base + ls * t_lo : s_base + ss * t_lo);
+        const uint32_t t2lo = lo_k + (MODE == MODE_DVS ? l_base + ls * t_lo : s_base + ss * t_lo);
         for (int ch = 0; ch < p.nch; ++ch) {   // 32 head-dim columns (2 k-steps) per asm block
           umma_ts_k2(c1, tm_r1 + 16 * ch, hi_k, t1lo + ch * 256, 2, idesc_c, ch != 0);
           if (HAS2) umma_k2(c2, hi_k, r2lo + ch * 512, 2, hi_k, t2lo + ch * 256, 2, idesc_c, ch != 0);
@@ -298,7 +300,7 @@ attn_bwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gr
       if (lane == 0) mbar_arrive(C_EMPTY(cb));   // this warp's share of the score tile is in registers
       if (warp == 0 && lane == 0) NB_STAMP(1, i, 2);
       uint32_t pk[16];
-      uint32_t ppk[STORE ? 16 : 1];   // MODE_DKS: P_d^T / (1 - p) of the same elements
+      uint32_t ppk[STORE ? 16 : 1];   // MODE_DVS: P_d^T / (1 - p) of the same elements (the TMEM operand; pk = E goes to the workspace)
       const float2 pdm_2 = make_float2(p.pd_mul, p.pd_mul);
 #pragma unroll
       for (int c = 0; c < 32; c += 4) {
@@ -338,9 +340,9 @@ attn_bwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gr
         for (int j = 0; j < 16; ++j)
           pk[j] &= (((bad >> (2 * j)) & 1u) ? 0u : 0x0000FFFFu) | (((bad >> (2 * j + 1)) & 1u) ? 0u : 0xFFFF0000u);
       }
-      if constexpr (STORE) if (!row_valid) {   // padded / out-of-range key: its rows of E and P_d^T are exactly 0 (dQ and dV sum over them)
+      if constexpr (STORE) if (!row_valid) {   // padded / out-of-range key: its row of E is exactly 0 (dQ sums over it)
 #pragma unroll
-        for (int j = 0; j < 16; ++j) { pk[j] = 0u; ppk[j] = 0u; }
+        for (int j = 0; j < 16; ++j) pk[j] = 0u;
       }
       if (warp == 0 && lane == 0) NB_STAMP(1, i, 3);
       // acc_{i-1} has consumed the previous E (for i = 0 the wait on the fresh barrier's opposite parity passes at
@@ -348,19 +350,19 @@ attn_bwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gr
       mbar_wait(E_EMPTY, (i + 1) & 1);
       tc_fence_after();
       if (warp == 0 && lane == 0) NB_STAMP(1, i, 4);
-      tmem_st16(tm_e + lane_sel + 16 * half, pk);
+      if constexpr (STORE) tmem_st16(tm_e + lane_sel + 16 * half, ppk);
+      else tmem_st16(tm_e + lane_sel + 16 * half, pk);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(E_FULL);
       if (warp == 0 && lane == 0) NB_STAMP(1, i, 5);
       if constexpr (STORE) if (t0 < p.Sq) {
-        // this warp's [32 keys x 32 queries] blocks of E and P_d^T -> workspace through one SWIZZLE_64B box (row-per-thread
-        // global stores would cost 32 LSU wavefronts per instruction).  Off the MMA critical path: E is already in TMEM.
+        // this warp's [32 keys x 32 queries] block of E -> workspace through a SWIZZLE_64B box (row-per-thread global
+        // stores would cost 32 LSU wavefronts per instruction).  Off the MMA critical path: P_d^T is already in TMEM.
         const uint32_t box = smem_u32(sBox) + warp * 2048u;
         const uint32_t row = box + lane * 64, sw = (lane >> 1) & 3;
-        const int key0 = r0 + quad * 32;
-        if (lane == 0) tma_store_wait_read<0>();   // the previous tile's second store has read the box (issued a tile ago)
+        if (lane == 0) tma_store_wait_read<0>();   // the previous tile's store has read the box (issued a tile ago)
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < 4; ++j)
@@ -368,18 +370,7 @@ attn_bwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_r1, const __gr
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_4d(&tmap_s1, box, t0, key0, 0, static_cast<int>(bh));
-          tma_store_commit();
-          tma_store_wait_read<0>();
-        }
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + ((j ^ sw) << 4)), "r"(ppk[4 * j]), "r"(ppk[4 * j + 1]), "r"(ppk[4 * j + 2]), "r"(ppk[4 * j + 3]) : "memory");
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_4d(&tmap_s2, box, t0, key0, 0, static_cast<int>(bh));
+          tma_store_4d(&tmap_s1, box, t0, r0 + quad * 32, 0, static_cast<int>(bh));
           tma_store_commit();
         }
       }
@@ -442,7 +433,7 @@ static int launch_bwd2(bool drop, int grid, int smem_bytes, cudaStream_t stream,
 extern "C" int64_t xf_attn_bwd_workspace_bytes(int B, int H, int Sq, int Sk) {
   if (B <= 0 || H <= 0 || Sq <= 0 || Sk <= 0) return 0;
   const int64_t pitch = ((Sq + 63) / 64) * 64;
-  return 2 * static_cast<int64_t>(B) * H * Sk * pitch * 2;   // E and P_d^T, bf16 [B, H, Sk, pitch]
+  return static_cast<int64_t>(B) * H * Sk * pitch * 2;   // E = scale * dS^T, bf16 [B, H, Sk, pitch]
 }
 
 extern "C" int xf_attn_bwd(const XfAttnBwd* a, xf_stream_t stream_) {
@@ -490,43 +481,41 @@ extern "C" int xf_attn_bwd(const XfAttnBwd* a, xf_stream_t stream_) {
   CUtensorMap none;
   memset(&none, 0, sizeof(none));
 
-  // ---- 5-unit path: one key-stationary pass (dK + E + P_d^T to the workspace), then dQ = E^T K and dV = P_d^T dO as
-  //      batched GEMMs over (sample, head)
+  // ---- 5-unit path: one key-stationary pass (dV in TMEM, E = scale dS^T to the workspace), then dQ = E^T K and
+  //      dK = E Q as batched GEMMs over (sample, head)
   const int64_t ws_need = xf_attn_bwd_workspace_bytes(a->B, a->H, a->Sq, a->Sk);
   if (a->workspace && a->workspace_bytes >= ws_need) {
     if (reinterpret_cast<uintptr_t>(a->workspace) & 15) return fail(-7, "xf_attn_bwd: workspace must be 16-byte aligned");
     const int64_t pitch = ((a->Sq + 63) / 64) * 64;
     __nv_bfloat16* ws_e = reinterpret_cast<__nv_bfloat16*>(a->workspace);
-    __nv_bfloat16* ws_p = ws_e + static_cast<int64_t>(a->B) * a->H * a->Sk * pitch;
-    CUtensorMap se, sp;
+    CUtensorMap se;
     const uint64_t bh_n = static_cast<uint64_t>(a->B) * a->H;
     if ((rc = make_tmap_4d_bf16(&se, ws_e, bh_n, 1, a->Sk, a->Sq, pitch, a->Sk * pitch, 0, 32, 32, 64))) return rc;
-    if ((rc = make_tmap_4d_bf16(&sp, ws_p, bh_n, 1, a->Sk, a->Sq, pitch, a->Sk * pitch, 0, 32, 32, 64))) return rc;
     AttnBwd2Params pk = p;
     pk.r_tiles = k_tiles; pk.n_stream = (a->Sq + NB_BN - 1) / NB_BN;
-    pk.out = reinterpret_cast<__nv_bfloat16*>(a->dk); pk.ldo = a->lddk;
+    pk.out = reinterpret_cast<__nv_bfloat16*>(a->dv); pk.ldo = a->lddv;
     pk.pd_mul = p.drop_scale / a->scale;
-    if ((rc = launch_bwd2<MODE_DKS>(drop, a->B * a->H * k_tiles, smem2 + NB_EW_WARPS * 2048, stream, k_stage, v_res, q64, do64, se, sp, pk)))
+    if ((rc = launch_bwd2<MODE_DVS>(drop, a->B * a->H * k_tiles, smem2 + NB_EW_WARPS * 2048, stream, k_stage, v_res, q64, do64, se, none, pk)))
       return rc;
     XfGemm g;
     memset(&g, 0, sizeof(g));
     g.batch1 = a->B; g.batch2 = a->H;
+    g.a = ws_e; g.a_ld = pitch;
     g.a_bs1 = static_cast<int64_t>(a->H) * a->Sk * pitch; g.a_bs2 = a->Sk * pitch;
-    g.a_ld = pitch;
     g.b_mn_major = 1;
     g.b_bs2 = a->dp; g.out_bs2 = a->dp;
     g.N = a->dp;
-    // dQ[b, q, h, :] = sum_k E[b, h, k, q] K[b, k, h, :]
-    g.a = ws_e; g.a_mn_major = 1;
+    // dQ[b, q, h, :] = sum_k E[b, h, k, q] K[b, k, h, :]     (A stored [K][M])
+    g.a_mn_major = 1;
     g.b = a->k; g.b_ld = a->ldk; g.b_bs1 = static_cast<int64_t>(a->Sk) * a->ldk;
     g.M = a->Sq; g.K = a->Sk;
     g.out = a->dq; g.ldc = a->lddq; g.out_bs1 = static_cast<int64_t>(a->Sq) * a->lddq;
     if ((rc = xf_gemm(&g, stream_))) return rc;
-    // dV[b, k, h, :] = sum_q P_d[b, h, k, q] dO[b, q, h, :]
-    g.a = ws_p; g.a_mn_major = 0;
-    g.b = a->d_out; g.b_ld = a->lddo; g.b_bs1 = static_cast<int64_t>(a->Sq) * a->lddo;
+    // dK[b, k, h, :] = sum_q E[b, h, k, q] Q[b, q, h, :]     (A stored [M][K])
+    g.a_mn_major = 0;
+    g.b = a->q; g.b_ld = a->ldq; g.b_bs1 = static_cast<int64_t>(a->Sq) * a->ldq;
     g.M = a->Sk; g.K = a->Sq;
-    g.out = a->dv; g.ldc = a->lddv; g.out_bs1 = static_cast<int64_t>(a->Sk) * a->lddv;
+    g.out = a->dk; g.ldc = a->lddk; g.out_bs1 = static_cast<int64_t>(a->Sk) * a->lddk;
     return xf_gemm(&g, stream_);
   }
   {
