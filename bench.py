@@ -2,7 +2,10 @@
 """bench.py — cross_fusion fwd+bwd samples/sec on B200 (BASELINE.json metric).
 
     python bench.py --gpus 1 --steps 10 --warmup 3                 # this repo's CUDA path
-    python bench.py --impl reference --steps 2 --warmup 1          # CPU baseline arm (oracle port)
+    python bench.py --impl reference --steps 2 --warmup 1          # CPU arm: the UNMODIFIED reference module (oracle/_ref)
+    python bench.py --impl reference-gpu                           # reported only: the same reference module on this GPU (autocast bf16)
+    python bench.py --sweep                                        # BASELINE config 5: one line per (D, image, language length)
+    python bench.py --workload ego4dv1 | --mode infer | --feat-dtype bf16 | --accumulate 2
     torchrun --nproc-per-node N bench.py --gpus N ...              # one rank per GPU, NCCL
 
 A "step" = one pass of the hot path (all 4 FPN levels x 4 encoder layers, forward + backward) over
@@ -35,6 +38,7 @@ if ROOT not in sys.path:
 import torch
 
 METRIC = "cross_fusion fwd+bwd samples/sec"
+METRIC_INFER = "cross_fusion fwd (inference) samples/sec"
 UNIT = "samples/s"
 
 
@@ -123,21 +127,70 @@ def algorithmic_flops_fwd(workload: dict, L: int) -> float:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port (oracle/ref_math.py, torch fp32, all host threads).  The reference is
-# pure Python and cannot travel to the GPU box, so kind = "port" (its restatement is pinned to the
-# reference by tests/golden and tests/test_oracle_vs_reference.py).
+# Reference arm.  kind = "reference": the UNMODIFIED reference CrossFusionBoxWrapper, imported from /root/reference (build
+# container) or its byte-identical staged copy oracle/_ref (oracle/build_ref.py; travels to the GPU box), run through its
+# own forward / autograd with the yml's dropout in train mode, all host threads.  kind = "port" (only when neither tree
+# exists): oracle/ref_math.py, whose restatement is pinned to the reference by tests/golden.
 # ------------------------------------------------------------------------------------------------
-def cpu_oracle_step(workload_name: str, batch: int, L: int, seed: int = 0):
-    from oracle import ref_math
-    from transfusion_b200.configs import WORKLOADS
-    from transfusion_b200.harness import build_workload_module, synthetic_inputs
+def config_dict(args, w, B, L, world, train):
+    """`config` of the JSON line -- shared by both arms so the driver compares like with like."""
+    return {"workload": f"{args.workload} cross_fusion {'fwd+bwd' if train else 'fwd'}: 4 FPN levels x 4 layers, "
+                        f"D={w['token_dim']}, image {w['image'][0]}x{w['image'][1]}",
+            "per_gpu_batch": B, "global_batch": B * world, "lang_len": L,
+            "dropout": "off" if (args.no_dropout or not train) else "on (0.1/0.15/0.1)",
+            "feature_dtype": args.feat_dtype, "parallelism": f"dp{world}",
+            "l2": "inputs and activations (>1 GB per step) exceed the 126 MB L2; no explicit flush",
+            "visual_input_grad": False}
+
+
+def reference_step(workload_name: str, batch: int, L: int, device="cpu", autocast=False, train=True, dropout=True, seed: int = 0):
+    """One fwd(+bwd) step of the reference module on `device`.  Returns (step fn, kind)."""
+    from transfusion_b200.configs import WORKLOADS, level_shapes
+    from transfusion_b200.harness import synthetic_inputs
     w = WORKLOADS[workload_name]
-    m = build_workload_module(workload_name, device="cpu", dropout=False, seed=seed)
-    sd = {k: p.detach().clone().requires_grad_(True) for k, p in m.named_parameters()
-          if not k.startswith(("rcnn_model", "narr_pooling_layer"))}
     feats, lang, mask = synthetic_inputs(workload_name, batch, L, seed + 1)
     g = torch.Generator().manual_seed(seed + 2)
     cot = {k: torch.randn(v.shape, generator=g) for k, v in feats.items()}
+    kind = "port"
+    try:
+        from oracle import ref_loader
+        if ref_loader.reference_available():
+            cfg = ref_loader.build_fusion_cfg(w["token_dim"], n_levels=len(w["channels"]), num_layers=w["num_layers"],
+                                              num_heads=w["num_heads"], patch=w["patch"], dropout=1.0 if dropout else 0.0)
+            m = ref_loader.build_reference_module(cfg, level_shapes(w), w["channels"], seed=seed,
+                                                  noun_classes=w["noun_classes"], verb_classes=w["verb_classes"])
+            kind = "reference"
+    except Exception as e:   # fall back to the port, say so
+        print(f"[bench] reference module unavailable ({e}); timing the oracle port", file=sys.stderr)
+    if kind == "reference":
+        m = m.to(device)
+        m.train(train)
+        for k, p in m.named_parameters():
+            if k.endswith("heatmap_token"):
+                p.requires_grad_(False)
+        feats = {k: v.to(device) for k, v in feats.items()}
+        cot = {k: v.to(device) for k, v in cot.items()}
+        lang, mask = lang.to(device), mask.to(device)
+        keys = sorted(feats, key=int)
+
+        def step():
+            m.zero_grad(set_to_none=True)
+            m.rcnn_model.features = feats
+            with torch.autocast(device_type="cuda" if str(device).startswith("cuda") else "cpu", dtype=torch.bfloat16, enabled=autocast):
+                if train:
+                    out = m({"image": None, "language_f": (lang, mask)})["features"]
+                else:
+                    with torch.no_grad():
+                        out = m({"image": None, "language_f": (lang, mask)})["features"]
+            if train:
+                torch.autograd.backward([out[k] for k in keys], [cot[k].to(out[k].dtype) for k in keys])
+        return step, kind
+
+    from oracle import ref_math
+    from transfusion_b200.harness import build_workload_module
+    mm = build_workload_module(workload_name, device="cpu", dropout=False, seed=seed)
+    sd = {k: p.detach().clone().requires_grad_(True) for k, p in mm.named_parameters()
+          if not k.startswith(("rcnn_model", "narr_pooling_layer"))}
 
     def step():
         for v in sd.values():
@@ -145,13 +198,14 @@ def cpu_oracle_step(workload_name: str, batch: int, L: int, seed: int = 0):
         lg = lang.clone().requires_grad_(True)
         out, _ = ref_math.cross_fusion_forward(feats, lg, mask, sd, w["patch"], w["num_heads"], w["num_layers"])
         loss = sum((out[k] * cot[k]).sum() for k in out)
-        loss.backward()
-        return float(loss.detach())
-
-    return step
+        if train:
+            loss.backward()
+    return step, kind
 
 
 def run_reference_arm(args):
+    """CPU arm (`--impl reference`): rank 0 only.  Same `config` as our arm; every step is a BOUNDED sample of that workload
+    (cpu_baseline.sample says how many samples) sized so the whole --steps/--warmup run ends within a few minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -160,8 +214,17 @@ def run_reference_arm(args):
     from transfusion_b200.configs import WORKLOADS
     w = WORKLOADS[args.workload]
     L = args.lang_len or w["lang_len"]
+    train = args.mode == "train"
+    B = args.batch or (w["train_batch"] if train else w["eval_batch"])
+    world = max(1, args.gpus)
     bs = args.cpu_batch
-    step = cpu_oracle_step(args.workload, bs, L)
+    if bs <= 0:   # auto: probe one sample, then size the per-step sample for ~150 s of total CPU work
+        probe, _ = reference_step(args.workload, 1, L, train=train, dropout=not args.no_dropout)
+        probe()
+        t0 = time.perf_counter(); probe(); t1 = time.perf_counter() - t0
+        bs = max(1, min(B, int(150.0 / (max(1, args.steps + args.warmup) * t1))))
+        del probe
+    step, kind = reference_step(args.workload, bs, L, train=train, dropout=not args.no_dropout)
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -169,16 +232,80 @@ def run_reference_arm(args):
         step()
     dt = time.perf_counter() - t0
     val = bs * args.steps / dt
-    sample = f"{bs} sample(s)/step of the {args.workload} 4-level workload (L={L}), fwd+bwd, fp32, dropout p=0"
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload} cross_fusion fwd+bwd (CPU oracle port of the reference module)",
-                       "per_step_batch": bs, "lang_len": L},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+    what = "the UNMODIFIED reference CrossFusionBoxWrapper (oracle/_ref), its own forward + autograd" if kind == "reference" \
+        else "oracle/ref_math.py (port; reference tree not staged)"
+    sample = (f"{bs} sample(s)/step of the {args.workload} 4-level workload (L={L}), {'fwd+bwd' if train else 'fwd'}, fp32, "
+              f"{'dropout on' if (kind == 'reference' and not args.no_dropout and train) else 'dropout p=0'}; {what}")
+    line = {"impl": "reference", "metric": METRIC if train else METRIC_INFER, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(args, w, B, L, world, train),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def run_reference_gpu(args):
+    """`--impl reference-gpu` (REPORTED ONLY, BASELINE.md §4's same-box comparator): the unmodified reference module on this
+    GPU under torch.autocast(bf16), full per-GPU batch, CUDA-event timed.  It is ATen/cuBLAS/SDPA library code -- the bar
+    the hand-written path has to beat on the same silicon -- not part of the product."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from transfusion_b200.configs import WORKLOADS
+    w = WORKLOADS[args.workload]
+    L = args.lang_len or w["lang_len"]
+    train = args.mode == "train"
+    B = args.batch or (w["train_batch"] if train else w["eval_batch"])
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    step, kind = reference_step(args.workload, B, L, device=dev, autocast=True, train=train, dropout=not args.no_dropout)
+    if kind != "reference":
+        print(json.dumps({"impl": "reference-gpu", "unavailable": "reference tree not staged (oracle/_ref missing)"}), flush=True)
+        return
+    for _ in range(max(3, args.warmup)):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    val = B * args.steps / (ms / 1e3)
+    line = {"impl": "reference-gpu", "metric": METRIC if train else METRIC_INFER, "value": val, "unit": UNIT, "n_gpus": 1,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "dtype": "bf16 (torch.autocast)", "data": "synthetic", "config": config_dict(args, w, B, L, 1, train),
+            "note": "unmodified reference module, stock ATen/cuBLAS/SDPA kernels on the same B200; reported only",
+            "peak_mem_gb": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 2), "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def bind_numa(gpu_index: int):
+    """Pin this rank's threads to the CPUs of its GPU's NUMA node (sysfs) before the pinned input buffers of the end-to-end
+    pass are allocated (first touch then places them on that node).  Returns a short note for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(gpu_index)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()]
+        if node < 0 or len(nodes) < 2:
+            return f"single NUMA domain ({len(nodes)} node(s)); no binding"
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        os.sched_setaffinity(0, cpus & os.sched_getaffinity(0) or cpus)
+        return f"rank bound to NUMA node {node} ({len(cpus)} cpus)"
+    except Exception as e:
+        return f"no NUMA binding ({type(e).__name__})"
 
 
 # ------------------------------------------------------------------------------------------------
@@ -222,16 +349,36 @@ def run_ours(args):
     cot = {k: torch.randn(v.shape, device=dev, dtype=torch.float32, generator=gen) for k, v in feats_d.items()}
     keys = sorted(feats_d, key=int)
 
+    acc_n = max(1, args.accumulate)
+
+    def fwd_bwd(feats, lg, mk, micro, want_loss=False):
+        """One micro-step.  accumulate_grad_batches = N (ego_nao_res50_ego4dv2.yml:125): gradients are zeroed before the first
+        micro-step, accumulate in place (in the first micro-step's arenas) and are all-reduced on the N-th only, like
+        Lightning's DDP no_sync (run_experiment.py:444)."""
+        first, last = micro % acc_n == 0, micro % acc_n == acc_n - 1
+        if first:
+            net.zero_grad(set_to_none=True)
+        if reducer is not None:
+            reducer.active = last
+            if last:
+                reducer.reset()
+        out = net({"image": None, "language_f": (lg, mk)})["features"]
+        loss = None
+        if want_loss:
+            with torch.no_grad():   # loss = <out, cot>; its gradient w.r.t. out is cot itself
+                loss = sum(torch.dot(out[k].float().reshape(-1), cot[k].reshape(-1)) for k in keys)
+        torch.autograd.backward([out[k] for k in keys], [cot[k].to(out[k].dtype) for k in keys])
+        if reducer is not None and last:
+            reducer.finish()
+        return loss
+
+    res_state = {"i": 0}
+
     def step_resident():
         model.rcnn_model.features = feats_d
         if train:
-            net.zero_grad(set_to_none=True)
-            if reducer is not None:
-                reducer.reset()
-            out = net({"image": None, "language_f": (lang_d, mask_d)})["features"]
-            torch.autograd.backward([out[k] for k in keys], [cot[k].to(out[k].dtype) for k in keys])
-            if reducer is not None:
-                reducer.finish()
+            fwd_bwd(feats_d, lang_d, mask_d, res_state["i"])
+            res_state["i"] += 1
         else:
             with torch.no_grad():
                 net({"image": None, "language_f": (lang_d, mask_d)})
@@ -241,57 +388,65 @@ def run_ours(args):
     # back to pinned host memory.  One H2D of the full input set and one D2H per step are inside the timed region.
     # Nothing blocks the host on the step it just launched: the staging slot is fenced on the device (the copy
     # stream waits for the event of the compute that last read the slot) and the loss is consumed one step later.
-    copy_stream = torch.cuda.Stream(device=dev)
-    stage_bufs = [({k: torch.empty_like(v, device=dev) for k, v in feats_h.items()}, torch.empty_like(lang_h, device=dev),
-                   torch.empty_like(mask_h, device=dev)) for _ in range(2)]
-    stage_ev = [torch.cuda.Event(), torch.cuda.Event()]
-    done_ev = [None, None]        # compute that last read staging slot s has finished
-    loss_ev = [None, None]
-    loss_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
-    e2e_state = {"i": 0, "last": 0.0}
+    def build_e2e(feats_src):
+        """End-to-end step over the HOST buffers `feats_src` (pinned; fp32 or bf16 maps) + lang_h / mask_h."""
+        copy_stream = torch.cuda.Stream(device=dev)
+        stage_bufs = [({k: torch.empty_like(v, device=dev) for k, v in feats_src.items()}, torch.empty_like(lang_h, device=dev),
+                       torch.empty_like(mask_h, device=dev)) for _ in range(2)]
+        stage_ev = [torch.cuda.Event(), torch.cuda.Event()]
+        done_ev = [None, None]        # compute that last read staging slot s has finished
+        loss_ev = [None, None]
+        loss_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+        st = {"i": 0, "last": 0.0, "copies": []}
 
-    def prefetch(slot):
-        f, lg, mk = stage_bufs[slot]
-        if done_ev[slot] is not None:
-            copy_stream.wait_event(done_ev[slot])
-        with torch.cuda.stream(copy_stream):
-            for k in f:
-                f[k].copy_(feats_h[k], non_blocking=True)
-            lg.copy_(lang_h, non_blocking=True)
-            mk.copy_(mask_h, non_blocking=True)
-            stage_ev[slot].record(copy_stream)
+        def prefetch(slot):
+            f, lg, mk = stage_bufs[slot]
+            if done_ev[slot] is not None:
+                copy_stream.wait_event(done_ev[slot])
+            with torch.cuda.stream(copy_stream):
+                c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                c0.record(copy_stream)
+                for k in f:
+                    f[k].copy_(feats_src[k], non_blocking=True)
+                lg.copy_(lang_h, non_blocking=True)
+                mk.copy_(mask_h, non_blocking=True)
+                c1.record(copy_stream)
+                st["copies"].append((c0, c1))
+                stage_ev[slot].record(copy_stream)
 
-    def step_e2e():
-        i = e2e_state["i"]
-        e2e_state["i"] = i + 1
-        slot = i & 1
-        prefetch(slot ^ 1)                      # next step's inputs, overlapped with this step's compute
-        cur = torch.cuda.current_stream()
-        cur.wait_event(stage_ev[slot])
-        f, lg, mk = stage_bufs[slot]
-        model.rcnn_model.features = f
-        if train:
-            net.zero_grad(set_to_none=True)
-            if reducer is not None:
-                reducer.reset()
-            out = net({"image": None, "language_f": (lg, mk)})["features"]
-            with torch.no_grad():   # loss = <out, cot>; its gradient w.r.t. out is cot itself
-                loss = sum(torch.dot(out[k].float().reshape(-1), cot[k].reshape(-1)) for k in keys)
-            torch.autograd.backward([out[k] for k in keys], [cot[k].to(out[k].dtype) for k in keys])
-            if reducer is not None:
-                reducer.finish()
-        else:
-            with torch.no_grad():
-                out = net({"image": None, "language_f": (lg, mk)})["features"]
-                loss = sum(out[k].float().sum() for k in keys)
-        loss_host[slot].copy_(loss.reshape(1), non_blocking=True)   # device -> host read of the step's result
-        loss_ev[slot] = torch.cuda.Event()
-        loss_ev[slot].record(cur)
-        done_ev[slot] = loss_ev[slot]
-        if loss_ev[slot ^ 1] is not None:       # consume the previous step's loss (already on the host)
-            loss_ev[slot ^ 1].synchronize()
-            e2e_state["last"] = float(loss_host[slot ^ 1][0])
-        return e2e_state["last"]
+        def step():
+            i = st["i"]
+            st["i"] = i + 1
+            slot = i & 1
+            prefetch(slot ^ 1)                      # next step's inputs, overlapped with this step's compute
+            cur = torch.cuda.current_stream()
+            cur.wait_event(stage_ev[slot])
+            f, lg, mk = stage_bufs[slot]
+            model.rcnn_model.features = f
+            if train:
+                loss = fwd_bwd(f, lg, mk, i, want_loss=True)
+            else:
+                with torch.no_grad():
+                    out = net({"image": None, "language_f": (lg, mk)})["features"]
+                    loss = sum(out[k].float().sum() for k in keys)
+            loss_host[slot].copy_(loss.reshape(1), non_blocking=True)   # device -> host read of the step's result
+            loss_ev[slot] = torch.cuda.Event()
+            loss_ev[slot].record(cur)
+            done_ev[slot] = loss_ev[slot]
+            if loss_ev[slot ^ 1] is not None:       # consume the previous step's loss (already on the host)
+                loss_ev[slot ^ 1].synchronize()
+                st["last"] = float(loss_host[slot ^ 1][0])
+            return st["last"]
+
+        nbytes = sum(v.numel() * v.element_size() for v in feats_src.values()) + lang_h.numel() * 4 + mask_h.numel() * 8
+
+        def h2d_rate():
+            """median GB/s of this rank's per-step input copies (the last `steps` of them)"""
+            torch.cuda.synchronize()
+            ts = sorted(a.elapsed_time(b) for a, b in st["copies"][-args.steps:])
+            return round(nbytes / (ts[len(ts) // 2] * 1e-3) / 1e9, 1) if ts else None
+
+        return prefetch, step, nbytes, h2d_rate
 
     def barrier():
         if world > 1:
@@ -354,13 +509,29 @@ def run_ours(args):
     value = world * B * args.steps / (ms / 1e3)
 
     # ---- end-to-end: host (pinned) inputs in, scalar loss out, every step
+    numa_note = bind_numa(local_rank) if world > 1 or os.environ.get("XF_NUMA_BIND") else None
+    prefetch, step_e2e, h2d, h2d_rate = build_e2e(feats_h)
     prefetch(0)
     for _ in range(2):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
-    h2d = sum(v.numel() * v.element_size() for v in feats_h.values()) + lang_h.numel() * 4 + mask_h.numel() * 8
+    h2d_gbs = h2d_rate()
     d2h = 4
+    del prefetch, step_e2e
+    # the same end-to-end step fed bf16 feature maps (half the host bytes; the module accepts bf16 maps and Ego4Dv1 trains
+    # with precision 16): reported BESIDE the fp32 headline, never instead of it
+    e2e_bf16 = None
+    if args.feat_dtype == "f32" and not args.no_bf16_e2e:
+        feats_hb = {k: v.to(torch.bfloat16).pin_memory() for k, v in feats_h.items()}
+        prefetch_b, step_b, h2d_b, rate_b = build_e2e(feats_hb)
+        prefetch_b(0)
+        for _ in range(3):
+            step_b()
+        ms_b = timed(step_b, args.steps)
+        e2e_bf16 = {"value": world * B * args.steps / (ms_b / 1e3), "unit": UNIT, "ms_per_step": ms_b / args.steps,
+                    "h2d_bytes_per_step": int(h2d_b), "d2h_bytes_per_step": 4, "h2d_gbs_achieved": rate_b()}
+        del prefetch_b, step_b, feats_hb
 
     # ---- per-kernel roofline pass: CUDA events around every launch (rank 0, separate from the timed run)
     roofline, kernels = None, None
@@ -416,41 +587,114 @@ def run_ours(args):
         roofline["whole_path_tflops"] = round(value / world * step_flops / 1e12, 2)
         roofline["whole_path_frac"] = round(value / world * step_flops / 1e12 / peaks["tflops"], 4)
 
-    # ---- CPU baseline (rank 0, N = 1 only): oracle port on a bounded sample of the same workload
+    # ---- CPU baseline (rank 0, N = 1 only): the reference module (oracle/_ref) on a bounded sample of the same workload
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        stepc = cpu_oracle_step(args.workload, args.cpu_batch, L)
+        nb = max(1, args.cpu_batch)
+        stepc, kind = reference_step(args.workload, nb, L, train=train, dropout=not args.no_dropout)
+        stepc()   # warm-up (allocator, thread pool)
         t0 = time.perf_counter()
         stepc()
         dt = time.perf_counter() - t0
-        cpu_baseline = {"value": args.cpu_batch / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                        "sample": f"{args.cpu_batch} sample(s) of the {args.workload} 4-level workload (L={L}), one fwd+bwd, fp32, "
-                                  f"dropout p=0 ({dt:.1f} s)"}
+        cpu_baseline = {"value": nb / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+                        "sample": f"{nb} sample(s) of the {args.workload} 4-level workload (L={L}), one {'fwd+bwd' if train else 'fwd'} after "
+                                  f"one warm-up, fp32, {'the unmodified reference module (oracle/_ref), dropout on' if kind == 'reference' else 'oracle port, dropout p=0'} "
+                                  f"({dt:.1f} s)"}
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        line = {"metric": METRIC if train else METRIC_INFER, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(3, args.warmup),
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": f"{args.workload} cross_fusion {'fwd+bwd' if train else 'fwd'}: 4 FPN levels x 4 layers, "
-                                       f"D={w['token_dim']}, image {w['image'][0]}x{w['image'][1]}",
-                           "per_gpu_batch": B, "global_batch": B * world, "lang_len": L,
-                           "dropout": "off" if (args.no_dropout or not train) else "on (0.1/0.15/0.1)",
-                           "feature_dtype": args.feat_dtype, "parallelism": f"dp{world}",
-                           "l2": "inputs and activations (>1 GB per step) exceed the 126 MB L2; no explicit flush",
-                           "visual_input_grad": False,
-                           "level_streams": "independent FPN levels overlap on side streams in the timed runs; the `kernels` "
-                                            "breakdown is taken with the levels serialised"},
+                "config": config_dict(args, w, B, L, world, train),
+                "notes": {"level_streams": "independent FPN levels overlap on side streams in the timed runs; the `kernels` "
+                                           "breakdown is taken with the levels serialised",
+                          "accumulate_grad_batches": args.accumulate,
+                          "attn_bwd": "5-unit schedule (scores once; bf16 [B,H,S,S] scratch)" if os.environ.get("XF_ATTN_BWD_WS", "1") != "0"
+                                      else "3 on-chip passes (8 units)"},
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                        # achieved host->device rate of THIS rank's input copies (CUDA events on the copy stream, median
+                        # over the timed steps) and the rate the step needs to hide them completely
+                        "h2d_gbs_achieved": h2d_gbs, "h2d_gbs_needed_to_hide": round(h2d / (ms_per_step * 1e-3) / 1e9, 1),
+                        "numa": numa_note,
                         "pipeline": "pinned host inputs copied on a side stream one step ahead (2 device slots, fenced by "
                                     "events); each step's loss is copied to pinned host memory and read one step later"},
+                "e2e_bf16_features": e2e_bf16,
                 "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+SWEEP_IMAGES = [(480, 608), (544, 640), (640, 768), (704, 896), (768, 1024), (800, 1280)]   # ego_nao_res50_ego4d.yml:22-23, padded to 32
+SWEEP_LANG = [16, 32, 64, 128, 256, 512]
+
+
+def run_sweep(args):
+    """BASELINE config 5: language-context length x visual token grid x width, B = 16, fwd+bwd, dropout on, 1 GPU.
+    One JSON line per (workload width, image, L): device-timed samples/s and the whole-path tensor fraction."""
+    import copy
+    from transfusion_b200.configs import WORKLOADS, level_shapes
+    from transfusion_b200.harness import build_workload_module
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    peaks = load_peaks()
+    B = args.batch or 16
+    for name in ("ego4dv2", "ego4dv1"):
+        model = build_workload_module(name, device=dev, dropout=not args.no_dropout, seed=0)
+        model.train(True)
+        for k, p in model.named_parameters():
+            if k.endswith("heatmap_token"):
+                p.requires_grad_(False)
+        for image in SWEEP_IMAGES:
+            w = copy.deepcopy(WORKLOADS[name])
+            w["image"] = image
+            g = torch.Generator(device=dev).manual_seed(7)
+            feats = {str(i): torch.relu(torch.randn(B, c, h, ww, device=dev, generator=g))
+                     for i, ((h, ww), c) in enumerate(zip(level_shapes(w), w["channels"]))}
+            cot = {k: torch.randn(v.shape, device=dev, generator=g) for k, v in feats.items()}
+            keys = sorted(feats, key=int)
+            for L in SWEEP_LANG:
+                lang = 0.5 * torch.randn(B, L, w["token_dim"], device=dev, generator=g)
+                lens = torch.randint(L // 2, L + 1, (B,), device=dev, generator=g)
+                lens[0] = L
+                mask = (torch.arange(L, device=dev)[None, :] < lens[:, None]).to(torch.int64)
+
+                def step():
+                    model.rcnn_model.features = feats
+                    model.zero_grad(set_to_none=True)
+                    out = model({"image": None, "language_f": (lang, mask)})["features"]
+                    torch.autograd.backward([out[k] for k in keys], [cot[k] for k in keys])
+
+                for _ in range(max(2, min(args.warmup, 3))):
+                    step()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                steps = max(3, min(args.steps, 5))
+                e0.record()
+                for _ in range(steps):
+                    step()
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / steps
+                f_fwd = algorithmic_flops_fwd(w, L)
+                pe_dgrad = sum(2.0 * ((h // p) * (ww // p)) * (C * p * p) * w["token_dim"]
+                               for (h, ww), C, p in zip(level_shapes(w), w["channels"], w["patch"]))
+                tf = B / (ms * 1e-3) * (3.0 * f_fwd - pe_dgrad) / 1e12
+                grids = [((h // p), (ww // p)) for (h, ww), p in zip(level_shapes(w), w["patch"])]
+                print(json.dumps({"metric": METRIC, "value": round(B / (ms * 1e-3), 2), "unit": UNIT, "n_gpus": 1, "ms_per_step": round(ms, 3),
+                                  "steps": steps, "dtype": "bf16", "data": "synthetic",
+                                  "config": {"workload": f"sweep: {name} width D={w['token_dim']}, image {image[0]}x{image[1]}, L={L}",
+                                             "per_gpu_batch": B, "lang_len": L, "token_grids": grids,
+                                             "dropout": "off" if args.no_dropout else "on (0.1/0.15/0.1)"},
+                                  "whole_path_tflops": round(tf, 1), "whole_path_frac": round(tf / peaks["tflops"], 4)}), flush=True)
+            del feats, cot
+        del model
+        torch.cuda.empty_cache()
 
 
 def main():
@@ -458,7 +702,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
     ap.add_argument("--workload", default="ego4dv2", choices=["ego4dv2", "ego4dv1"])
     ap.add_argument("--mode", default="train", choices=["train", "infer"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the reference's per-GPU batch)")
@@ -466,10 +710,18 @@ def main():
     ap.add_argument("--feat-dtype", default="f32", choices=["f32", "bf16"])
     ap.add_argument("--no-dropout", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-batch", type=int, default=1)
+    ap.add_argument("--cpu-batch", type=int, default=0,
+                    help="samples per CPU step; 0 = auto (1 for the in-line cpu_baseline, sized for ~150 s total in --impl reference)")
+    ap.add_argument("--accumulate", type=int, default=1, help="accumulate_grad_batches: all-reduce every N-th micro-step")
+    ap.add_argument("--no-bf16-e2e", action="store_true", help="skip the extra end-to-end pass with bf16 feature maps")
+    ap.add_argument("--sweep", action="store_true", help="BASELINE config 5: language length x image size x width, B = 16")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.sweep:
+        run_sweep(args)
+    elif args.impl == "reference":
         run_reference_arm(args)
+    elif args.impl == "reference-gpu":
+        run_reference_gpu(args)
     else:
         run_ours(args)
 

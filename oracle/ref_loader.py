@@ -1,6 +1,7 @@
 """TEST INFRASTRUCTURE ONLY — loads the *unmodified* reference hot path in-process.
 
-Works only where ``/root/reference`` exists (the build container).  It is used to
+Works where ``/root/reference`` exists (the build container) or where its byte-identical staged copy
+``oracle/_ref`` (oracle/build_ref.py; git-ignored, travels with the gpurun snapshot) does.  It is used to
  (1) pin ``oracle/ref_math.py`` (tests/test_oracle_vs_reference.py, skipped elsewhere) and
  (2) generate the committed golden fixtures (oracle/make_golden.py).
 
@@ -23,8 +24,23 @@ import types
 import torch
 from torch import nn
 
-REFERENCE_ROOT = os.environ.get("XF_REFERENCE_ROOT", "/root/reference")
 FUSION_YAML = "modeling/cross_fusion/ego_fusion/cross_fusion_config_sym_ego_res50.yml"
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")   # oracle/build_ref.py (unmodified copies)
+
+
+def _pick_root() -> str:
+    """The reference tree itself where it exists (build container), else the byte-identical staged copy oracle/_ref
+    (git-ignored; travels to the GPU box), else the path that will fail ``reference_available()``."""
+    env = os.environ.get("XF_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", _STAGED):
+        if os.path.isfile(os.path.join(cand, FUSION_YAML)):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _pick_root()
 
 
 def reference_available() -> bool:

@@ -424,9 +424,11 @@ class FusionLevelFunction(torch.autograd.Function):
                 out_grads.append(g.view_as(prm) if g.shape != prm.shape else g)
         # every parameter gradient of the level lives in the arena: a data-parallel reducer can all-reduce that one
         # buffer in place (parallel.BucketedGradAllReduce) instead of flattening ~70 tensors
+        # With gradient accumulation (a .grad already exists) autograd adds this backward's gradients IN PLACE into the first
+        # micro-step's arena views, so that first arena stays the one to reduce: only a fresh .grad adopts the new arena.
         if arena["buf"] is not None:
             used = arena["buf"][:arena["off"]]
             for prm in params:
-                if prm is not None and prm.requires_grad:
+                if prm is not None and prm.requires_grad and (prm.grad is None or getattr(prm, "_xf_grad_arena", None) is None):
                     prm._xf_grad_arena = used
         return (None, d_feat, d_lang, None, *out_grads)

@@ -33,6 +33,8 @@ class BucketedGradAllReduce:
         self.pending = [0] * len(self.buckets)
         self.works = []
         self._handles = []
+        # False = accumulate only (DDP no_sync: the non-final micro-steps of accumulate_grad_batches, run_experiment.py:444)
+        self.active = True
         for bi, bucket in enumerate(self.buckets):
             for p in bucket:
                 self._handles.append(p.register_post_accumulate_grad_hook(self._make_hook(bi)))
@@ -47,6 +49,8 @@ class BucketedGradAllReduce:
 
     def _make_hook(self, bi):
         def hook(param):
+            if not self.active:
+                return
             self.pending[bi] -= 1
             if self.pending[bi] == 0:
                 self._launch(bi)
