@@ -251,6 +251,32 @@ int xf_rows_gather(const void* in_bf16, int64_t ldi, void* out_bf16, int64_t ldo
                    float* colsum, float drop_p, uint32_t drop_seed, uint32_t drop_stream, xf_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Fused optimizer step over the path's parameters: global-norm clipping (Lightning gradient_clip_val,
+ * runner/run_experiment.py:445-446 -> torch clip_grad_norm_) + RAdam (runner/metrics_losses/radam_optim.py:30-104) +
+ * the bf16 weight copy of the next forward, one HBM pass.  Up to XF_OPT_MAX_JOBS tensors per call; all fp32 pointers
+ * 16-byte aligned.  xf_grad_sqnorm ADDS sum(grad^2) over the jobs to *out (zero it first; add the squared norm of any
+ * gradient outside this path before the step so the clip is global).  xf_radam_step: the moments are always updated;
+ * the parameter moves per radam_optim.py:89-102 (N_sma >= 5: adaptive; else SGD-like iff degenerated_to_sgd; else not
+ * at all) with gradients pre-scaled by min(1, max_grad_norm / (sqrt(*grad_sqnorm) + 1e-6)) when max_grad_norm > 0.
+ * Gradients themselves are NOT rewritten (clip_grad_norm_ scales them in place; nothing on this path reads them again).
+ * ------------------------------------------------------------------------------------------ */
+#define XF_OPT_MAX_JOBS 32
+typedef struct XfRAdamJob {
+  float* param; const float* grad; float* exp_avg; float* exp_avg_sq;
+  void* param_bf16;      /* optional: bf16 copy of the updated parameter (same flat indexing), or NULL */
+  int64_t n;
+} XfRAdamJob;
+typedef struct XfRAdam {
+  float lr, beta1, beta2, eps, weight_decay;
+  int32_t degenerated_to_sgd;
+  int64_t step;                 /* 1-based step count of these tensors (state["step"] after the increment, :65) */
+  float max_grad_norm;          /* <= 0: no clipping */
+  const float* grad_sqnorm;     /* device scalar (see xf_grad_sqnorm), or NULL */
+} XfRAdam;
+int xf_grad_sqnorm(const XfRAdamJob* jobs, int n_jobs, float* out, xf_stream_t stream);
+int xf_radam_step(const XfRAdamJob* jobs, int n_jobs, const XfRAdam* a, xf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Test aids (not on the hot path): materialise the counter-based dropout keep masks that the kernels above
  * recompute on the fly, so a CPU checker can replay a train-mode step with the SAME masks (the reference draws
  * its masks from torch's RNG inside F.dropout: cross_f_box_layers.py:74, torch18_adapters.py:109-112,796-797,

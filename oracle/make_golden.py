@@ -169,3 +169,48 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Optimizer golden: the UNMODIFIED reference RAdam (runner/metrics_losses/radam_optim.py) preceded by
+# torch.nn.utils.clip_grad_norm_ (what Lightning's gradient_clip_val does), 8 steps so that the rectification threshold
+# N_sma >= 5 is crossed (steps 1-5 leave the parameters untouched, radam_optim.py:86-87,98), ragged tensor sizes.
+def run_radam_golden(name="radam8"):
+    import sys
+    if ref_loader.REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, ref_loader.REFERENCE_ROOT)
+    from runner.metrics_losses.radam_optim import RAdam
+    g = torch.Generator().manual_seed(91)
+    shapes = [(37, 16), (64,), (5, 3, 7), (1, 1, 33)]
+    params = [torch.nn.Parameter(torch.randn(s, generator=g)) for s in shapes]
+    extra = torch.nn.Parameter(torch.randn(50, generator=g))   # clipped together with `params`, stepped by another optimizer
+    p0 = [p.detach().clone() for p in params]
+    lr, wd, max_norm, steps = 2e-4, 1e-4, 4.0, 8                # ego_nao_res50_ego4dv2.yml:129,159,161
+    opt = RAdam(params, lr=lr, weight_decay=wd)
+    blob = {"meta.lr": np.array(lr), "meta.wd": np.array(wd), "meta.max_norm": np.array(max_norm), "meta.steps": np.array(steps)}
+    for t in range(steps):
+        scale = 6.0 if t % 2 == 0 else 0.3   # some steps clip (norm > 4), some do not
+        for i, p in enumerate(params):
+            p.grad = scale * torch.randn(p.shape, generator=g)
+            blob[f"grad.{t}.{i}"] = p.grad.numpy().copy()
+        extra.grad = scale * torch.randn(extra.shape, generator=g)
+        blob[f"extra_sqnorm.{t}"] = np.array(float(extra.grad.double().pow(2).sum()))
+        torch.nn.utils.clip_grad_norm_(params + [extra], max_norm)
+        opt.step()
+        if t in (4, 5):   # around the N_sma threshold
+            for i, p in enumerate(params):
+                blob[f"p_after{t + 1}.{i}"] = p.detach().numpy().copy()
+    for i, p in enumerate(params):
+        blob[f"p0.{i}"] = p0[i].numpy()
+        blob[f"p.{i}"] = p.detach().numpy().copy()
+        blob[f"m.{i}"] = opt.state[p]["exp_avg"].numpy().copy()
+        blob[f"v.{i}"] = opt.state[p]["exp_avg_sq"].numpy().copy()
+    path = os.path.join(GOLDEN_DIR, name + ".npz")
+    np.savez_compressed(path, **blob)
+    print(f"{name}: wrote {path} ({os.path.getsize(path) / 1e3:.1f} kB)")
+
+
+if __name__ == "__main__":
+    import sys as _sys
+    if not _sys.argv[1:] or "radam8" in _sys.argv[1:]:
+        run_radam_golden()

@@ -46,6 +46,24 @@ class XfCastJob(C.Structure):
 
 
 XF_CAST_MAX_JOBS = 32
+XF_OPT_MAX_JOBS = 32
+
+
+class XfRAdamJob(C.Structure):
+    _fields_ = [
+        ("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+        ("param_bf16", C.c_void_p), ("n", C.c_int64),
+    ]
+
+
+class XfRAdam(C.Structure):
+    _fields_ = [
+        ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float),
+        ("degenerated_to_sgd", C.c_int32),
+        ("step", C.c_int64),
+        ("max_grad_norm", C.c_float),
+        ("grad_sqnorm", C.c_void_p),
+    ]
 
 
 class XfLayerNorm(C.Structure):
@@ -147,6 +165,7 @@ EXPORTS = [
     "xf_layernorm_fwd", "xf_layernorm_bwd", "xf_colsum", "xf_cast_pad", "xf_cast_pad_multi", "xf_unpad_add",
     "xf_attn_delta", "xf_attn_fwd", "xf_attn_bwd", "xf_attn_bwd_workspace_bytes", "xf_rows_gather",
     "xf_lm_pool_fwd", "xf_lm_pool_bwd", "xf_rowln_fwd", "xf_rowln_bwd", "xf_small_linear_fwd", "xf_small_linear_bwd",
+    "xf_grad_sqnorm", "xf_radam_step",
     "xf_debug_dropout_mask", "xf_debug_attn_dropout_mask",
 ]
 

@@ -114,6 +114,19 @@ class CrossFusionBoxWrapper(nn.Module):
         return nn.Conv2d(in_channels=in_channels, out_channels=token_dim, kernel_size=(patch_h, patch_w),
                          stride=(patch_h, patch_w), bias=False)
 
+    # ---- cached bf16 weight copies (cross_fusion/level_fn.py) ---------------------------------
+    def invalidate_weight_cache(self):
+        """Drops the cached bf16 weight copies; call after modifying parameters behind autograd's back (`p.data.<op>_()`)
+        between two inference calls.  train() / eval() switches do it automatically."""
+        for p in self.parameters():
+            if hasattr(p, "_xf_bf16"):
+                del p._xf_bf16
+
+    def train(self, mode: bool = True):
+        if mode != self.training:
+            self.invalidate_weight_cache()
+        return super().train(mode)
+
     # ---- the hot path -----------------------------------------------------------------------
     def run_level(self, i: int, feat: torch.Tensor, language_f: torch.Tensor, lang_pad_mask, need_lang_out=False, out_stream=None):
         """One FPN level: reference :180-212.  Returns (fused [B,C,h,w], fused language tokens or None)."""
