@@ -267,7 +267,10 @@ typedef struct XfRAdamJob {
   int64_t n;
 } XfRAdamJob;
 typedef struct XfRAdam {
-  float lr, beta1, beta2, eps, weight_decay;
+  /* doubles: the reference evaluates its scalar coefficients (1 - beta, weight_decay * lr, step_size * lr, N_sma) with
+   * Python floats before they meet an fp32 tensor; doing that arithmetic in fp32 is 5e-5 off (1.f - 0.999f) */
+  double lr_d, beta1_d, beta2_d, weight_decay_d;
+  float eps;
   int32_t degenerated_to_sgd;
   int64_t step;                 /* 1-based step count of these tensors (state["step"] after the increment, :65) */
   float max_grad_norm;          /* <= 0: no clipping */

@@ -58,7 +58,8 @@ class XfRAdamJob(C.Structure):
 
 class XfRAdam(C.Structure):
     _fields_ = [
-        ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float),
+        ("lr_d", C.c_double), ("beta1_d", C.c_double), ("beta2_d", C.c_double), ("weight_decay_d", C.c_double),
+        ("eps", C.c_float),
         ("degenerated_to_sgd", C.c_int32),
         ("step", C.c_int64),
         ("max_grad_norm", C.c_float),

@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(256) grad_sqnorm_multi_kernel(const __grid_con
 
 struct RAdamScalars {
   float beta1, beta2, eps;
+  float omb1, omb2;  // 1 - beta, evaluated in double on the host like the reference's Python floats (1.f - 0.999f is 4.7e-5 off)
   float decay;       // 1 - weight_decay * lr  (p <- p * decay before the step; 1 when weight_decay = 0)
   float step_lr;     // step_size * lr
   int mode;          // 0: moments only (N_sma < 5 and not degenerated_to_sgd), 1: adaptive step, 2: SGD-like step
@@ -65,8 +66,8 @@ struct RAdamScalars {
 
 __device__ __forceinline__ void radam_elem(float& p, float g, float& m, float& v, const RAdamScalars& h, float coef) {
   g *= coef;
-  v = h.beta2 * v + (1.f - h.beta2) * g * g;     // radam_optim.py:62
-  m = h.beta1 * m + (1.f - h.beta1) * g;         // :63
+  v = h.beta2 * v + h.omb2 * g * g;              // radam_optim.py:62
+  m = h.beta1 * m + h.omb1 * g;                  // :63
   if (h.mode == 1) {                             // :92-97
     p *= h.decay;
     p -= h.step_lr * m / (sqrtf(v) + h.eps);
@@ -153,7 +154,7 @@ extern "C" int xf_grad_sqnorm(const XfRAdamJob* jobs, int n_jobs, float* out, xf
 
 extern "C" int xf_radam_step(const XfRAdamJob* jobs, int n_jobs, const XfRAdam* a, xf_stream_t s) {
   if (!a) return fail(-1, "xf_radam_step: null hyper-parameters");
-  if (!(a->beta1 >= 0.f && a->beta1 < 1.f && a->beta2 >= 0.f && a->beta2 < 1.f) || a->lr < 0.f || a->eps < 0.f)
+  if (!(a->beta1_d >= 0. && a->beta1_d < 1. && a->beta2_d >= 0. && a->beta2_d < 1.) || a->lr_d < 0. || a->eps < 0.f)
     return fail(-4, "xf_radam_step: invalid hyper-parameters");
   if (a->step < 1) return fail(-4, "xf_radam_step: step counts from 1");
   OptJobs js;
@@ -161,14 +162,15 @@ extern "C" int xf_radam_step(const XfRAdamJob* jobs, int n_jobs, const XfRAdam* 
   const long long total = js.unit_start[js.n];
   if (total == 0) return 0;
   // radam_optim.py:66-87 in double precision on the host (the reference evaluates it with Python floats)
-  const double b1 = a->beta1, b2 = a->beta2, t = static_cast<double>(a->step);
+  const double b1 = a->beta1_d, b2 = a->beta2_d, t = static_cast<double>(a->step);
   const double beta2_t = pow(b2, t);
   const double n_max = 2.0 / (1.0 - b2) - 1.0;
   const double n_sma = n_max - 2.0 * t * beta2_t / (1.0 - beta2_t);
   RAdamScalars h;
   memset(&h, 0, sizeof(h));
-  h.beta1 = a->beta1; h.beta2 = a->beta2; h.eps = a->eps;
-  h.decay = a->weight_decay != 0.f ? static_cast<float>(1.0 - static_cast<double>(a->weight_decay) * a->lr) : 1.f;
+  h.beta1 = static_cast<float>(a->beta1_d); h.beta2 = static_cast<float>(a->beta2_d); h.eps = a->eps;
+  h.omb1 = static_cast<float>(1.0 - a->beta1_d); h.omb2 = static_cast<float>(1.0 - a->beta2_d);
+  h.decay = a->weight_decay_d != 0. ? static_cast<float>(1.0 - a->weight_decay_d * a->lr_d) : 1.f;
   double step_size = -1.0;
   if (n_sma >= 5.0) {
     step_size = sqrt((1.0 - beta2_t) * (n_sma - 4.0) / (n_max - 4.0) * (n_sma - 2.0) / n_sma * n_max / (n_max - 2.0)) / (1.0 - pow(b1, t));
@@ -179,7 +181,7 @@ extern "C" int xf_radam_step(const XfRAdamJob* jobs, int n_jobs, const XfRAdam* 
   } else {
     h.mode = 0;
   }
-  h.step_lr = static_cast<float>(step_size * a->lr);
+  h.step_lr = static_cast<float>(step_size * a->lr_d);
   h.max_norm = a->max_grad_norm;
   h.sqnorm = a->grad_sqnorm;
   long long ctas = (total + 255) / 256;

@@ -101,7 +101,7 @@ class FusedRAdam(torch.optim.Optimizer):
                 n_sma = (2.0 / (1.0 - beta2) - 1.0) - 2.0 * step * b2t / (1.0 - b2t)
                 h_mode_moves = n_sma >= 5 or self.degenerated_to_sgd
                 h = XfRAdam()
-                h.lr, h.beta1, h.beta2, h.eps, h.weight_decay = group["lr"], beta1, beta2, group["eps"], group["weight_decay"]
+                h.lr_d, h.beta1_d, h.beta2_d, h.eps, h.weight_decay_d = group["lr"], beta1, beta2, group["eps"], group["weight_decay"]
                 h.degenerated_to_sgd = int(self.degenerated_to_sgd)
                 h.step = int(step)
                 h.max_grad_norm = self.max_grad_norm
