@@ -302,7 +302,10 @@ def test_layernorm_row_remap_and_dropout_pairing():
 @pytest.mark.parametrize("B,C,H,W,p,dt", [(2, 256, 16, 24, 4, torch.float32), (2, 512, 8, 12, 4, torch.bfloat16),
                                           (2, 64, 12, 20, 2, torch.float32), (3, 2048, 24, 32, 1, torch.float32),
                                           (2, 8, 16, 24, 4, torch.float32), (1, 16, 16, 272, 4, torch.float32),
-                                          (1, 6, 16, 64, 8, torch.float32)])
+                                          (1, 6, 16, 64, 8, torch.float32),
+                                          # bf16 maps on the 128-bit path (W % 8 == 0), incl. partial token tiles
+                                          (2, 256, 16, 24, 4, torch.bfloat16), (1, 16, 16, 272, 4, torch.bfloat16),
+                                          (1, 6, 16, 64, 8, torch.bfloat16), (2, 8, 16, 40, 4, torch.bfloat16)])
 def test_patchify_fold_bit_exact(B, C, H, W, p, dt):
     torch.manual_seed(9)
     f = torch.randn(B, C, H, W, device=DEV).to(dt)

@@ -166,6 +166,92 @@ patchify_fold_vec4_kernel(float* __restrict__ feat, __nv_bfloat16* __restrict__ 
   }
 }
 
+// bf16 feature maps, P >= 4: the same tile with 128-bit accesses on the feature side (8 consecutive pixels along w = 8 / P
+// patch rows) and 64-bit on the token side; the scalar kernel moves 2 bytes per instruction on the feature side.
+template <int P, bool FOLD, bool ACC>
+__global__ void __launch_bounds__(256)
+patchify_fold_vec8h_kernel(__nv_bfloat16* __restrict__ feat, __nv_bfloat16* __restrict__ tok, int B, int Cc, int H, int W, long long tok_ld) {
+  constexpr int LDT = PF_TK + 4;
+  __shared__ __align__(16) float tile[PF_TJ][LDT];
+  constexpr int PP = P * P;
+  constexpr int WRUN8 = PF_TJ * P / 8;  // 8-pixel units per (c, u) run along w
+  constexpr int TPU = 8 / P;            // tokens touched by one unit (2 for P = 4, 1 for P = 8)
+  const int gh = H / P, gw = W / P;
+  const int K = Cc * PP;
+  const int jt = (gw + PF_TJ - 1) / PF_TJ;
+  int bid = blockIdx.x;
+  const int j0 = (bid % jt) * PF_TJ; bid /= jt;
+  const int i = bid % gh; bid /= gh;
+  const int b = bid;
+  const int k0 = blockIdx.y * PF_TK;
+  const int c0 = k0 / PP;
+  const long long row0 = (static_cast<long long>(b) * gh + i) * gw + j0;
+  constexpr int UNITS8 = PF_TJ * PF_TK / 8;   // 512 feature-side units per tile
+  constexpr int UNITS4 = PF_TJ * PF_TK / 4;   // 1024 token-side units per tile
+
+  auto feat_unit = [&](int t, int& jl, int& col, long long& off, int& ntok) {
+    const int w8 = t % WRUN8, cu = t / WRUN8;
+    const int u = cu % P, cl = cu / P;
+    jl = (w8 * 8) / P;
+    const int v0 = (w8 * 8) % P;            // 0 for P = 4 and P = 8
+    col = cl * PP + u * P + v0;
+    const int c = c0 + cl;
+    ntok = c < Cc ? min(TPU, gw - (j0 + jl)) : 0;   // tokens of this unit inside the grid (gw * P % 8 == 0: whole units)
+    off = ((static_cast<long long>(b) * Cc + c) * H + i * P + u) * W + (j0 + jl) * P + v0;
+  };
+  if (!FOLD) {
+#pragma unroll
+    for (int t = threadIdx.x; t < UNITS8; t += 256) {
+      int jl, col, ntok; long long off;
+      feat_unit(t, jl, col, off, ntok);
+      uint4 q = make_uint4(0u, 0u, 0u, 0u);
+      if (ntok > 0) q = __ldg(reinterpret_cast<const uint4*>(feat + off));
+      if (P == 4) {
+        *reinterpret_cast<float4*>(&tile[jl][col]) = make_float4(bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y));
+        if (jl + 1 < PF_TJ) *reinterpret_cast<float4*>(&tile[jl + 1][col]) = make_float4(bf16_lo(q.z), bf16_hi(q.z), bf16_lo(q.w), bf16_hi(q.w));
+      } else {
+        *reinterpret_cast<float4*>(&tile[jl][col]) = make_float4(bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y));
+        *reinterpret_cast<float4*>(&tile[jl][col + 4]) = make_float4(bf16_lo(q.z), bf16_hi(q.z), bf16_lo(q.w), bf16_hi(q.w));
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int t = threadIdx.x; t < UNITS4; t += 256) {
+      const int k4 = (t % (PF_TK / 4)) * 4, jl = t / (PF_TK / 4);
+      if (j0 + jl < gw && k0 + k4 < K) {
+        const float4 x = *reinterpret_cast<const float4*>(&tile[jl][k4]);
+        *reinterpret_cast<uint2*>(tok + (row0 + jl) * tok_ld + k0 + k4) = make_uint2(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w));
+      }
+    }
+  } else {
+#pragma unroll
+    for (int t = threadIdx.x; t < UNITS4; t += 256) {
+      const int k4 = (t % (PF_TK / 4)) * 4, jl = t / (PF_TK / 4);
+      uint2 q = make_uint2(0u, 0u);
+      if (j0 + jl < gw && k0 + k4 < K) q = *reinterpret_cast<const uint2*>(tok + (row0 + jl) * tok_ld + k0 + k4);
+      *reinterpret_cast<float4*>(&tile[jl][k4]) = make_float4(bf16_lo(q.x), bf16_hi(q.x), bf16_lo(q.y), bf16_hi(q.y));
+    }
+    __syncthreads();
+#pragma unroll
+    for (int t = threadIdx.x; t < UNITS8; t += 256) {
+      int jl, col, ntok; long long off;
+      feat_unit(t, jl, col, off, ntok);
+      if (ntok > 0) {
+        float4 a = *reinterpret_cast<const float4*>(&tile[jl][col]);
+        float4 c = P == 4 ? (jl + 1 < PF_TJ ? *reinterpret_cast<const float4*>(&tile[jl + 1][col]) : make_float4(0.f, 0.f, 0.f, 0.f))
+                          : *reinterpret_cast<const float4*>(&tile[jl][col + 4]);
+        uint4* dst = reinterpret_cast<uint4*>(feat + off);
+        if (ACC) {
+          const uint4 o = *dst;
+          a.x += bf16_lo(o.x); a.y += bf16_hi(o.x); a.z += bf16_lo(o.y); a.w += bf16_hi(o.y);
+          c.x += bf16_lo(o.z); c.y += bf16_hi(o.z); c.z += bf16_lo(o.w); c.w += bf16_hi(o.w);
+        }
+        *dst = make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(c.x, c.y), pack_bf16(c.z, c.w));
+      }
+    }
+  }
+}
+
 template <typename FT, bool FOLD, bool ACC>
 static void launch_patchify_fold(FT* feat, __nv_bfloat16* tok, int B, int C, int H, int W, int p, long long tok_ld, cudaStream_t st) {
   const int gh = H / p, gw = W / p, K = C * p * p;
@@ -176,6 +262,15 @@ static void launch_patchify_fold(FT* feat, __nv_bfloat16* tok, int B, int C, int
     if (vec) {
       if (p == 4) patchify_fold_vec4_kernel<4, FOLD, ACC><<<grid, 256, 0, st>>>(reinterpret_cast<float*>(feat), tok, B, C, H, W, tok_ld);
       else patchify_fold_vec4_kernel<8, FOLD, ACC><<<grid, 256, 0, st>>>(reinterpret_cast<float*>(feat), tok, B, C, H, W, tok_ld);
+      return;
+    }
+  } else {
+    // W % 8 == 0 keeps every 8-pixel unit inside one image row and 16-byte aligned; gw * p % 8 == 0 follows
+    const bool vec = (p == 4 || p == 8) && W % 8 == 0 && (reinterpret_cast<uintptr_t>(feat) & 15) == 0 && tok_ld % 4 == 0 &&
+                     (reinterpret_cast<uintptr_t>(tok) & 7) == 0 && K % 4 == 0;
+    if (vec) {
+      if (p == 4) patchify_fold_vec8h_kernel<4, FOLD, ACC><<<grid, 256, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(feat), tok, B, C, H, W, tok_ld);
+      else patchify_fold_vec8h_kernel<8, FOLD, ACC><<<grid, 256, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(feat), tok, B, C, H, W, tok_ld);
       return;
     }
   }
