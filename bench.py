@@ -522,7 +522,9 @@ def run_ours(args):
     # the same end-to-end step fed bf16 feature maps (half the host bytes; the module accepts bf16 maps and Ego4Dv1 trains
     # with precision 16): reported BESIDE the fp32 headline, never instead of it
     e2e_bf16 = None
-    if args.feat_dtype == "f32" and not args.no_bf16_e2e:
+    # (N > 1: only on request -- `--bf16-e2e` or a separate `--feat-dtype bf16` run -- so the scaling runs time exactly the
+    # fp32 pipeline and nothing else)
+    if args.feat_dtype == "f32" and not args.no_bf16_e2e and (world == 1 or args.bf16_e2e):
         feats_hb = {k: v.to(torch.bfloat16).pin_memory() for k, v in feats_h.items()}
         prefetch_b, step_b, h2d_b, rate_b = build_e2e(feats_hb)
         prefetch_b(0)
@@ -714,6 +716,7 @@ def main():
                     help="samples per CPU step; 0 = auto (1 for the in-line cpu_baseline, sized for ~150 s total in --impl reference)")
     ap.add_argument("--accumulate", type=int, default=1, help="accumulate_grad_batches: all-reduce every N-th micro-step")
     ap.add_argument("--no-bf16-e2e", action="store_true", help="skip the extra end-to-end pass with bf16 feature maps")
+    ap.add_argument("--bf16-e2e", action="store_true", help="run the extra bf16-feature end-to-end pass for N > 1 too")
     ap.add_argument("--sweep", action="store_true", help="BASELINE config 5: language length x image size x width, B = 16")
     args = ap.parse_args()
     if args.sweep:
