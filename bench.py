@@ -339,7 +339,7 @@ def run_ours(args):
         # same initial weights on every rank (seeded construction); gradients averaged per level bucket,
         # each bucket's NCCL all-reduce launched as soon as that level's backward has been enqueued
         from transfusion_b200.parallel import BucketedGradAllReduce, level_buckets
-        reducer = BucketedGradAllReduce(level_buckets(model))
+        reducer = BucketedGradAllReduce(level_buckets(model), compress=args.grad_compress if args.grad_compress != "none" else None)
 
     feat_dtype = torch.float32 if args.feat_dtype == "f32" else torch.bfloat16
     feats_h, lang_h, mask_h = synthetic_inputs(args.workload, B, L, seed=1234 + rank, feat_dtype=feat_dtype, pin=True)
@@ -613,7 +613,7 @@ def run_ours(args):
                 "config": config_dict(args, w, B, L, world, train),
                 "notes": {"level_streams": "independent FPN levels overlap on side streams in the timed runs; the `kernels` "
                                            "breakdown is taken with the levels serialised",
-                          "accumulate_grad_batches": args.accumulate,
+                          "accumulate_grad_batches": args.accumulate, "grad_allreduce": "fp32" if args.grad_compress == "none" else args.grad_compress,
                           "attn_bwd": "5-unit schedule (scores once; bf16 [B,H,S,S] scratch)" if os.environ.get("XF_ATTN_BWD_WS", "1") != "0"
                                       else "3 on-chip passes (8 units)"},
                 "clocks": clocks, "gpu_launches": int(launches),
@@ -716,6 +716,8 @@ def main():
                     help="samples per CPU step; 0 = auto (1 for the in-line cpu_baseline, sized for ~150 s total in --impl reference)")
     ap.add_argument("--accumulate", type=int, default=1, help="accumulate_grad_batches: all-reduce every N-th micro-step")
     ap.add_argument("--no-bf16-e2e", action="store_true", help="skip the extra end-to-end pass with bf16 feature maps")
+    ap.add_argument("--grad-compress", default="none", choices=["none", "bf16"],
+                    help="N > 1: exchange the gradient arenas as bf16 (default: fp32 like the reference's DDP)")
     ap.add_argument("--bf16-e2e", action="store_true", help="run the extra bf16-feature end-to-end pass for N > 1 too")
     ap.add_argument("--sweep", action="store_true", help="BASELINE config 5: language length x image size x width, B = 16")
     args = ap.parse_args()

@@ -152,6 +152,10 @@ int xf_cast_pad(const float* src, int64_t lds, void* dst_bf16, int64_t ldd, int 
 int xf_unpad_add(const float* src_padded, int64_t lds, float* dst, int64_t ldd, int rows, int cols, int rin, int rout, int cin,
                  int cout, xf_stream_t stream);
 
+/* dst[i] = scale * float(src_bf16[i]), n % 8 == 0: unpacks a bf16-compressed gradient arena after its all-reduce (and
+ * averages it) -- the optional compression of the data-parallel exchange (run_experiment.py:452 runs DDP in fp32). */
+int xf_bf16_to_f32(const void* src_bf16, float* dst, int64_t n, float scale, xf_stream_t stream);
+
 /* The same cast for up to XF_CAST_MAX_JOBS tensors in ONE launch (all bf16 weight copies of an FPN level:
  * 18 small tensors whose separate launches were latency-bound).  Replaces the implicit per-module
  * fp32 -> autocast-bf16 weight conversions of ego_fusion/cross_f_box_layers.py:75-103. */

@@ -1370,6 +1370,33 @@ extern "C" int xf_rows_gather(const void* in, int64_t ldi, void* out, int64_t ld
 }
 
 // ------------------------------------------------------------------------------------------
+// bf16 -> fp32 with a scale (the inverse of the weight cast): unpacks a bf16-compressed gradient arena after its
+// all-reduce and applies the 1 / world averaging in the same pass.
+// ------------------------------------------------------------------------------------------
+namespace xf {
+__global__ void __launch_bounds__(256) bf16_to_f32_scale_kernel(const uint4* __restrict__ src, float4* __restrict__ dst, long long nvec, float scale) {
+  for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; t < nvec;
+       t += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint4 q = __ldg(src + t);
+    dst[2 * t] = make_float4(bf16_lo(q.x) * scale, bf16_hi(q.x) * scale, bf16_lo(q.y) * scale, bf16_hi(q.y) * scale);
+    dst[2 * t + 1] = make_float4(bf16_lo(q.z) * scale, bf16_hi(q.z) * scale, bf16_lo(q.w) * scale, bf16_hi(q.w) * scale);
+  }
+}
+}  // namespace xf
+
+extern "C" int xf_bf16_to_f32(const void* src_bf16, float* dst, int64_t n, float scale, xf_stream_t s) {
+  if (!src_bf16 || !dst) return fail(-1, "xf_bf16_to_f32: null pointer");
+  if (n % 8 || ((reinterpret_cast<uintptr_t>(src_bf16) | reinterpret_cast<uintptr_t>(dst)) & 15))
+    return fail(-2, "xf_bf16_to_f32: n must be a multiple of 8 and the pointers 16-byte aligned");
+  if (n == 0) return 0;
+  bf16_to_f32_scale_kernel<<<grid_for(n / 8, 256), 256, 0, reinterpret_cast<cudaStream_t>(s)>>>(
+      reinterpret_cast<const uint4*>(src_bf16), reinterpret_cast<float4*>(dst), n / 8, scale);
+  g_launches.fetch_add(1);
+  XF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // Test aid: materialise the counter-based dropout keep masks (ptx.cuh) so a CPU checker can apply the SAME masks.
 // These are the canonical definitions every kernel of the library recomputes on the fly.
 // ------------------------------------------------------------------------------------------

@@ -239,6 +239,14 @@ def cast_pad_multi(jobs):
             check(lib().xf_cast_pad_multi(arr, len(chunk), _stream()), "xf_cast_pad_multi")
 
 
+def bf16_to_f32(src: torch.Tensor, dst: torch.Tensor, scale: float = 1.0):
+    """dst (fp32, flat) = scale * src (bf16, flat); numel % 8 == 0."""
+    _req(src, torch.bfloat16, "src"); _req(dst, torch.float32, "dst")
+    n = src.numel()
+    with _Prof("cast", 0.0, 6.0 * n):
+        check(lib().xf_bf16_to_f32(_ptr(src), _ptr(dst), C.c_int64(n), C.c_float(scale), _stream()), "xf_bf16_to_f32")
+
+
 def unpad_add(src: torch.Tensor, dst: torch.Tensor, rows: int, cols: int, rin=0, rout=0, cin=0, cout=0):
     _req(src, torch.float32, "src"); _req(dst, torch.float32, "dst")
     with _Prof("cast", 0.0, 12.0 * rows * cols):

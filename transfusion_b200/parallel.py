@@ -23,9 +23,16 @@ def shard_range(global_batch: int, rank: int, world: int):
 
 class BucketedGradAllReduce:
     def __init__(self, buckets: Sequence[Iterable[torch.nn.Parameter]], group: Optional[dist.ProcessGroup] = None,
-                 average: bool = True):
+                 average: bool = True, compress: Optional[str] = None):
+        """compress = "bf16": the level arenas are exchanged as bf16 (half the NVLink bytes and half the time NCCL's
+        channel CTAs hold SMs the persistent compute kernels want); the sum runs in NCCL's bf16 reduction, the result is
+        unpacked to fp32 with the 1 / world factor.  Default None = fp32 like the reference's DDP."""
         self.group = group
         self.average = average
+        if compress not in (None, "bf16"):
+            raise ValueError("compress must be None or 'bf16'")
+        self.compress = compress
+        self._packed = {}
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.buckets: List[List[torch.nn.Parameter]] = [[p for p in b if p.requires_grad] for b in buckets]
         self.buckets = [b for b in self.buckets if b]
@@ -77,6 +84,17 @@ class BucketedGradAllReduce:
         arena = self._arena_of(bucket)
         if arena is not None:
             self._arena_buckets.add(bi)
+        if arena is not None and self.compress == "bf16" and arena.is_cuda and arena.numel() % 64 == 0:
+            # bf16-compressed exchange: pack (one cast launch), all-reduce half the bytes, unpack + average in finish()
+            from . import ops
+            n = arena.numel()
+            buf = self._packed.get(bi)
+            if buf is None or buf.numel() != n or buf.device != arena.device:
+                buf = self._packed[bi] = torch.empty(n, dtype=torch.bfloat16, device=arena.device)
+            ops.cast_pad(arena.view(n // 64, 64), buf.view(n // 64, 64), n // 64, 64)
+            work = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True) if self.world > 1 else None
+            self.works.append((bi, work, ("bf16", arena, buf)))
+            return
         if arena is not None:   # one in-place all-reduce of the level's arena: no flatten / scatter copies
             if self.world > 1:
                 # NCCL averages inside the collective; other backends sum and finish() divides
@@ -118,6 +136,11 @@ class BucketedGradAllReduce:
         for bi, work, arena in self.works:
             if work is not None:
                 work.wait()
+            if isinstance(arena, tuple):   # bf16-compressed: unpack into the fp32 arena the .grad views live in
+                from . import ops
+                _, dst, buf = arena
+                ops.bf16_to_f32(buf, dst, 1.0 / self.world if (self.average and self.world > 1) else 1.0)
+                continue
             if arena is not None:
                 if self.average and self.world > 1:
                     arena.div_(self.world)
