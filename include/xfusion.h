@@ -65,9 +65,10 @@ typedef struct XfGemm {
   const float* bias;        /* [N] fp32 or NULL */
   const float* pos_table;   /* [>= rows_in, N] fp32, row = m % rows_in, or NULL (utils.py:209-214) */
   int64_t rows_in, rows_out, row_off;
-  int32_t act;              /* 0 none, 1 GELU erf (F.gelu) */
+  int32_t act;              /* 0 none, 1 GELU erf (F.gelu), 2 ReLU (TwoMLPHead fc6 / fc7, torchvision faster_rcnn.py) */
   void* preact_out;         /* bf16, indexed like out: value before act (saved for backward), or NULL */
-  const void* dact_in;      /* bf16, indexed like out: v *= gelu'(dact_in[m,n]) (GELU backward), or NULL */
+  const void* dact_in;      /* bf16, indexed like out, or NULL.  act 0: v *= gelu'(dact_in[m,n]) (GELU backward, dact_in = saved
+                               pre-activation); act 2: v = dact_in[m,n] > 0 ? v : 0 (ReLU backward, dact_in = forward output) */
   const void* residual;     /* bf16 [m_out, n], leading dim ldr, or NULL */
   int64_t ldr;
   void* out; int64_t ldc;

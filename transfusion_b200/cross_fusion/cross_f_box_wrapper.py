@@ -118,9 +118,8 @@ class CrossFusionBoxWrapper(nn.Module):
     def invalidate_weight_cache(self):
         """Drops the cached bf16 weight copies; call after modifying parameters behind autograd's back (`p.data.<op>_()`)
         between two inference calls.  train() / eval() switches do it automatically."""
-        for p in self.parameters():
-            if hasattr(p, "_xf_bf16"):
-                del p._xf_bf16
+        from ..weight_cache import invalidate
+        invalidate(self)
 
     def train(self, mode: bool = True):
         if mode != self.training:

@@ -21,6 +21,7 @@ from typing import List, Optional
 import torch
 
 from .. import ops
+from ..weight_cache import bf16_weight
 
 LN_EPS = 1e-5
 
@@ -144,37 +145,13 @@ class FusionLevelFunction(torch.autograd.Function):
         pd_back = cfg.backproj_dropout if train else 0.0
         seed = cfg.seed
 
-        # ---- bf16 weight copies (head dim padded d -> dp with zero rows / columns): one launch for the level.
-        # A copy is cached on its parameter as (version, buffer, flat layout?, tag) and reused
-        #   * in training only when transfusion_b200.optim.FusedRAdam produced it in its update pass (tag "opt": the
-        #     optimizer owns parameter AND copy; one forward consumes it), so steady-state training casts nothing here;
-        #     any other optimizer may write through `p.data` without touching the version counter (the reference's RAdam
-        #     does, radam_optim.py:96), so nothing else is trusted while training;
-        #   * in inference while the parameter's version counter is unchanged (CrossFusionBoxWrapper.train() drops the
-        #     cache on every mode switch; invalidate_weight_cache() does it on demand).
+        # ---- bf16 weight copies (head dim padded d -> dp with zero rows / columns): one launch for the level; cached per
+        # parameter (weight_cache.py: produced by FusedRAdam in training, version-keyed in inference)
         casts = []
         trust_version = not (train and need_grad)
 
         def bf16_of(prm, rows, cols, pad=None):
-            """pad = (rin, rout, cin, cout, out_rows, out_cols) for head-padded layouts, else the flat [rows, cols] copy."""
-            cache = getattr(prm, "_xf_bf16", None)
-            flat = pad is None
-            ok = cache is not None and cache[0] == prm._version and cache[1].device == dev and cache[2] == flat
-            if ok and (trust_version or cache[3] == "opt"):
-                if cache[3] == "opt":
-                    prm._xf_bf16 = (cache[0], cache[1], cache[2], "used")
-                return cache[1]
-            if flat:
-                buf = cache[1] if (cache is not None and cache[2] and cache[1].device == dev and cache[1].numel() == rows * cols) \
-                    else empty(rows, cols)
-                casts.append((prm.reshape(rows, cols), buf.view(rows, cols), rows, cols, 0, 0, 0, 0))
-                buf = buf.view(rows, cols)
-            else:
-                rin, rout, cin, cout, orows, ocols = pad
-                buf = torch.zeros(orows, ocols, device=dev, dtype=bf)
-                casts.append((prm, buf, rows, cols, rin, rout, cin, cout))
-            prm._xf_bf16 = (prm._version, buf, flat, "cast")
-            return buf
+            return bf16_weight(prm, rows, cols, casts, trust_version, dev, pad)
 
         wpe_b = bf16_of(wpe, D, K)
         wbp_b = bf16_of(wbp, K, D)

@@ -143,8 +143,16 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int m, int n
     }
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+  } else if (p.act == 2 && !p.dact_in) {   // ReLU (TwoMLPHead fc6 / fc7)
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
   }
-  if (p.dact_in) {
+  if (p.dact_in && p.act == 2) {   // ReLU backward: dact_in holds the forward OUTPUT (> 0 exactly where the input was)
+    const __nv_bfloat16* di = p.dact_in + orow;
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (n0 + i < p.N && !(__bfloat162float(di[i]) > 0.f)) v[i] = 0.f;
+  } else if (p.dact_in) {
     const __nv_bfloat16* di = p.dact_in + orow;
     if (full && p.vec_ok) {
 #pragma unroll
@@ -338,15 +346,24 @@ __device__ __forceinline__ void epilogue_fast(const GemmParams& p, const CUtenso
     } else if (EPI == EPI_DGELU) {
       float2 u[16];
       unpack32(aux, u);
+      if (p.act == 2) {   // ReLU backward: aux = forward output
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = __fmul2_rn(v[i], gelu_grad2(u[i]));
+        for (int i = 0; i < 16; ++i) v[i] = make_float2(u[i].x > 0.f ? v[i].x : 0.f, u[i].y > 0.f ? v[i].y : 0.f);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __fmul2_rn(v[i], gelu_grad2(u[i]));
+      }
       if (p.drop_p > 0.f) {
         drop32(v, rh, col_addr, p.drop_thresh);
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = __fmul2_rn(v[i], ds);
       }
       box_store_begin<0>(lane);
-    } else {  // EPI_LINEAR: [bias] [dropout] [+ residual]
+    } else {  // EPI_LINEAR: [bias] [ReLU] [dropout] [+ residual]
+      if (p.act == 2) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = make_float2(fmaxf(v[i].x, 0.f), fmaxf(v[i].y, 0.f));
+      }
       if (p.drop_p > 0.f) drop32(v, rh, col_addr, p.drop_thresh);
       if (p.residual) {
         float2 rs[16];
@@ -682,6 +699,7 @@ extern "C" int xf_gemm(const XfGemm* g, xf_stream_t stream_) {
   if (split_k > 1 && !(g->out_dtype == 1 && g->accumulate == 1)) return fail(-4, "xf_gemm: split_k needs fp32 atomic accumulation");
   if (g->accumulate && g->out_dtype != 1) return fail(-5, "xf_gemm: accumulate needs fp32 output");
   if (g->drop_p < 0.f || g->drop_p >= 1.f) return fail(-6, "xf_gemm: drop_p out of range");
+  if (g->act < 0 || g->act > 2) return fail(-6, "xf_gemm: act must be 0 (none), 1 (GELU) or 2 (ReLU)");
 
   const int nb1 = g->batch1 > 0 ? g->batch1 : 0, nb2 = g->batch2 > 0 ? g->batch2 : (nb1 > 0 ? 1 : 0);
   const bool batched = nb1 > 0;
@@ -770,8 +788,8 @@ extern "C" int xf_gemm(const XfGemm* g, xf_stream_t stream_) {
     if (p.accumulate && !g->bias && !g->act && !g->dact_in && !g->residual && !(g->drop_p > 0.f)) epi = EPI_RED;
   } else if (plain) {
     if (g->act == 1 && !g->dact_in && !g->residual && !drop_pre_act) epi = EPI_GELU;
-    else if (g->act == 0 && g->dact_in && !g->residual && !g->bias && !g->preact_out) epi = EPI_DGELU;
-    else if (g->act == 0 && !g->dact_in && !g->preact_out) epi = EPI_LINEAR;
+    else if ((g->act == 0 || g->act == 2) && g->dact_in && !g->residual && !g->bias && !g->preact_out) epi = EPI_DGELU;
+    else if ((g->act == 0 || g->act == 2) && !g->dact_in && !g->preact_out) epi = EPI_LINEAR;
   }
 
   // output / operand boxes of the specialised epilogues: [32 columns x 32 rows] bf16, SWIZZLE_64B
