@@ -89,6 +89,10 @@ typedef struct XfGemm {
 } XfGemm;
 
 int xf_gemm(const XfGemm* g, xf_stream_t stream);
+/* Per-host-thread cap on the persistent grid of xf_gemm calls that leave max_ctas = 0 (also the GEMMs xf_attn_bwd issues);
+ * 0 removes the cap.  Returns the previous cap.  For callers that run independent problems on several streams and give
+ * each a fixed share of the SMs. */
+int xf_set_gemm_cta_cap(int ctas);
 
 
 /* ------------------------------------------------------------------------------------------

@@ -20,6 +20,7 @@ from .utils import PositionalEmbeddingLayer, RegroupPatchesLayerBox, get_visual_
 
 MAX_NUM_PATCHES = 8192  # cross_f_box_wrapper.py:21
 LEVEL_STREAMS = bool(int(_os.environ.get("XF_LEVEL_STREAMS", "1")))   # run independent FPN levels on side streams
+SM_PARTITION = bool(int(_os.environ.get("XF_SM_PARTITION", "0")))     # give each concurrent level a fixed share of the SMs
 
 
 def _default_pooling_factory(narr_embed_args, cross_layer_args):
@@ -127,7 +128,8 @@ class CrossFusionBoxWrapper(nn.Module):
         return super().train(mode)
 
     # ---- the hot path -----------------------------------------------------------------------
-    def run_level(self, i: int, feat: torch.Tensor, language_f: torch.Tensor, lang_pad_mask, need_lang_out=False, out_stream=None):
+    def run_level(self, i: int, feat: torch.Tensor, language_f: torch.Tensor, lang_pad_mask, need_lang_out=False, out_stream=None,
+                  gemm_ctas: int = 0):
         """One FPN level: reference :180-212.  Returns (fused [B,C,h,w], fused language tokens or None)."""
         enc: CrossTransformerModuleBox = self.cross_fusion_encoders[i]
         t2f: RegroupPatchesLayerBox = self.tokens_to_features[i]
@@ -148,12 +150,40 @@ class CrossFusionBoxWrapper(nn.Module):
         cfg = LevelConfig(level=i, patch=p, num_heads=enc.num_heads, num_layers=enc.num_layers, training=self.training,
                           patch_dropout=float(enc.patch_dropout), token_dropout=float(enc.token_dropout),
                           backproj_dropout=float(t2f.back_dropout.p), seed=seed, need_lang_out=need_lang_out,
-                          out_stream=out_stream)
+                          out_stream=out_stream, gemm_ctas=gemm_ctas)
         params = [pe.weight, enc.image_kind_embedding, enc.lang_kind_embedding, enc.pos_embedding_layer.table(),
                   *enc.level_params(), enc.final_norm_layer.weight, enc.final_norm_layer.bias, t2f.linear.weight,
                   t2f.linear.bias]
         fused, lang_out = FusionLevelFunction.apply(cfg, feat, language_f, lang_pad_mask, *params)
         return fused, (lang_out if need_lang_out else None)
+
+    def _sm_shares(self, feats, language_f):
+        """Spatial partition of the SMs between the concurrently running FPN levels: each level's persistent GEMM grids get a
+        share proportional to the level's algorithmic FLOPs (SURVEY 8d formula), so the four levels advance side by side and
+        finish together instead of queueing full-machine grids behind one another (the coarse levels fill only 2.3 - 4.6
+        waves of a 148-SM grid).  XF_SM_SHARES="a,b,c,d" overrides (CTAs per level, 0 = whole machine); "off" disables."""
+        env = _os.environ.get("XF_SM_SHARES", "")
+        n_lv = len(self.fpn_features_idx)
+        if env == "off":
+            return None
+        if env:
+            v = [int(x) for x in env.split(",")]
+            return (v + [0] * n_lv)[:n_lv]
+        if not SM_PARTITION:
+            return None
+        D, L = self.token_dim, language_f.shape[1]
+        work = []
+        for i, key in enumerate(self.fpn_features_idx):
+            f = feats[str(key)]
+            p = self.tokens_to_features[i].patch_h
+            n = (f.shape[2] // p) * (f.shape[3] // p)
+            S = n + L
+            nl = self.cross_fusion_encoders[i].num_layers
+            work.append(4.0 * n * f.shape[1] * p * p * D + nl * (16.0 * S * D * D + 4.0 * S * S * D))
+        total_sms = torch.cuda.get_device_properties(language_f.device).multi_processor_count
+        tot = sum(work)
+        shares = [max(2, int(round(total_sms * w / tot / 2.0)) * 2) for w in work]   # even: the GEMM runs on CTA pairs
+        return shares
 
     def _level_streams(self, ref):
         """One side stream per FPN level on `ref`'s device (None on CPU tensors: the kernels will raise anyway)."""
@@ -205,6 +235,7 @@ class CrossFusionBoxWrapper(nn.Module):
             depth = 1 if (self.training and torch.is_grad_enabled()) else 2
             while len(pending) >= depth:
                 pending.pop(0).synchronize()
+        shares = self._sm_shares(features_dict["features"], language_f) if side is not None else None
         for i, key in level_order:
             key = str(key)
             feat = features_dict["features"][key]
@@ -215,7 +246,8 @@ class CrossFusionBoxWrapper(nn.Module):
                 st = side[i % len(side)]
                 st.wait_stream(cur)
                 with torch.cuda.stream(st):
-                    fused, fused_l_features = self.run_level(i, feat, language_f, lang_pad, need_lang_out, out_stream=cur)
+                    fused, fused_l_features = self.run_level(i, feat, language_f, lang_pad, need_lang_out, out_stream=cur,
+                                                             gemm_ctas=shares[i] if shares else 0)
                 # Memory safety across streams without record_stream (whose deferred frees made the allocator's
                 # demand depend on host run-ahead): the outputs come from the caller stream's pool (out_stream) and
                 # are written on `st`, which waited for everything the caller had enqueued; the inputs, allocated on

@@ -51,6 +51,9 @@ class LevelConfig:
     # allocated from THAT stream's pool (no record_stream, so no deferred frees that make the allocator's needs
     # depend on how far the host runs ahead)
     out_stream: object = None
+    # share of the SMs this level's persistent GEMM grids may occupy when the levels run concurrently on side streams
+    # (0 = whole machine)
+    gemm_ctas: int = 0
 
     def stream(self, layer: int, site: int) -> int:
         return ((self.level * 16 + layer) * 64 + site) & 0xFFFFFFFF
@@ -73,24 +76,24 @@ N_TAIL_PARAMS = 4       # final LN weight/bias, back-projection weight/bias
 N_CLUSTERS = 74  # CTA pairs on a 148-SM B200
 
 
-def _split_k_for(tiles: int, total_kb: int) -> int:
+def _split_k_for(tiles: int, total_kb: int, clusters: int = N_CLUSTERS) -> int:
     """Split-K factor for a wgrad GEMM with `tiles` output tiles and `total_kb` 64-token k-blocks: minimise
     waves x (k-blocks per item + fixed per-item cost) over the persistent grid of CTA pairs."""
     best, best_cost = 1, None
     for s in range(1, max(1, min(32, total_kb // 8)) + 1):
         items = tiles * s
-        waves = -(-items // N_CLUSTERS)
+        waves = -(-items // clusters)
         cost = waves * (-(-total_kb // s) + 6)
         if best_cost is None or cost < best_cost:
             best, best_cost = s, cost
     return best
 
 
-def _wgrad(dy: torch.Tensor, x: torch.Tensor, out_f32: torch.Tensor, n_out: int, k_in: int, tokens: int):
+def _wgrad(dy: torch.Tensor, x: torch.Tensor, out_f32: torch.Tensor, n_out: int, k_in: int, tokens: int, ctas: int = 0):
     """out_f32[n_out, k_in] += dy[tokens, n_out]^T @ x[tokens, k_in]  (both operands MN-major)."""
     tn = next((c for c in (256, 224, 192, 160, 128) if k_in % c == 0), 256)   # mirrors pick_tile_n in gemm.cu
     tiles = ((n_out + 255) // 256) * ((k_in + tn - 1) // tn)
-    split = _split_k_for(tiles, (tokens + 63) // 64)
+    split = _split_k_for(tiles, (tokens + 63) // 64, max(1, ctas // 2) if ctas > 0 else N_CLUSTERS)
     ops.gemm(dy, x, out_f32, M=n_out, N=k_in, K=tokens, a_mn_major=True, b_mn_major=True, accumulate=True,
              split_k=split)
 
@@ -102,6 +105,14 @@ class FusionLevelFunction(torch.autograd.Function):
     def forward(ctx, cfg: LevelConfig, feat: torch.Tensor, lang: torch.Tensor, key_pad: Optional[torch.Tensor], *params):
         if not feat.is_cuda:
             raise RuntimeError("transfusion_b200: the fusion path has no CPU implementation (CUDA tensors required)")
+        prev_cap = ops.set_gemm_cta_cap(cfg.gemm_ctas)
+        try:
+            return FusionLevelFunction._forward(ctx, cfg, feat, lang, key_pad, *params)
+        finally:
+            ops.set_gemm_cta_cap(prev_cap)
+
+    @staticmethod
+    def _forward(ctx, cfg: LevelConfig, feat: torch.Tensor, lang: torch.Tensor, key_pad: Optional[torch.Tensor], *params):
         dev = feat.device
         B, C, Hf, Wf = feat.shape
         p = cfg.patch
@@ -258,6 +269,14 @@ class FusionLevelFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_fused, d_lang_out):
+        prev_cap = ops.set_gemm_cta_cap(ctx.cfg.gemm_ctas)
+        try:
+            return FusionLevelFunction._backward(ctx, d_fused, d_lang_out)
+        finally:
+            ops.set_gemm_cta_cap(prev_cap)
+
+    @staticmethod
+    def _backward(ctx, d_fused, d_lang_out):
         cfg: LevelConfig = ctx.cfg
         (B, C, Hf, Wf, p, n, L, D, S, H, d, dp, Dp, F, K, M, Sp) = ctx.dims
         pd_patch, pd_tok, pd_back = ctx.pd
@@ -317,7 +336,7 @@ class FusionLevelFunction(torch.autograd.Function):
         dyb = empty(B * n, K)
         ops.patchify(d_fused_c, p, dyb)
         g_bbp = zeros(K); ops.colsum(dyb, g_bbp, B * n, K)
-        g_wbp = zeros(K, D); _wgrad(dyb, ctx.vis, g_wbp, K, D, B * n)
+        g_wbp = zeros(K, D); _wgrad(dyb, ctx.vis, g_wbp, K, D, B * n, ctas=cfg.gemm_ctas)
         dvis = empty(B * n, D)
         ops.gemm(dyb, ctx.wbp_b, dvis, M=B * n, N=D, K=K, b_mn_major=True)
         del dyb
@@ -355,13 +374,13 @@ class FusionLevelFunction(torch.autograd.Function):
                               dx2_drop=(pd_tok, seed, cfg.stream(l, SITE_DROP2)))
             G2 = g2 if g2 is not None else dy2
             # linear2: wgrad, dgrad fused with dropout(ffn) mask and GELU'
-            g_w2 = zeros(D, F); _wgrad(G2, h, g_w2, D, F, M)
+            g_w2 = zeros(D, F); _wgrad(G2, h, g_w2, D, F, M, ctas=cfg.gemm_ctas)
             du = empty(M, F)
             ops.gemm(G2, w2_b, du, M=M, N=F, K=D, b_mn_major=True, dact_in=u, drop_p=pd_tok, drop_seed=seed,
                      drop_stream=cfg.stream(l, SITE_FFN), drop_first=True)
             # linear1
             g_b1 = zeros(F); ops.colsum(du, g_b1, M, F)
-            g_w1 = zeros(F, D); _wgrad(du, x1, g_w1, F, D, M)
+            g_w1 = zeros(F, D); _wgrad(du, x1, g_w1, F, D, M, ctas=cfg.gemm_ctas)
             dx1 = empty(M, D)
             ops.gemm(du, w1_b, dx1, M=M, N=D, K=F, b_mn_major=True, residual=dy2)
             del du
@@ -373,7 +392,7 @@ class FusionLevelFunction(torch.autograd.Function):
                               dx2_drop=(pd_tok, seed, cfg.stream(l, SITE_DROP1)))
             G1 = g1 if g1 is not None else dy1
             # out_proj
-            g_wo_p = zeros(D, Dp); _wgrad(G1, att, g_wo_p, D, Dp, M)
+            g_wo_p = zeros(D, Dp); _wgrad(G1, att, g_wo_p, D, Dp, M, ctas=cfg.gemm_ctas)
             datt = empty(M, Dp)
             ops.gemm(G1, wo_b, datt, M=M, N=Dp, K=D, b_mn_major=True)
             # attention backward
@@ -387,7 +406,7 @@ class FusionLevelFunction(torch.autograd.Function):
             del datt
             # in_proj
             g_bin_p = zeros(3 * Dp); ops.colsum(dqkv, g_bin_p, M, 3 * Dp)
-            g_win_p = zeros(3 * Dp, D); _wgrad(dqkv, x, g_win_p, 3 * Dp, D, M)
+            g_win_p = zeros(3 * Dp, D); _wgrad(dqkv, x, g_win_p, 3 * Dp, D, M, ctas=cfg.gemm_ctas)
             dxin = empty(M, D)
             ops.gemm(dqkv, win_b, dxin, M=M, N=D, K=3 * Dp, b_mn_major=True, residual=dy1)
             del dqkv
@@ -411,7 +430,7 @@ class FusionLevelFunction(torch.autograd.Function):
         g_img_kind = zeros(D)
         ops.rows_gather(dz0, dz0v, B * n, D, in_map=(n, S, 0), colsum=g_img_kind, drop_p=pd_patch, drop_seed=seed,
                         drop_stream=cfg.stream(0, SITE_PATCH))
-        g_wpe = zeros(D, K); _wgrad(dz0v, ctx.tok, g_wpe, D, K, B * n)
+        g_wpe = zeros(D, K); _wgrad(dz0v, ctx.tok, g_wpe, D, K, B * n, ctas=cfg.gemm_ctas)
         d_feat = None
         if ctx.needs[0]:
             dtok = empty(B * n, K)

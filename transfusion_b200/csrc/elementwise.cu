@@ -433,6 +433,15 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const LnParams p) {
   }
 }
 
+// fp32 += of 4 consecutive columns: a 128-bit vector reduction when the address is 16-byte aligned, else scalar atomics
+__device__ __forceinline__ void red_add4(float* dst, float2 a, float2 b) {
+  if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y) : "memory");
+  } else {
+    atomicAdd(dst, a.x); atomicAdd(dst + 1, a.y); atomicAdd(dst + 2, b.x); atomicAdd(dst + 3, b.y);
+  }
+}
+
 // LayerNorm backward.  dx = rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy * gamma.
 // Also: dgamma += sum dy*xhat, dbeta += sum dy (fp32) and, optionally, colsum of the gradient that
 // enters the producing linear (= its bias grad) and a dropout-masked copy dx2 of dx (the gradient of
@@ -634,12 +643,10 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_kernel(const LnBwdParams
   for (int j = 0; j < NJ; ++j) {
     const int col = c4 + 1024 * j;
     if (col < p.D) {
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        atomicAdd(p.dgamma + col + 2 * k, cg[j][k].x); atomicAdd(p.dgamma + col + 2 * k + 1, cg[j][k].y);
-        atomicAdd(p.dbeta + col + 2 * k, cb[j][k].x); atomicAdd(p.dbeta + col + 2 * k + 1, cb[j][k].y);
-        if (p.dbias) { atomicAdd(p.dbias + col + 2 * k, cbias[j][k].x); atomicAdd(p.dbias + col + 2 * k + 1, cbias[j][k].y); }
-      }
+      // one 128-bit reduction per array instead of four scalar atomics (hundreds of CTAs hit the same D columns)
+      red_add4(p.dgamma + col, cg[j][0], cg[j][1]);
+      red_add4(p.dbeta + col, cb[j][0], cb[j][1]);
+      if (p.dbias) red_add4(p.dbias + col, cbias[j][0], cbias[j][1]);
     }
   }
 }
@@ -844,12 +851,10 @@ layernorm_bwd_tma_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
   for (int j = 0; j < NJ; ++j) {
     const int col = threadIdx.x * 4 + 1024 * j;
     if (col < p.D) {
-#pragma unroll
-      for (int kk = 0; kk < 2; ++kk) {
-        atomicAdd(p.dgamma + col + 2 * kk, cg[j][kk].x); atomicAdd(p.dgamma + col + 2 * kk + 1, cg[j][kk].y);
-        atomicAdd(p.dbeta + col + 2 * kk, cb[j][kk].x); atomicAdd(p.dbeta + col + 2 * kk + 1, cb[j][kk].y);
-        if (p.dbias) { atomicAdd(p.dbias + col + 2 * kk, cbias[j][kk].x); atomicAdd(p.dbias + col + 2 * kk + 1, cbias[j][kk].y); }
-      }
+      // one 128-bit reduction per array instead of four scalar atomics (hundreds of CTAs hit the same D columns)
+      red_add4(p.dgamma + col, cg[j][0], cg[j][1]);
+      red_add4(p.dbeta + col, cb[j][0], cb[j][1]);
+      if (p.dbias) red_add4(p.dbias + col, cbias[j][0], cbias[j][1]);
     }
   }
 }

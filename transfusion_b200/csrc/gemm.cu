@@ -688,6 +688,17 @@ static int launch_gemm(int ctas, int smem_bytes, cudaStream_t stream, const CUte
 
 }  // namespace xf
 
+namespace xf { thread_local int g_gemm_cta_cap = 0; }
+
+// Caps the persistent grid of every xf_gemm issued by THIS host thread whose max_ctas is 0 (0 = no cap).  Lets a caller
+// that runs independent problems on several streams give each a fixed share of the SMs (spatial partition) instead of
+// letting full-machine persistent grids queue behind one another.
+extern "C" int xf_set_gemm_cta_cap(int ctas) {
+  const int prev = xf::g_gemm_cta_cap;
+  xf::g_gemm_cta_cap = ctas > 0 ? ctas : 0;
+  return prev;
+}
+
 extern "C" int xf_gemm(const XfGemm* g, xf_stream_t stream_) {
   using namespace xf;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -812,6 +823,7 @@ extern "C" int xf_gemm(const XfGemm* g, xf_stream_t stream_) {
   const int smem_bytes = 1024 /*align slack*/ + GEMM_CTRL_BYTES + GEMM_IO_BYTES + p.stages * p.stage_bytes;
   const int items = p.num_m_tiles * p.num_n_tiles * p.split_k * (batched ? nb1 * nb2 : 1);
   int sms = g->max_ctas > 0 ? g->max_ctas : sm_count();
+  if (g->max_ctas <= 0 && g_gemm_cta_cap > 0 && g_gemm_cta_cap < sms) sms = g_gemm_cta_cap;
   if (cg == 1) {
     int ctas = sms < items ? sms : items;
     switch (epi) {

@@ -125,6 +125,11 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, M: int, N: int,
     return out
 
 
+def set_gemm_cta_cap(ctas: int) -> int:
+    """Caps the persistent grid of the GEMMs issued by this host thread (0 = no cap); returns the previous cap."""
+    return int(lib().xf_set_gemm_cta_cap(int(ctas)))
+
+
 def _feat_dtype(t: torch.Tensor) -> int:
     if t.dtype == torch.float32:
         return 1
