@@ -115,6 +115,24 @@ class CrossFusionBoxWrapper(nn.Module):
         return nn.Conv2d(in_channels=in_channels, out_channels=token_dim, kernel_size=(patch_h, patch_w),
                          stride=(patch_h, patch_w), bias=False)
 
+    # ---- FPN laterals folded into the back-projection ---------------------------------
+    def fuse_fpn_inner(self, fpn):
+        """`fpn`: the torchvision FeaturePyramidNetwork the fused maps feed (rcnn_to_wrap.backbone.fpn,
+        faster_rcnn_wrapper.py:419-421).  After this call every level computes its FPN lateral (inner 1x1 conv) inside
+        the back-projection GEMM, the [B, C, h, w] fused maps are never materialised, and `forward` runs the rest of the
+        FPN (top-down additions, 3x3 output convs, extra blocks) on the laterals instead of calling
+        `rcnn_model.apply_fpn`.  The FPN keeps owning its parameters (not re-registered here: state_dict unchanged).
+        Pass None to undo."""
+        if fpn is not None:
+            if len(fpn.inner_blocks) != len(self.fpn_features_idx):
+                raise ValueError("fuse_fpn_inner: the FPN must have one inner block per fused level")
+            for blk in fpn.inner_blocks:
+                conv = blk[0] if isinstance(blk, nn.Sequential) else blk
+                if (isinstance(blk, nn.Sequential) and len(blk) != 1) or not isinstance(conv, nn.Conv2d) or \
+                        conv.kernel_size != (1, 1) or conv.stride != (1, 1) or conv.groups != 1 or conv.bias is None:
+                    raise NotImplementedError("fuse_fpn_inner: inner blocks must be plain 1x1 convolutions with bias")
+        self.__dict__["_xf_fpn"] = fpn
+
     # ---- cached bf16 weight copies (cross_fusion/level_fn.py) ---------------------------------
     def invalidate_weight_cache(self):
         """Drops the cached bf16 weight copies; call after modifying parameters behind autograd's back (`p.data.<op>_()`)
@@ -129,7 +147,7 @@ class CrossFusionBoxWrapper(nn.Module):
 
     # ---- the hot path -----------------------------------------------------------------------
     def run_level(self, i: int, feat: torch.Tensor, language_f: torch.Tensor, lang_pad_mask, need_lang_out=False, out_stream=None,
-                  gemm_ctas: int = 0):
+                  gemm_ctas: int = 0, lateral_conv=None):
         """One FPN level: reference :180-212.  Returns (fused [B,C,h,w], fused language tokens or None)."""
         enc: CrossTransformerModuleBox = self.cross_fusion_encoders[i]
         t2f: RegroupPatchesLayerBox = self.tokens_to_features[i]
@@ -150,10 +168,12 @@ class CrossFusionBoxWrapper(nn.Module):
         cfg = LevelConfig(level=i, patch=p, num_heads=enc.num_heads, num_layers=enc.num_layers, training=self.training,
                           patch_dropout=float(enc.patch_dropout), token_dropout=float(enc.token_dropout),
                           backproj_dropout=float(t2f.back_dropout.p), seed=seed, need_lang_out=need_lang_out,
-                          out_stream=out_stream, gemm_ctas=gemm_ctas)
+                          out_stream=out_stream, gemm_ctas=gemm_ctas, lateral=lateral_conv is not None)
         params = [pe.weight, enc.image_kind_embedding, enc.lang_kind_embedding, enc.pos_embedding_layer.table(),
                   *enc.level_params(), enc.final_norm_layer.weight, enc.final_norm_layer.bias, t2f.linear.weight,
                   t2f.linear.bias]
+        if lateral_conv is not None:
+            params += [lateral_conv.weight, lateral_conv.bias]
         fused, lang_out = FusionLevelFunction.apply(cfg, feat, language_f, lang_pad_mask, *params)
         return fused, (lang_out if need_lang_out else None)
 
@@ -236,6 +256,14 @@ class CrossFusionBoxWrapper(nn.Module):
             while len(pending) >= depth:
                 pending.pop(0).synchronize()
         shares = self._sm_shares(features_dict["features"], language_f) if side is not None else None
+        fpn = self.__dict__.get("_xf_fpn")
+
+        def lat_conv(i):
+            if fpn is None:
+                return None
+            blk = fpn.inner_blocks[i]
+            return blk[0] if isinstance(blk, nn.Sequential) else blk
+
         for i, key in level_order:
             key = str(key)
             feat = features_dict["features"][key]
@@ -247,14 +275,14 @@ class CrossFusionBoxWrapper(nn.Module):
                 st.wait_stream(cur)
                 with torch.cuda.stream(st):
                     fused, fused_l_features = self.run_level(i, feat, language_f, lang_pad, need_lang_out, out_stream=cur,
-                                                             gemm_ctas=shares[i] if shares else 0)
+                                                             gemm_ctas=shares[i] if shares else 0, lateral_conv=lat_conv(i))
                 # Memory safety across streams without record_stream (whose deferred frees made the allocator's
                 # demand depend on host run-ahead): the outputs come from the caller stream's pool (out_stream) and
                 # are written on `st`, which waited for everything the caller had enqueued; the inputs, allocated on
                 # the caller's stream and read on `st`, are kept alive until the caller's stream has joined `st`.
                 keep_alive.append((feat, language_f, lang_pad))
             else:
-                fused, fused_l_features = self.run_level(i, feat, language_f, lang_pad, need_lang_out)
+                fused, fused_l_features = self.run_level(i, feat, language_f, lang_pad, need_lang_out, lateral_conv=lat_conv(i))
             if i == last_level:
                 lm_tokens = fused_l_features   # independent of the visiting order
             if self.multi_lm:
@@ -274,7 +302,13 @@ class CrossFusionBoxWrapper(nn.Module):
             ev.record(cur)
             self.__dict__["_xf_fwd_events"].append(ev)
             keep_alive.clear()   # the join is enqueued: later frees are ordered after the side streams' reads
-        features_dict = self.rcnn_model.apply_fpn(features_dict)
+        if fpn is not None:
+            # features_dict["features"][key] now holds the LATERALS: finish the FPN here (reference: rcnn_model.apply_fpn ->
+            # backbone.fpn(features), faster_rcnn_wrapper.py:171-174,419-421)
+            from ..obj_detection.fpn import fpn_from_laterals
+            features_dict["features"] = fpn_from_laterals(fpn, features_dict["features"])
+        else:
+            features_dict = self.rcnn_model.apply_fpn(features_dict)
         if "hand_boxes" in x:
             features_dict["hand_boxes"] = x["hand_boxes"]
         if "hand_poses" in x:

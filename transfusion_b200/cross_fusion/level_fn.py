@@ -54,6 +54,9 @@ class LevelConfig:
     # share of the SMs this level's persistent GEMM grids may occupy when the levels run concurrently on side streams
     # (0 = whole machine)
     gemm_ctas: int = 0
+    # the level's FPN lateral (inner 1x1 conv, C -> Co) is folded into the back-projection; the function then
+    # returns the [B, Co, h, w] lateral map instead of the fused [B, C, h, w] map and takes two more parameters
+    lateral: bool = False
 
     def stream(self, layer: int, site: int) -> int:
         return ((self.level * 16 + layer) * 64 + site) & 0xFFFFFFFF
@@ -71,6 +74,7 @@ def _dbg(name, t):
 N_HEAD_PARAMS = 4       # patch-embed weight, image_kind, lang_kind, pos table (buffer, no grad)
 N_LAYER_PARAMS = 12
 N_TAIL_PARAMS = 4       # final LN weight/bias, back-projection weight/bias
+N_LATERAL_PARAMS = 2    # optional: FPN inner 1x1 conv weight [Co, C, 1, 1] / bias [Co] folded into the back-projection (8f N1)
 
 
 N_CLUSTERS = 74  # CTA pairs on a 148-SM B200
@@ -137,7 +141,9 @@ class FusionLevelFunction(torch.autograd.Function):
 
         wpe, img_kind, lang_kind, pos_table = params[:N_HEAD_PARAMS]
         layer_params = [params[N_HEAD_PARAMS + i * N_LAYER_PARAMS: N_HEAD_PARAMS + (i + 1) * N_LAYER_PARAMS] for i in range(nl)]
-        lnf_w, lnf_b, wbp, bbp = params[N_HEAD_PARAMS + nl * N_LAYER_PARAMS:]
+        tail = params[N_HEAD_PARAMS + nl * N_LAYER_PARAMS:]
+        lnf_w, lnf_b, wbp, bbp = tail[:N_TAIL_PARAMS]
+        lat_w, lat_b = (tail[N_TAIL_PARAMS:] if cfg.lateral else (None, None))
 
         def empty(*shape, dtype=bf):
             return torch.empty(*shape, device=dev, dtype=dtype)
@@ -236,15 +242,33 @@ class FusionLevelFunction(torch.autograd.Function):
         rstdf = empty(B * n, dtype=torch.float32) if need_grad else None
         ops.layernorm_fwd(x, vis, lnf_w, lnf_b, meanf, rstdf, B * n, D, in_map=(n, S, 0), eps=LN_EPS,
                           drop_p=pd_back, drop_seed=seed, drop_stream=cfg.stream(0, SITE_BACKPROJ))
-        yb = empty(B * n, K)
-        ops.gemm(vis, wbp_b, yb, M=B * n, N=K, K=D, bias=bbp)
+        w2_b = wl_b = None
+        Co, Ko = C, K
+        if cfg.lateral:
+            # FPN lateral folded into the back-projection (both linear, nothing in between: utils.py:114-119 ->
+            # torchvision FeaturePyramidNetwork.inner_blocks[i], faster_rcnn_wrapper.py:419-421):
+            #   W2[(o,u,v), d] = sum_c Wl[o,c] Wbp[(c,u,v), d],   b2[(o,u,v)] = sum_c Wl[o,c] bbp[(c,u,v)] + bl[o]
+            # One weight-space GEMM per step ([Co, C] x [C, p^2 D]) replaces the [B,C,h,w] fused map, its fold pass and the
+            # 1x1 convolution over it; the token GEMM shrinks from N = C p^2 to N = Co p^2 (8x at C5).
+            Co = lat_w.shape[0]
+            Ko = Co * p * p
+            wl_b = empty(Co, C)
+            ops.cast_pad(lat_w.reshape(Co, C), wl_b, Co, C)
+            w2_b = empty(Co, p * p * D)
+            ops.gemm(wl_b, wbp_b.view(C, p * p * D), w2_b, M=Co, N=p * p * D, K=C, b_mn_major=True)
+            b2 = (lat_w.reshape(Co, C).float() @ bbp.reshape(C, p * p).float() + lat_b.float()[:, None]).reshape(Ko)   # [Co, p^2]: tiny, weight space
+            yb = empty(B * n, Ko)
+            ops.gemm(vis, w2_b.view(Ko, D), yb, M=B * n, N=Ko, K=D, bias=b2.detach())
+        else:
+            yb = empty(B * n, K)
+            ops.gemm(vis, wbp_b, yb, M=B * n, N=K, K=D, bias=bbp)
         _dbg("vis", vis); _dbg("yb", yb)
         if cfg.out_stream is not None:
             with torch.cuda.stream(cfg.out_stream):
-                fused = torch.empty(B, C, Hf, Wf, device=dev, dtype=feat_c.dtype)
+                fused = torch.empty(B, Co, Hf, Wf, device=dev, dtype=feat_c.dtype)
                 lang_out = torch.empty(B, L, D, device=dev, dtype=torch.float32) if cfg.need_lang_out else lang.new_zeros(())
         else:
-            fused = torch.empty(B, C, Hf, Wf, device=dev, dtype=feat_c.dtype)
+            fused = torch.empty(B, Co, Hf, Wf, device=dev, dtype=feat_c.dtype)
             lang_out = torch.empty(B, L, D, device=dev, dtype=torch.float32) if cfg.need_lang_out else lang.new_zeros(())
         ops.fold(yb, fused, p)
         if cfg.need_lang_out:
@@ -262,6 +286,7 @@ class FusionLevelFunction(torch.autograd.Function):
             ctx.saved_layers = saved_layers
             ctx.lw = lw
             ctx.wpe_b, ctx.wbp_b = wpe_b, wbp_b
+            ctx.lateral = (w2_b, wl_b, Co, Ko)
             ctx.param_refs = params
             ctx.needs = (feat.requires_grad, lang.requires_grad)
             ctx.feat_dtype = feat_c.dtype
@@ -290,7 +315,10 @@ class FusionLevelFunction(torch.autograd.Function):
         kpm = ctx.kpm
         wpe, img_kind, lang_kind, pos_table = params[:N_HEAD_PARAMS]
         layer_params = [params[N_HEAD_PARAMS + i * N_LAYER_PARAMS: N_HEAD_PARAMS + (i + 1) * N_LAYER_PARAMS] for i in range(nl)]
-        lnf_w, lnf_b, wbp, bbp = params[N_HEAD_PARAMS + nl * N_LAYER_PARAMS:]
+        tail = params[N_HEAD_PARAMS + nl * N_LAYER_PARAMS:]
+        lnf_w, lnf_b, wbp, bbp = tail[:N_TAIL_PARAMS]
+        lat_w, lat_b = (tail[N_TAIL_PARAMS:] if cfg.lateral else (None, None))
+        w2_b, wl_b, Co, Ko = ctx.lateral
 
         def empty(*shape, dtype=bf):
             return torch.empty(*shape, device=dev, dtype=dtype)
@@ -333,12 +361,35 @@ class FusionLevelFunction(torch.autograd.Function):
         d_fused_c = d_fused.contiguous()
         if d_fused_c.dtype not in (torch.float32, torch.bfloat16):
             d_fused_c = d_fused_c.float()
-        dyb = empty(B * n, K)
+        g_lat_w = g_lat_b = None
+        dyb = empty(B * n, Ko)
         ops.patchify(d_fused_c, p, dyb)
-        g_bbp = zeros(K); ops.colsum(dyb, g_bbp, B * n, K)
-        g_wbp = zeros(K, D); _wgrad(dyb, ctx.vis, g_wbp, K, D, B * n, ctas=cfg.gemm_ctas)
         dvis = empty(B * n, D)
-        ops.gemm(dyb, ctx.wbp_b, dvis, M=B * n, N=D, K=K, b_mn_major=True)
+        if cfg.lateral:
+            # gradients of the folded weights, then the chain rule back to (Wl, bl) and (Wbp, bbp) in weight space
+            g_b2 = torch.zeros(Ko, device=dev, dtype=f32); ops.colsum(dyb, g_b2, B * n, Ko)
+            g_w2 = torch.zeros(Ko, D, device=dev, dtype=f32); _wgrad(dyb, ctx.vis, g_w2, Ko, D, B * n, ctas=cfg.gemm_ctas)
+            ops.gemm(dyb, w2_b.view(Ko, D), dvis, M=B * n, N=D, K=Ko, b_mn_major=True)
+            pp = p * p
+            g_w2_b = empty(Co, pp * D)
+            ops.cast_pad(g_w2.view(Co, pp * D), g_w2_b, Co, pp * D)
+            # dWl[o,c] = sum_{u,v,d} dW2[(o,u,v),d] Wbp[(c,u,v),d]  (+ the bias term below)
+            g_lat_w = torch.zeros(Co, C, device=dev, dtype=f32)
+            ops.gemm(g_w2_b, ctx.wbp_b.view(C, pp * D), g_lat_w, M=Co, N=C, K=pp * D, accumulate=True,
+                     split_k=max(1, min(32, (pp * D) // 512)))   # few output tiles, long K: spread it over the SMs
+            # dWbp[(c,u,v),d] = sum_o Wl[o,c] dW2[(o,u,v),d]
+            g_wbp = zeros(K, D)
+            ops.gemm(wl_b, g_w2_b, g_wbp.view(C, pp * D), M=C, N=pp * D, K=Co, a_mn_major=True, b_mn_major=True, accumulate=True)
+            gb2 = g_b2.view(Co, pp)
+            g_lat_w += gb2 @ bbp.detach().reshape(C, pp).float().t()            # tiny weight-space terms ([Co, p^2] x [p^2, C])
+            g_lat_b = gb2.sum(1)
+            g_bbp = zeros(K)
+            g_bbp.view(C, pp).copy_(lat_w.detach().reshape(Co, C).float().t() @ gb2)
+            g_lat_w = g_lat_w.view_as(lat_w)
+        else:
+            g_bbp = zeros(K); ops.colsum(dyb, g_bbp, B * n, K)
+            g_wbp = zeros(K, D); _wgrad(dyb, ctx.vis, g_wbp, K, D, B * n, ctas=cfg.gemm_ctas)
+            ops.gemm(dyb, ctx.wbp_b, dvis, M=B * n, N=D, K=K, b_mn_major=True)
         del dyb
         # ---- final LN backward into the visual rows of dz; language rows from d_lang_out (or zero)
         dx = empty(B, S, D)
@@ -354,6 +405,8 @@ class FusionLevelFunction(torch.autograd.Function):
         base_tail = N_HEAD_PARAMS + nl * N_LAYER_PARAMS
         grads[base_tail + 0], grads[base_tail + 1] = g_lnf_w, g_lnf_b
         grads[base_tail + 2], grads[base_tail + 3] = g_wbp, g_bbp
+        if cfg.lateral:   # FPN parameters: not part of the level's arena / bucket
+            grads[base_tail + 4], grads[base_tail + 5] = g_lat_w, g_lat_b
         del dvis
 
         # scratch of the 5-unit attention backward (E = scale dS^T as bf16 [B, H, S, S]); one buffer for all layers
