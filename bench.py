@@ -334,6 +334,27 @@ def run_ours(args):
         if k.endswith("heatmap_token"):
             p.requires_grad_(False)  # registered but unused in forward (reference cross_f_box_layers.py:43)
     net = model
+    fpn = None
+    if args.with_fpn != "none":
+        # SURVEY 8f N1 measurement: a stock torchvision FPN (256 channels + max-pool level) consumes the fused maps, either
+        # as the reference does (fused [B,C,h,w] maps -> inner 1x1 convs -> ...) or with the laterals folded into the
+        # back-projection GEMM (fuse_fpn_inner).  Everything after the laterals is identical library code in both arms.
+        from collections import OrderedDict
+        from torchvision.ops import FeaturePyramidNetwork
+        from torchvision.ops.feature_pyramid_network import LastLevelMaxPool
+        torch.manual_seed(5)
+        torch.backends.cudnn.allow_tf32 = True   # the detector's own 3x3 convolutions: library code, identical in both arms
+        fpn = FeaturePyramidNetwork(w["channels"], 256, extra_blocks=LastLevelMaxPool()).to(dev)
+        if args.with_fpn in ("fused", "laterals"):
+            model.fuse_fpn_inner(fpn)
+            if args.with_fpn == "laterals":   # stop at the laterals: isolates what the fusion path itself gains from N1
+                import transfusion_b200.obj_detection.fpn as _fpn_mod
+                _fpn_mod.fpn_from_laterals = lambda _f, lat: lat
+        else:
+            def apply_fpn(d, _fpn=fpn):
+                d["features"] = _fpn(OrderedDict((k, d["features"][k].float()) for k in sorted(d["features"], key=int)))
+                return d
+            model.rcnn_model.apply_fpn = apply_fpn
     reducer = None
     if world > 1 and train:
         # same initial weights on every rank (seeded construction); gradients averaged per level bucket,
@@ -348,6 +369,13 @@ def run_ours(args):
     gen = torch.Generator(device=dev).manual_seed(99 + rank)
     cot = {k: torch.randn(v.shape, device=dev, dtype=torch.float32, generator=gen) for k, v in feats_d.items()}
     keys = sorted(feats_d, key=int)
+    if fpn is not None:   # the outputs are the FPN maps (256 channels per level + the pooled level)
+        model.rcnn_model.features = feats_d
+        with torch.no_grad():
+            probe = net({"image": None, "language_f": (lang_d, mask_d)})["features"]
+        keys = list(probe.keys())
+        cot = {k: torch.randn(v.shape, device=dev, dtype=torch.float32, generator=gen) for k, v in probe.items()}
+        del probe
 
     acc_n = max(1, args.accumulate)
 
@@ -613,7 +641,7 @@ def run_ours(args):
                 "config": config_dict(args, w, B, L, world, train),
                 "notes": {"level_streams": "independent FPN levels overlap on side streams in the timed runs; the `kernels` "
                                            "breakdown is taken with the levels serialised",
-                          "accumulate_grad_batches": args.accumulate, "grad_allreduce": "fp32" if args.grad_compress == "none" else args.grad_compress,
+                          "accumulate_grad_batches": args.accumulate, "fpn": args.with_fpn, "grad_allreduce": "fp32" if args.grad_compress == "none" else args.grad_compress,
                           "attn_bwd": "5-unit schedule (scores once; bf16 [B,H,S,S] scratch)" if os.environ.get("XF_ATTN_BWD_WS", "1") != "0"
                                       else "3 on-chip passes (8 units)"},
                 "clocks": clocks, "gpu_launches": int(launches),
@@ -716,6 +744,10 @@ def main():
                     help="samples per CPU step; 0 = auto (1 for the in-line cpu_baseline, sized for ~150 s total in --impl reference)")
     ap.add_argument("--accumulate", type=int, default=1, help="accumulate_grad_batches: all-reduce every N-th micro-step")
     ap.add_argument("--no-bf16-e2e", action="store_true", help="skip the extra end-to-end pass with bf16 feature maps")
+    ap.add_argument("--with-fpn", default="none", choices=["none", "stock", "fused", "laterals"],
+                    help="append a torchvision FPN to the step: 'stock' = on the fused maps (reference data flow), 'fused' = "
+                         "laterals folded into the back-projection GEMM (SURVEY 8f N1), 'laterals' = the same but the step "
+                         "ends at the [B,256,h,w] laterals (no cuDNN convolutions in the timed region)")
     ap.add_argument("--grad-compress", default="none", choices=["none", "bf16"],
                     help="N > 1: exchange the gradient arenas as bf16 (default: fp32 like the reference's DDP)")
     ap.add_argument("--bf16-e2e", action="store_true", help="run the extra bf16-feature end-to-end pass for N > 1 too")
