@@ -1,0 +1,105 @@
+"""GPU: SURVEY 8f N2 -- the MiniLM-L12-H384 language-context encoder (narr_pooling_layers.py:160-202) on the fusion path's
+kernels against HuggingFace's own BertModel in fp32 on the same random-init weights (no checkpoint offline), ragged
+attention masks, and the trainable out_mlp Linear(384 -> D) forward + backward.
+
+Tolerance: rel-Frobenius <= 1.5e-2 on the valid tokens after 12 layers.  The kernels keep every activation in bf16 between
+launches (the fusion stack's layout: 5e-3 after its 4 layers, growing ~ sqrt(layers)), whereas torch.autocast -- whose own
+error on the same inputs is asserted to stay below ours, 2.7e-3 -- keeps the residual stream and the LayerNorms in fp32.
+Inference (eval) only: in training the reference leaves the encoder's LayerNorm parameters trainable and its dropouts on
+(freeze_all_but_bn, modeling/commons.py:33-42), which needs the encoder backward; bert_encoder_forward raises there."""
+import pytest
+import torch
+
+from tests.golden_utils import rel_fro
+from transfusion_b200 import _lib
+from transfusion_b200.narration_embeds import SBertTokensXf, XfLinear, bert_encoder_forward
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _minilm(layers=12):
+    from transformers import BertConfig, BertModel
+    cfg = BertConfig(vocab_size=30522, hidden_size=384, num_hidden_layers=layers, num_attention_heads=12, intermediate_size=1536,
+                     max_position_embeddings=512)   # sentence-transformers/all-MiniLM-L12 geometry (run_experiment.py:45)
+    torch.manual_seed(0)
+    m = BertModel(cfg, add_pooling_layer=False).eval().to(DEV)
+    for p in m.parameters():
+        p.requires_grad_(False)     # freeze_all_but_bn (narr_pooling_layers.py:87): the shipped, frozen encoder
+    return m
+
+
+@pytest.mark.parametrize("B,L,lens", [(4, 64, [64, 33, 1, 50]), (3, 17, [17, 9, 17]), (2, 128, [128, 77])])
+def test_minilm_encoder_matches_huggingface(B, L, lens):
+    bert = _minilm()
+    g = torch.Generator(device=DEV).manual_seed(1)
+    ids = torch.randint(0, 30522, (B, L), device=DEV, generator=g)
+    am = torch.zeros(B, L, dtype=torch.long, device=DEV)
+    for b, n in enumerate(lens):
+        am[b, :n] = 1
+    with torch.no_grad():
+        ref = bert(input_ids=ids, attention_mask=am).last_hidden_state
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            ac = bert(input_ids=ids, attention_mask=am).last_hidden_state.float()
+    n0 = _lib.lib().xf_launch_count()
+    got = bert_encoder_forward(bert, ids, am)
+    assert _lib.lib().xf_launch_count() - n0 >= 12 * 7
+    valid = am.bool()
+    e_ac = rel_fro(ac[valid], ref[valid])
+    e = rel_fro(got[valid], ref[valid])     # padded query rows are don't-care (the fusion path masks them as keys)
+    assert e < 1.5e-2, (e, e_ac)
+    assert e_ac < e      # documents the gap to an fp32 residual stream
+    # second call: cached bf16 weights, identical result
+    assert torch.equal(bert_encoder_forward(bert, ids, am), got)
+
+
+def test_out_mlp_and_token_wrapper_forward_backward():
+    bert = _minilm(layers=2)
+    torch.manual_seed(2)
+    out_mlp = torch.nn.Linear(384, 896).to(DEV)
+    mod = SBertTokensXf(bert, out_mlp).train()
+    bert.eval()          # the HF reference call below must not apply dropout; the CUDA encoder forward is the eval forward
+    B, L = 3, 20
+    ids = torch.randint(0, 30522, (B, L), device=DEV)
+    am = torch.ones(B, L, dtype=torch.long, device=DEV)
+    am[2, 11:] = 0
+    emb, att, mask = mod({"input_ids": ids, "attention_mask": am}, pad_mask=True)
+    assert emb.shape == (B, L, 896) and att is None and torch.equal(mask, am)
+    with torch.no_grad():
+        tok = bert(input_ids=ids, attention_mask=am).last_hidden_state
+    ref = torch.nn.functional.linear(tok, out_mlp.weight, out_mlp.bias)
+    assert rel_fro(emb[am.bool()], ref[am.bool()]) < 1e-2
+    cot = torch.randn_like(emb) * am[..., None]
+    (emb * cot).sum().backward()
+    gw, gb = out_mlp.weight.grad.clone(), out_mlp.bias.grad.clone()
+    w2 = out_mlp.weight.detach().clone().requires_grad_(True)
+    b2 = out_mlp.bias.detach().clone().requires_grad_(True)
+    (torch.nn.functional.linear(tok, w2, b2) * cot).sum().backward()
+    assert rel_fro(gw, w2.grad) < 1e-2 and rel_fro(gb, b2.grad) < 1e-2
+
+
+def test_trainable_encoder_is_rejected_loudly():
+    bert = _minilm(layers=1)
+    for mod_ in bert.modules():
+        if isinstance(mod_, torch.nn.LayerNorm):
+            for p in mod_.parameters():
+                p.requires_grad_(True)    # what freeze_all_but_bn leaves trainable in the reference
+    ids = torch.randint(0, 30522, (1, 8), device=DEV)
+    with pytest.raises(NotImplementedError):
+        with torch.enable_grad():
+            bert_encoder_forward(bert, ids)
+
+
+def test_xflinear_input_gradient_and_cpu_rejection():
+    torch.manual_seed(3)
+    lin = XfLinear(384, 712).to(DEV)
+    x = torch.randn(5, 9, 384, device=DEV, requires_grad=True)
+    y = lin(x)
+    cot = torch.randn_like(y)
+    (y * cot).sum().backward()
+    xr = x.detach().clone().requires_grad_(True)
+    (torch.nn.functional.linear(xr, lin.weight, lin.bias) * cot).sum().backward()
+    assert rel_fro(y, torch.nn.functional.linear(xr, lin.weight, lin.bias)) < 1e-2
+    assert rel_fro(x.grad, xr.grad) < 1e-2
+    with pytest.raises(RuntimeError):
+        XfLinear(8, 8)(torch.randn(2, 8))
