@@ -83,7 +83,7 @@ typedef struct XfGemm {
    * a + i * a_bs1 + j * a_bs2 (elements), B and out likewise (residual / preact_out / dact_in use the out strides).
    * The two-level index lets a per-(sample, head) problem address token-major [B*S, H*dp] tensors: bs1 = S * ld,
    * bs2 = dp.  Rows / columns outside M, N, K are zero-filled per entry (TMA bounds), so neighbouring entries may
-   * overlap in memory.  Specialised epilogues only; no split_k. */
+   * overlap in memory.  Specialised epilogues only (split_k: the fp32 reduction epilogue, as without batching). */
   int32_t batch1, batch2;
   int64_t a_bs1, a_bs2, b_bs1, b_bs2, out_bs1, out_bs2;
 } XfGemm;
@@ -258,6 +258,22 @@ int64_t xf_attn_bwd_workspace_bytes(int B, int H, int Sq, int Sk);
  * visual rows of d(sequence) (cross_f_box_layers.py:72-74 backward; colsum = image_kind_embedding grad). */
 int xf_rows_gather(const void* in_bf16, int64_t ldi, void* out_bf16, int64_t ldo, int rows, int D, int rin, int rout, int roff,
                    float* colsum, float drop_p, uint32_t drop_seed, uint32_t drop_stream, xf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * fp32-tolerance mode helpers (csrc/fp32_mode.cu; the reference's Ego4Dv2 config runs precision 32,
+ * ego_nao_res50_ego4dv2.yml:124).  xf_split3 writes the 3-term bf16 split of an fp32 [rows, cols] matrix concatenated
+ * along K as [rows, 6*cols]: pattern 0 = (a0 a0 a0 a1 a1 a2) for the A side, 1 = (b0 b1 b2 b0 b1 b0) for the B side, so
+ * xf_gemm on the two (K' = 6K, fp32 output) returns the fp32-accurate product on the bf16 tensor cores.  act = 1 applies the
+ * exact GELU(erf) to the source first; bias_cols = 8 appends eight columns that carry a bias through the GEMM (A side:
+ * 1 1 1 0.., B side: the 3-term split of bias[row]), so the split-K fp32-reduction epilogue suffices: split-K matters
+ * because the tensor core truncates when it adds into its fp32 accumulator -- a 6K-long chain loses ~1e-5 relative, twelve
+ * short chains summed by round-to-nearest reductions ~1e-6.
+ * xf_softmax_rows_f32: in-place softmax_k(scale * s[b,h,q,k]) over k < Sk of a padded [B,H,Sq,Sp] fp32 score tensor with
+ * key padding kpm[B,Sk] (nonzero = masked); pad columns come out 0 (torch18_adapters.py:578-597,789-798).
+ * ------------------------------------------------------------------------------------------ */
+int xf_split3(const float* src, int64_t lds, int rows, int cols, void* dst_bf16, int pattern, int act, int bias_cols,
+              const float* bias, xf_stream_t stream);
+int xf_softmax_rows_f32(float* s, int B, int H, int Sq, int Sk, int Sp, const uint8_t* kpm, float scale, xf_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused optimizer step over the path's parameters: global-norm clipping (Lightning gradient_clip_val,

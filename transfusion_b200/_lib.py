@@ -166,7 +166,7 @@ EXPORTS = [
     "xf_layernorm_fwd", "xf_layernorm_bwd", "xf_colsum", "xf_cast_pad", "xf_cast_pad_multi", "xf_unpad_add", "xf_bf16_to_f32",
     "xf_attn_delta", "xf_attn_fwd", "xf_attn_bwd", "xf_attn_bwd_workspace_bytes", "xf_rows_gather",
     "xf_lm_pool_fwd", "xf_lm_pool_bwd", "xf_rowln_fwd", "xf_rowln_bwd", "xf_small_linear_fwd", "xf_small_linear_bwd",
-    "xf_grad_sqnorm", "xf_radam_step",
+    "xf_grad_sqnorm", "xf_radam_step", "xf_split3", "xf_softmax_rows_f32",
     "xf_debug_dropout_mask", "xf_debug_attn_dropout_mask",
 ]
 

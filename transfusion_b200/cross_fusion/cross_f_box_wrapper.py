@@ -36,8 +36,14 @@ def _default_pooling_factory(narr_embed_args, cross_layer_args):
 
 
 class CrossFusionBoxWrapper(nn.Module):
-    def __init__(self, rcnn_model, cross_layer_args, narr_embed_args, criterion=None, narr_pooling_layer=None):
+    def __init__(self, rcnn_model, cross_layer_args, narr_embed_args, criterion=None, narr_pooling_layer=None, precision=None):
+        """precision: None / "bf16" = the tensor-core path (bf16 operands, fp32 accumulate; training and inference);
+        "fp32" (or XF_PRECISION=fp32) = the forward-only fp32-tolerance mode of cross_fusion/level_fp32.py (3-way bf16 split
+        GEMMs, ~1e-5 relative to the fp32 reference; the reference's Ego4Dv2 config runs precision 32)."""
         super().__init__()
+        self.precision = precision or _os.environ.get("XF_PRECISION", "bf16")
+        if self.precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
         self.rcnn_model = rcnn_model
         self.narr_embed_args = narr_embed_args
         if "final_ln" in cross_layer_args["args"]:  # compatibility shim, reference :49-52
@@ -172,6 +178,12 @@ class CrossFusionBoxWrapper(nn.Module):
         params = [pe.weight, enc.image_kind_embedding, enc.lang_kind_embedding, enc.pos_embedding_layer.table(),
                   *enc.level_params(), enc.final_norm_layer.weight, enc.final_norm_layer.bias, t2f.linear.weight,
                   t2f.linear.bias]
+        if self.precision == "fp32":
+            if lateral_conv is not None:
+                raise NotImplementedError("precision='fp32' does not combine with fuse_fpn_inner")
+            from .level_fp32 import fusion_level_forward_fp32
+            fused, lang_out = fusion_level_forward_fp32(cfg, feat, language_f, lang_pad_mask, *params)
+            return fused.to(feat.dtype) if feat.dtype in (torch.float32, torch.bfloat16) else fused, (lang_out if need_lang_out else None)
         if lateral_conv is not None:
             params += [lateral_conv.weight, lateral_conv.bias]
         fused, lang_out = FusionLevelFunction.apply(cfg, feat, language_f, lang_pad_mask, *params)

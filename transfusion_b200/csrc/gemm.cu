@@ -715,7 +715,6 @@ extern "C" int xf_gemm(const XfGemm* g, xf_stream_t stream_) {
   const int nb1 = g->batch1 > 0 ? g->batch1 : 0, nb2 = g->batch2 > 0 ? g->batch2 : (nb1 > 0 ? 1 : 0);
   const bool batched = nb1 > 0;
   if (batched && (nb1 > 32767 || nb2 > 65535)) return fail(-9, "xf_gemm: batch counts out of range");
-  if (batched && split_k > 1) return fail(-9, "xf_gemm: batched GEMM does not combine with split_k");
 
   // CTA pairs (cta_group::2) unless disabled or the problem is a single small tile
   int cg = g->cta_group == 1 ? 1 : 2;

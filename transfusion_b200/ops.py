@@ -424,3 +424,25 @@ def debug_attn_dropout_mask(p: float, seed: int, stream: int, BH: int, Sq: int, 
     check(lib().xf_debug_attn_dropout_mask(C.c_float(p), C.c_uint32(seed), C.c_uint32(stream), BH, Sq, Sk, _ptr(out), _stream()),
           "xf_debug_attn_dropout_mask")
     return out
+
+
+# ---- fp32-tolerance mode helpers (csrc/fp32_mode.cu) -------------------------------------------------------------------
+def split3(src: torch.Tensor, pattern: int, act: int = 0, bias: Optional[torch.Tensor] = None, bias_cols: int = 0) -> torch.Tensor:
+    """fp32 [rows, cols] (row stride src.stride(0)) -> bf16 [rows, 6*cols + bias_cols]: the 3-term split concatenated along
+    K (pattern 0: A side, 1: B side); xf_gemm on an A-side and a B-side operand gives the fp32-accurate product.
+    bias_cols = 8 appends the bias-carrying columns (A side: ones; B side: the split of bias[row]); act = 1: GELU first."""
+    _req(src, torch.float32, "src")
+    rows, cols = src.shape
+    dst = torch.empty(rows, 6 * cols + bias_cols, device=src.device, dtype=torch.bfloat16)
+    with _Prof("fp32_mode", 0.0, 16.0 * rows * cols):
+        check(lib().xf_split3(_ptr(src), C.c_int64(src.stride(0)), rows, cols, _ptr(dst), pattern, act, bias_cols, _ptr(bias),
+                              _stream()), "xf_split3")
+    return dst
+
+
+def softmax_rows_f32(s: torch.Tensor, Sk: int, kpm: Optional[torch.Tensor], scale: float):
+    """in place on fp32 [B, H, Sq, Sp]"""
+    _req(s, torch.float32, "s")
+    B, H, Sq, Sp = s.shape
+    with _Prof("fp32_mode", 0.0, 8.0 * s.numel()):
+        check(lib().xf_softmax_rows_f32(_ptr(s), B, H, Sq, Sk, Sp, _ptr(kpm), C.c_float(scale), _stream()), "xf_softmax_rows_f32")
