@@ -100,7 +100,9 @@ int xf_set_gemm_cta_cap(int ctas);
  * Token matrix T[(b,i,j), (c,u,v)] <-> feature map F[b,c,i*p+u,j*p+v].
  * xf_patchify replaces the im2col of nn.Conv2d(k=stride=p) (cross_f_box_wrapper.py:268-274) and
  * patchify_image(.,1,1) (utils.py:35-39); xf_fold replaces regroup_patches / F.fold
- * (utils.py:42-46).  Each is the other's backward.  feat_dtype: 0 bf16, 1 fp32.
+ * (utils.py:42-46).  Each is the other's backward.  feat_dtype: 0 bf16, 1 fp32; + 4 = the map is stored channels_last
+ * (NHWC memory: F[b, h, w, c], torch.channels_last), SURVEY 8f N3 -- a channels_last backbone feeds the patch-embed and receives
+ * the fused map without any layout conversion pass.
  * ------------------------------------------------------------------------------------------ */
 int xf_patchify(const void* feat, int feat_dtype, void* tok_bf16, int64_t tok_ld, int B, int C, int H, int W, int p,
                 xf_stream_t stream);

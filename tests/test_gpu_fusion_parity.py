@@ -177,3 +177,30 @@ def test_train_mode_dropout_is_reproducible_per_seed():
     # weight gradients accumulate with fp32 atomics (split-K): equal up to summation order
     assert rel_fro(ga, gb) < 1e-5
     assert not torch.equal(a, c)
+
+
+def test_channels_last_feature_maps_in_and_out():
+    """channels_last maps from a channels_last backbone go through the module without a layout conversion:
+    same numbers as with NCHW maps, the fused maps and the input gradients come back channels_last."""
+    m = build_module(256, [(16, 24), (8, 12)], [32, 64], [2, 1], [1, 1], 4, seed=61)
+    m.train()
+    g = torch.Generator().manual_seed(62)
+    feats = {"0": torch.relu(torch.randn(2, 32, 16, 24, generator=g)), "1": torch.relu(torch.randn(2, 64, 8, 12, generator=g))}
+    lang = 0.5 * torch.randn(2, 10, 256, generator=g)
+    mask = torch.ones(2, 10, dtype=torch.int64)
+    outs, grads = [], []
+    for fmt in (torch.contiguous_format, torch.channels_last):
+        f_in = {k: v.cuda().contiguous(memory_format=fmt).requires_grad_(True) for k, v in feats.items()}
+        out, _ = run_module(m, f_in, lang.cuda(), mask.cuda())
+        for k in out:
+            assert out[k].is_contiguous(memory_format=fmt)
+        m.zero_grad(set_to_none=True)
+        sum(o.float().pow(2).sum() for o in out.values()).backward()
+        outs.append({k: v.detach().float().cpu() for k, v in out.items()})
+        grads.append({k: v.grad.float().cpu() for k, v in f_in.items()})
+        if fmt == torch.channels_last:
+            for k, v in f_in.items():
+                assert v.grad.is_contiguous(memory_format=torch.channels_last)
+    for k in outs[0]:
+        assert torch.equal(outs[0][k], outs[1][k])
+        assert rel_fro(grads[1][k], grads[0][k]) < 1e-5   # split-K atomics reorder fp32 sums upstream of this gradient

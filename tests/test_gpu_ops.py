@@ -319,6 +319,24 @@ def test_patchify_fold_bit_exact(B, C, H, W, p, dt):
     assert torch.equal(out.float(), f.bfloat16().float())  # fold(patchify(x)) = bf16(x): a pure permutation
 
 
+@pytest.mark.parametrize("B,C,H,W,p,dt", [(2, 256, 16, 24, 4, torch.float32), (2, 70, 12, 20, 2, torch.bfloat16),
+                                          (3, 2048, 6, 8, 1, torch.float32), (1, 48, 16, 272, 4, torch.bfloat16)])
+def test_patchify_fold_channels_last_bit_exact(B, C, H, W, p, dt):
+    """channels_last (NHWC memory) maps are read and written in place of an NCHW conversion pass."""
+    torch.manual_seed(19)
+    f = torch.randn(B, C, H, W, device=DEV).to(dt).contiguous(memory_format=torch.channels_last)
+    assert not f.is_contiguous() or C == 1
+    gh, gw = H // p, W // p
+    tok = torch.empty(B * gh * gw, C * p * p, device=DEV, dtype=torch.bfloat16)
+    ops.patchify(f, p, tok)
+    ref = f.float().reshape(B, C, gh, p, gw, p).permute(0, 2, 4, 1, 3, 5).reshape(B * gh * gw, C * p * p).bfloat16()
+    assert torch.equal(tok, ref)
+    out = torch.zeros(B, C, H, W, device=DEV, dtype=dt).contiguous(memory_format=torch.channels_last)
+    ops.fold(tok, out, p)
+    assert out.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(out.float(), f.bfloat16().float())
+
+
 def test_small_kernels():
     torch.manual_seed(10)
     x = torch.randn(1000, 2688, device=DEV).bfloat16()

@@ -148,9 +148,13 @@ class FusionLevelFunction(torch.autograd.Function):
         def empty(*shape, dtype=bf):
             return torch.empty(*shape, device=dev, dtype=dtype)
 
-        feat_c = feat.contiguous()
+        # channels_last maps (a channels_last backbone) are consumed and produced as they are: the layout
+        # kernels read / write NHWC memory directly, no conversion pass; any other non-contiguous layout is made NCHW
+        cl = feat.dim() == 4 and not feat.is_contiguous() and feat.is_contiguous(memory_format=torch.channels_last)
+        feat_c = feat if cl else feat.contiguous()
         if feat_c.dtype not in (torch.float32, torch.bfloat16):
             feat_c = feat_c.float()
+        mem_fmt = torch.channels_last if cl else torch.contiguous_format
         lang_c = lang.contiguous().float()
         kpm = None
         if key_pad is not None:
@@ -265,10 +269,10 @@ class FusionLevelFunction(torch.autograd.Function):
         _dbg("vis", vis); _dbg("yb", yb)
         if cfg.out_stream is not None:
             with torch.cuda.stream(cfg.out_stream):
-                fused = torch.empty(B, Co, Hf, Wf, device=dev, dtype=feat_c.dtype)
+                fused = torch.empty(B, Co, Hf, Wf, device=dev, dtype=feat_c.dtype, memory_format=mem_fmt)
                 lang_out = torch.empty(B, L, D, device=dev, dtype=torch.float32) if cfg.need_lang_out else lang.new_zeros(())
         else:
-            fused = torch.empty(B, Co, Hf, Wf, device=dev, dtype=feat_c.dtype)
+            fused = torch.empty(B, Co, Hf, Wf, device=dev, dtype=feat_c.dtype, memory_format=mem_fmt)
             lang_out = torch.empty(B, L, D, device=dev, dtype=torch.float32) if cfg.need_lang_out else lang.new_zeros(())
         ops.fold(yb, fused, p)
         if cfg.need_lang_out:
@@ -290,6 +294,7 @@ class FusionLevelFunction(torch.autograd.Function):
             ctx.param_refs = params
             ctx.needs = (feat.requires_grad, lang.requires_grad)
             ctx.feat_dtype = feat_c.dtype
+            ctx.mem_fmt = mem_fmt
         return fused, lang_out
 
     @staticmethod
@@ -358,7 +363,8 @@ class FusionLevelFunction(torch.autograd.Function):
             if isinstance(d_lang_out, torch.Tensor) and d_lang_out.is_cuda:
                 d_lang_out.record_stream(cur_stream)
         # ---- fold^T, back-projection
-        d_fused_c = d_fused.contiguous()
+        d_cl = d_fused.dim() == 4 and not d_fused.is_contiguous() and d_fused.is_contiguous(memory_format=torch.channels_last)
+        d_fused_c = d_fused if d_cl else d_fused.contiguous()
         if d_fused_c.dtype not in (torch.float32, torch.bfloat16):
             d_fused_c = d_fused_c.float()
         g_lat_w = g_lat_b = None
@@ -488,7 +494,7 @@ class FusionLevelFunction(torch.autograd.Function):
         if ctx.needs[0]:
             dtok = empty(B * n, K)
             ops.gemm(dz0v, ctx.wpe_b, dtok, M=B * n, N=K, K=D, b_mn_major=True)
-            d_feat = torch.empty(B, C, Hf, Wf, device=dev, dtype=ctx.feat_dtype)
+            d_feat = torch.empty(B, C, Hf, Wf, device=dev, dtype=ctx.feat_dtype, memory_format=ctx.mem_fmt)
             ops.fold(dtok, d_feat, p)
         grads[0] = g_wpe.view_as(wpe)
         grads[1] = g_img_kind.view_as(img_kind)

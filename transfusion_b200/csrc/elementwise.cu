@@ -252,6 +252,74 @@ patchify_fold_vec8h_kernel(__nv_bfloat16* __restrict__ feat, __nv_bfloat16* __re
   }
 }
 
+// channels_last (NHWC memory) feature maps -- SURVEY 8f N3: a channels_last backbone feeds the patch-embed without an
+// NCHW conversion pass, and the fused map goes back out in channels_last for the detector's cuDNN convolutions.
+//   tok[(b,i,j), c*p*p + u*p + v]  <->  F_nhwc[b, i*p+u, j*p+v, c]
+// A CTA moves 32 tokens (along j) x 32 channels x p*p positions through shared memory: the feature side is accessed in
+// runs along c, the token side in runs of 32*p*p consecutive k.
+template <typename FT, int P, bool FOLD>
+__global__ void __launch_bounds__(256)
+patchify_fold_nhwc_kernel(FT* __restrict__ feat, __nv_bfloat16* __restrict__ tok, int B, int Cc, int H, int W, long long tok_ld) {
+  constexpr int PP = P * P;
+  constexpr int TC = 32;                      // channels per tile
+  constexpr int TJ = P >= 4 ? 16 : 32;        // tokens per tile (static shared memory stays under 48 KB)
+  __shared__ float tile[TJ][TC][PP + 1];      // +1: conflict-free transposed access
+  const int gh = H / P, gw = W / P;
+  const int jt = (gw + TJ - 1) / TJ;
+  int bid = blockIdx.x;
+  const int j0 = (bid % jt) * TJ; bid /= jt;
+  const int i = bid % gh; bid /= gh;
+  const int b = bid;
+  const int c0 = blockIdx.y * TC;
+  const long long row0 = (static_cast<long long>(b) * gh + i) * gw + j0;
+  constexpr int TOTAL = TJ * TC * PP;
+  auto feat_at = [&](int jl, int cl, int uv) -> FT* {
+    const int u = uv / P, v = uv % P;
+    return feat + ((static_cast<long long>(b) * H + i * P + u) * W + (j0 + jl) * P + v) * Cc + c0 + cl;
+  };
+  if (!FOLD) {
+    for (int t = threadIdx.x; t < TOTAL; t += 256) {      // c fastest: coalesced along the channel axis
+      const int cl = t % TC, uv = (t / TC) % PP, jl = t / (TC * PP);
+      float x = 0.f;
+      if (j0 + jl < gw && c0 + cl < Cc) x = to_f32<FT>(*feat_at(jl, cl, uv));
+      tile[jl][cl][uv] = x;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < TOTAL; t += 256) {      // k fastest: 32 * p*p consecutive columns of a token row
+      const int kl = t % (TC * PP), jl = t / (TC * PP);
+      const int cl = kl / PP, uv = kl % PP;
+      if (j0 + jl < gw && c0 + cl < Cc) tok[(row0 + jl) * tok_ld + static_cast<long long>(c0) * PP + kl] = __float2bfloat16(tile[jl][cl][uv]);
+    }
+  } else {
+    for (int t = threadIdx.x; t < TOTAL; t += 256) {
+      const int kl = t % (TC * PP), jl = t / (TC * PP);
+      const int cl = kl / PP, uv = kl % PP;
+      float x = 0.f;
+      if (j0 + jl < gw && c0 + cl < Cc) x = __bfloat162float(tok[(row0 + jl) * tok_ld + static_cast<long long>(c0) * PP + kl]);
+      tile[jl][cl][uv] = x;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < TOTAL; t += 256) {
+      const int cl = t % TC, uv = (t / TC) % PP, jl = t / (TC * PP);
+      if (j0 + jl < gw && c0 + cl < Cc) *feat_at(jl, cl, uv) = from_f32<FT>(tile[jl][cl][uv]);
+    }
+  }
+}
+
+template <typename FT, bool FOLD>
+static int launch_patchify_fold_nhwc(FT* feat, __nv_bfloat16* tok, int B, int C, int H, int W, int p, long long tok_ld, cudaStream_t st) {
+  const int gh = H / p, gw = W / p;
+  const int tj = p >= 4 ? 16 : 32;
+  dim3 grid(B * gh * ((gw + tj - 1) / tj), (C + 31) / 32);
+  switch (p) {
+    case 1: patchify_fold_nhwc_kernel<FT, 1, FOLD><<<grid, 256, 0, st>>>(feat, tok, B, C, H, W, tok_ld); break;
+    case 2: patchify_fold_nhwc_kernel<FT, 2, FOLD><<<grid, 256, 0, st>>>(feat, tok, B, C, H, W, tok_ld); break;
+    case 4: patchify_fold_nhwc_kernel<FT, 4, FOLD><<<grid, 256, 0, st>>>(feat, tok, B, C, H, W, tok_ld); break;
+    default: return fail(-2, "channels_last patchify / fold supports patch sizes 1, 2, 4");
+  }
+  return 0;
+}
+
 template <typename FT, bool FOLD, bool ACC>
 static void launch_patchify_fold(FT* feat, __nv_bfloat16* tok, int B, int C, int H, int W, int p, long long tok_ld, cudaStream_t st) {
   const int gh = H / p, gw = W / p, K = C * p * p;
@@ -1102,6 +1170,14 @@ extern "C" int xf_patchify(const void* feat, int feat_dtype, void* tok, int64_t 
   if (!(p == 1 || p == 2 || p == 4 || p == 8) || H % p || W % p) return fail(-2, "xf_patchify: unsupported patch %d for %dx%d", p, H, W);
   if (tok_ld % 2 || (C * p * p) % 2) return fail(-4, "xf_patchify: token matrix width must be even");
   __nv_bfloat16* t = reinterpret_cast<__nv_bfloat16*>(tok);
+  if (feat_dtype & 4) {   // channels_last (NHWC) memory
+    int rc = (feat_dtype & 3) == 1 ? launch_patchify_fold_nhwc<float, false>(const_cast<float*>(reinterpret_cast<const float*>(feat)), t, B, C, H, W, p, tok_ld, stream)
+                                   : launch_patchify_fold_nhwc<__nv_bfloat16, false>(const_cast<__nv_bfloat16*>(reinterpret_cast<const __nv_bfloat16*>(feat)), t, B, C, H, W, p, tok_ld, stream);
+    if (rc) return rc;
+    g_launches.fetch_add(1);
+    XF_CUDA(cudaGetLastError());
+    return 0;
+  }
   if (feat_dtype == 1) launch_patchify_fold<float, false, false>(const_cast<float*>(reinterpret_cast<const float*>(feat)), t, B, C, H, W, p, tok_ld, stream);
   else if (feat_dtype == 0) launch_patchify_fold<__nv_bfloat16, false, false>(const_cast<__nv_bfloat16*>(reinterpret_cast<const __nv_bfloat16*>(feat)), t, B, C, H, W, p, tok_ld, stream);
   else return fail(-3, "xf_patchify: bad dtype");
@@ -1117,6 +1193,15 @@ extern "C" int xf_fold(const void* tok, int64_t tok_ld, void* feat, int feat_dty
   if (!(p == 1 || p == 2 || p == 4 || p == 8) || H % p || W % p) return fail(-2, "xf_fold: unsupported patch %d for %dx%d", p, H, W);
   if (tok_ld % 2 || (C * p * p) % 2) return fail(-4, "xf_fold: token matrix width must be even");
   __nv_bfloat16* t = const_cast<__nv_bfloat16*>(reinterpret_cast<const __nv_bfloat16*>(tok));
+  if (feat_dtype & 4) {   // channels_last (NHWC) memory
+    if (accumulate) return fail(-5, "xf_fold: accumulate is not supported for channels_last maps");
+    int rc = (feat_dtype & 3) == 1 ? launch_patchify_fold_nhwc<float, true>(reinterpret_cast<float*>(feat), t, B, C, H, W, p, tok_ld, stream)
+                                   : launch_patchify_fold_nhwc<__nv_bfloat16, true>(reinterpret_cast<__nv_bfloat16*>(feat), t, B, C, H, W, p, tok_ld, stream);
+    if (rc) return rc;
+    g_launches.fetch_add(1);
+    XF_CUDA(cudaGetLastError());
+    return 0;
+  }
   if (feat_dtype == 1) {
     if (accumulate) launch_patchify_fold<float, true, true>(reinterpret_cast<float*>(feat), t, B, C, H, W, p, tok_ld, stream);
     else launch_patchify_fold<float, true, false>(reinterpret_cast<float*>(feat), t, B, C, H, W, p, tok_ld, stream);

@@ -138,14 +138,22 @@ def _feat_dtype(t: torch.Tensor) -> int:
     raise _lib.XfError(f"feature map dtype {t.dtype} unsupported (fp32 or bf16)")
 
 
+def _feat_layout(feat: torch.Tensor, what: str) -> int:
+    """0 = contiguous NCHW, 4 = channels_last (NHWC memory); anything else is rejected (no hidden conversion copies)."""
+    if feat.is_contiguous():
+        return 0
+    if feat.dim() == 4 and feat.is_contiguous(memory_format=torch.channels_last):
+        return 4
+    raise _lib.XfError(f"{what}: feature map must be contiguous NCHW or channels_last")
+
+
 def patchify(feat: torch.Tensor, p: int, tok: torch.Tensor) -> torch.Tensor:
-    """feat [B,C,H,W] (contiguous NCHW, fp32/bf16) -> tok bf16 [B*n, C*p*p] (utils.py:35-39 order)."""
+    """feat [B,C,H,W] (contiguous NCHW or channels_last, fp32/bf16) -> tok bf16 [B*n, C*p*p] (utils.py:35-39 order)."""
     B, Cc, H, W = feat.shape
-    if not feat.is_contiguous():
-        raise _lib.XfError("patchify: feature map must be contiguous NCHW")
+    layout = _feat_layout(feat, "patchify")
     _req(tok, torch.bfloat16, "tok")
     with _Prof("patchify_fold", 0.0, feat.numel() * (feat.element_size() + 2.0)):
-        check(lib().xf_patchify(_ptr(feat), _feat_dtype(feat), _ptr(tok), C.c_int64(tok.stride(0)), B, Cc, H, W, p, _stream()),
+        check(lib().xf_patchify(_ptr(feat), _feat_dtype(feat) | layout, _ptr(tok), C.c_int64(tok.stride(0)), B, Cc, H, W, p, _stream()),
               "xf_patchify")
     return tok
 
@@ -153,11 +161,10 @@ def patchify(feat: torch.Tensor, p: int, tok: torch.Tensor) -> torch.Tensor:
 def fold(tok: torch.Tensor, feat: torch.Tensor, p: int, accumulate: bool = False) -> torch.Tensor:
     """tok bf16 [B*n, C*p*p] -> feat [B,C,H,W] (utils.py:42-46)."""
     B, Cc, H, W = feat.shape
-    if not feat.is_contiguous():
-        raise _lib.XfError("fold: feature map must be contiguous NCHW")
+    layout = _feat_layout(feat, "fold")
     _req(tok, torch.bfloat16, "tok")
     with _Prof("patchify_fold", 0.0, feat.numel() * (feat.element_size() + 2.0)):
-        check(lib().xf_fold(_ptr(tok), C.c_int64(tok.stride(0)), _ptr(feat), _feat_dtype(feat), int(accumulate), B, Cc, H, W, p,
+        check(lib().xf_fold(_ptr(tok), C.c_int64(tok.stride(0)), _ptr(feat), _feat_dtype(feat) | layout, int(accumulate), B, Cc, H, W, p,
                             _stream()), "xf_fold")
     return feat
 
