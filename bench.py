@@ -593,13 +593,20 @@ def run_ours(args):
         top = next(iter(kernels))
         kname = {"gemm_fwd": "gemm_bf16_tcgen05_kernel (forward x W^T)", "gemm_dgrad": "gemm_bf16_tcgen05_kernel (dgrad)",
                  "gemm_wgrad": "gemm_bf16_tcgen05_kernel (wgrad, split-K)", "attn_fwd": "attn_fwd_tcgen05_kernel",
-                 "attn_bwd": "attn_bwd2_tcgen05_kernel<MODE_DQ|MODE_DK|MODE_DV> (one xf_attn_bwd call = 3 passes)"}.get(top, top)
+                 "attn_bwd": ("xf_attn_bwd = attn_bwd2_tcgen05_kernel<MODE_DVS> (scores once, dV on chip, E -> scratch) + two batched "
+                              "gemm_bf16_tcgen05_kernel (dQ = E^T K, dK = E Q)") if os.environ.get("XF_ATTN_BWD_WS", "1") != "0"
+                 else "attn_bwd2_tcgen05_kernel<MODE_DQ|MODE_DK|MODE_DV> (one xf_attn_bwd call = 3 passes)"}.get(top, top)
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")
-        if os.path.isfile(tpath):   # DRAM bytes of the dominant kernel from the committed ncu --set full capture (level-0 launch)
+        # DRAM bytes per call of the dominant kernel family at the level-0 shape: ncu cannot run inside this process, so the
+        # figure comes from the committed `ncu --set full` capture of the SAME kernels (tools/profile_kernels.py, regenerated
+        # per round by tools/make_traffic_json.py); `traffic_source` names it.  null when no capture is committed.
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic_r2.json")
+        traffic_source = None
+        if os.path.isfile(tpath):
             with open(tpath) as tf:
                 tfam = json.load(tf)["families"].get(top.split("_")[0] if top.startswith("gemm") else top, {})
             traffic = tfam.get("traffic_bytes_per_call", tfam.get("traffic_bytes_per_launch"))
+            traffic_source = "profiles/ncu_traffic_r2.json (ncu --set full of tools/profile_kernels.py, level-0 shape, B = 13)"
         if "tflops" in kernels[top]:
             roofline = {"bound": "tensor", "kernel": kname, "achieved": kernels[top]["tflops"], "peak": peaks["tflops"],
                         "unit": "TFLOP/s", "frac": round(kernels[top]["tflops"] / peaks["tflops"], 4), "traffic": traffic,
@@ -614,6 +621,7 @@ def run_ours(args):
                        for (h, ww), C, p in zip(level_shapes(w), w["channels"], w["patch"]))
         # fwd+bwd = 3 F_fwd minus the patch-embed dgrad (visual inputs do not require grad: frozen backbone)
         step_flops = (3.0 * f_fwd - pe_dgrad) if train else f_fwd
+        roofline["traffic_source"] = traffic_source
         roofline["whole_path_tflops"] = round(value / world * step_flops / 1e12, 2)
         roofline["whole_path_frac"] = round(value / world * step_flops / 1e12 / peaks["tflops"], 4)
 

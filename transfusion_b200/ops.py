@@ -21,12 +21,23 @@ PROFILE = None
 PROFILE_DETAIL = bool(int(_os.environ.get("XF_PROFILE_DETAIL", "0")))
 
 
+# dev aid (tools/ablate.sh): XF_ABLATE="fam1,fam2" turns the launches of those op families into no-ops, so the difference in
+# step time is the family's TRUE marginal cost inside the overlapped multi-stream schedule (results are garbage, of course)
+ABLATE = frozenset(x for x in _os.environ.get("XF_ABLATE", "").split(",") if x)
+
+
+class _Skip(Exception):
+    pass
+
+
 class _Prof:
     __slots__ = ("fam", "flops", "nbytes", "e0")
 
     def __init__(self, fam, flops=0.0, nbytes=0.0):
         self.fam, self.flops, self.nbytes = fam, flops, nbytes
         self.e0 = None
+        if ABLATE and fam.split("[")[0] in ABLATE:
+            raise _Skip()
 
     def __enter__(self):
         if PROFILE is not None:
@@ -453,3 +464,20 @@ def softmax_rows_f32(s: torch.Tensor, Sk: int, kpm: Optional[torch.Tensor], scal
     B, H, Sq, Sp = s.shape
     with _Prof("fp32_mode", 0.0, 8.0 * s.numel()):
         check(lib().xf_softmax_rows_f32(_ptr(s), B, H, Sq, Sk, Sp, _ptr(kpm), C.c_float(scale), _stream()), "xf_softmax_rows_f32")
+
+
+if ABLATE:   # dev aid only: swallow the skip signal of _Prof for the void-returning hot-path ops
+    import functools as _ft
+
+    def _ablatable(fn):
+        @_ft.wraps(fn)
+        def wrapper(*a, **k):
+            try:
+                return fn(*a, **k)
+            except _Skip:
+                return None
+        return wrapper
+
+    for _name in ("gemm", "patchify", "fold", "lang_rows_fwd", "lang_rows_bwd", "layernorm_fwd", "layernorm_bwd", "colsum", "cast_pad",
+                  "cast_pad_multi", "unpad_add", "attn_delta", "attn_fwd", "attn_bwd", "rows_gather"):
+        globals()[_name] = _ablatable(globals()[_name])
