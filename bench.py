@@ -682,7 +682,7 @@ def run_sweep(args):
     torch.cuda.set_device(dev)
     peaks = load_peaks()
     B = args.batch or 16
-    for name in ("ego4dv2", "ego4dv1"):
+    for name in args.sweep_widths.split(","):
         model = build_workload_module(name, device=dev, dropout=not args.no_dropout, seed=0)
         model.train(True)
         for k, p in model.named_parameters():
@@ -760,6 +760,7 @@ def main():
                     help="N > 1: exchange the gradient arenas as bf16 (default: fp32 like the reference's DDP)")
     ap.add_argument("--bf16-e2e", action="store_true", help="run the extra bf16-feature end-to-end pass for N > 1 too")
     ap.add_argument("--sweep", action="store_true", help="BASELINE config 5: language length x image size x width, B = 16")
+    ap.add_argument("--sweep-widths", default="ego4dv2,ego4dv1", help="which widths the sweep covers (D = 896 / 712)")
     args = ap.parse_args()
     if args.sweep:
         run_sweep(args)

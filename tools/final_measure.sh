@@ -24,4 +24,4 @@ b reference_gpu --impl reference-gpu --steps 5 --warmup 3
 $T python bench.py --sweep --steps 4 --warmup 2 > gpurun_out/final_sweep.jsonl 2> gpurun_out/final_sweep.err; echo "sweep rc=$? lines=$(wc -l < gpurun_out/final_sweep.jsonl)"
 # ncu: launch list of one bench step, then --set full of one launch of each hot kernel (tools/profile_kernels.py, 2nd iteration)
 $T ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/final_launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-bf16-e2e > /dev/null 2>&1; echo "launch list rc=$?"
-$T ncu --set full --clock-control none --import-source on -k regex:"xf::" --launch-skip 13 -c 13 -f -o gpurun_out/final_full python tools/profile_kernels.py > gpurun_out/final_full.log 2>&1; echo "ncu full rc=$? $(ls -la gpurun_out/final_full.ncu-rep 2>/dev/null | awk '{print $5}')"
+$T ncu --set full --clock-control none --import-source on -k regex:"tcgen05|layernorm|attn_delta" --launch-skip 13 -c 13 -f -o gpurun_out/final_full python tools/profile_kernels.py > gpurun_out/final_full.log 2>&1; echo "ncu full rc=$? $(ls -la gpurun_out/final_full.ncu-rep 2>/dev/null | awk '{print $5}')"
