@@ -5,8 +5,9 @@ attention masks, and the trainable out_mlp Linear(384 -> D) forward + backward.
 Tolerance: rel-Frobenius <= 1.5e-2 on the valid tokens after 12 layers.  The kernels keep every activation in bf16 between
 launches (the fusion stack's layout: 5e-3 after its 4 layers, growing ~ sqrt(layers)), whereas torch.autocast -- whose own
 error on the same inputs is asserted to stay below ours, 2.7e-3 -- keeps the residual stream and the LayerNorms in fp32.
-Inference (eval) only: in training the reference leaves the encoder's LayerNorm parameters trainable and its dropouts on
-(freeze_all_but_bn, modeling/commons.py:33-42), which needs the encoder backward; bert_encoder_forward raises there."""
+Training: the reference leaves the encoder's LayerNorm parameters trainable and its dropouts on (freeze_all_but_bn,
+modeling/commons.py:33-42): the LayerNorm gradients through all 12 layers are checked against HF's autograd (dropout
+probabilities 0 for a deterministic reference; dropout-on runs are checked for reproducibility per seed)."""
 import pytest
 import torch
 
@@ -78,16 +79,78 @@ def test_out_mlp_and_token_wrapper_forward_backward():
     assert rel_fro(gw, w2.grad) < 1e-2 and rel_fro(gb, b2.grad) < 1e-2
 
 
-def test_trainable_encoder_is_rejected_loudly():
-    bert = _minilm(layers=1)
+def _unfreeze_layernorms(bert):
     for mod_ in bert.modules():
         if isinstance(mod_, torch.nn.LayerNorm):
             for p in mod_.parameters():
-                p.requires_grad_(True)    # what freeze_all_but_bn leaves trainable in the reference
+                p.requires_grad_(True)    # what freeze_all_but_bn leaves trainable in the reference (modeling/commons.py:33-42)
+
+
+def test_training_state_of_the_reference_layernorm_gradients_match_huggingface():
+    """Matrices frozen, LayerNorms trainable (the reference's training state), dropout probabilities 0 so HF's autograd is a
+    deterministic reference: hidden states and every LayerNorm gradient through all 12 layers, anchored on HF's own
+    autocast-bf16 error."""
+    from transformers import BertConfig, BertModel
+    cfg = BertConfig(vocab_size=30522, hidden_size=384, num_hidden_layers=12, num_attention_heads=12, intermediate_size=1536,
+                     max_position_embeddings=512, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    torch.manual_seed(0)
+    bert = BertModel(cfg, add_pooling_layer=False).to(DEV)
+    for p in bert.parameters():
+        p.requires_grad_(False)
+    _unfreeze_layernorms(bert)
+    bert.train()
+    B, L = 3, 48
+    g = torch.Generator(device=DEV).manual_seed(5)
+    ids = torch.randint(0, 30522, (B, L), device=DEV, generator=g)
+    am = torch.ones(B, L, dtype=torch.long, device=DEV)
+    am[1, 30:] = 0
+    cot = torch.randn(B, L, 384, device=DEV, generator=g) * am[..., None]
+    ln_params = {k: p for k, p in bert.named_parameters() if p.requires_grad}
+    assert len(ln_params) == 2 + 4 * 12
+
+    def run(fn):
+        for p in ln_params.values():
+            p.grad = None
+        out = fn()
+        (out.float() * cot).sum().backward()
+        return out.detach().float(), {k: p.grad.clone() for k, p in ln_params.items()}
+
+    ref_o, ref_g = run(lambda: bert(input_ids=ids, attention_mask=am).last_hidden_state)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        ac_o, ac_g = run(lambda: bert(input_ids=ids, attention_mask=am).last_hidden_state)
+    got_o, got_g = run(lambda: bert_encoder_forward(bert, ids, am))
+    v = am.bool()
+    assert rel_fro(got_o[v], ref_o[v]) < 1.5e-2
+    worst = max((rel_fro(got_g[k], ref_g[k]), k) for k in ref_g)
+    worst_ac = max(rel_fro(ac_g[k], ref_g[k]) for k in ref_g)
+    assert worst[0] < max(2e-2, 2 * worst_ac), (worst, worst_ac)
+
+
+def test_training_dropout_runs_and_is_seed_reproducible():
+    bert = _minilm(layers=2)
+    _unfreeze_layernorms(bert)
+    bert.train()
+    ids = torch.randint(0, 30522, (2, 16), device=DEV)
+    outs = []
+    for seed in (7, 7, 8):
+        torch.manual_seed(seed)
+        o = bert_encoder_forward(bert, ids)
+        o.sum().backward()
+        outs.append(o.detach().clone())
+        assert all(torch.isfinite(p.grad).all() for p in bert.parameters() if p.requires_grad)
+    assert torch.equal(outs[0], outs[1]) and not torch.equal(outs[0], outs[2])
+    bert.eval()
+    with torch.no_grad():
+        e = bert_encoder_forward(bert, ids)
+    assert not torch.equal(e, outs[0])      # eval: no dropout
+
+
+def test_other_trainable_encoder_weights_are_rejected_loudly():
+    bert = _minilm(layers=1)
+    bert.encoder.layer[0].output.dense.weight.requires_grad_(True)     # unfreeze_embeddings()-style fine-tuning (train_ep >= 0)
     ids = torch.randint(0, 30522, (1, 8), device=DEV)
     with pytest.raises(NotImplementedError):
-        with torch.enable_grad():
-            bert_encoder_forward(bert, ids)
+        bert_encoder_forward(bert, ids)
 
 
 def test_xflinear_input_gradient_and_cpu_rejection():
