@@ -653,6 +653,7 @@ def run_ours(args):
                           "attn_bwd": "5-unit schedule (scores once; bf16 [B,H,S,S] scratch)" if os.environ.get("XF_ATTN_BWD_WS", "1") != "0"
                                       else "3 on-chip passes (8 units)"},
                 "clocks": clocks, "gpu_launches": int(launches),
+                "tma_descriptor_cache": {"hits": int(_lib.lib().xf_tmap_cache_stats(0)), "encoded": int(_lib.lib().xf_tmap_cache_stats(1))},
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                         # achieved host->device rate of THIS rank's input copies (CUDA events on the copy stream, median
@@ -688,7 +689,8 @@ def run_sweep(args):
         for k, p in model.named_parameters():
             if k.endswith("heatmap_token"):
                 p.requires_grad_(False)
-        for image in SWEEP_IMAGES:
+        images = SWEEP_IMAGES if not args.sweep_images else [tuple(int(v) for v in t.split("x")) for t in args.sweep_images.split(",")]
+        for image in images:
             w = copy.deepcopy(WORKLOADS[name])
             w["image"] = image
             g = torch.Generator(device=dev).manual_seed(7)
@@ -760,6 +762,7 @@ def main():
                     help="N > 1: exchange the gradient arenas as bf16 (default: fp32 like the reference's DDP)")
     ap.add_argument("--bf16-e2e", action="store_true", help="run the extra bf16-feature end-to-end pass for N > 1 too")
     ap.add_argument("--sweep", action="store_true", help="BASELINE config 5: language length x image size x width, B = 16")
+    ap.add_argument("--sweep-images", default="", help="restrict the sweep to these padded image sizes, e.g. 704x896,768x1024")
     ap.add_argument("--sweep-widths", default="ego4dv2,ego4dv1", help="which widths the sweep covers (D = 896 / 712)")
     args = ap.parse_args()
     if args.sweep:

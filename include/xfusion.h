@@ -30,6 +30,9 @@ int xf_version(void);
 const char* xf_last_error(void);
 /* number of kernel launches issued through this library since load (bench.py: gpu_launches) */
 int64_t xf_launch_count(void);
+/* TMA descriptor cache (descriptors are keyed by address / extents / pitches / box / swizzle under a mutex): which = 0 hits,
+ * 1 misses (descriptors actually encoded) since load */
+int64_t xf_tmap_cache_stats(int which);
 
 /* ------------------------------------------------------------------------------------------
  * GEMM  D[M,N] (+)= A(M x K) * B(N x K)^T  on tcgen05 tensor cores (bf16 in, fp32 accumulate

@@ -150,7 +150,7 @@ def lib():
         for name in EXPORTS:
             if name in ("xf_version", "xf_last_error", "xf_launch_count"):
                 continue
-            if name == "xf_attn_bwd_workspace_bytes":
+            if name in ("xf_attn_bwd_workspace_bytes", "xf_tmap_cache_stats"):
                 getattr(L, name).restype = C.c_int64
                 continue
             fn = getattr(L, name)
@@ -161,7 +161,7 @@ def lib():
 
 # every symbol include/xfusion.h declares (checked by tests/test_cabi.py)
 EXPORTS = [
-    "xf_version", "xf_last_error", "xf_launch_count", "xf_gemm", "xf_set_gemm_cta_cap",
+    "xf_version", "xf_last_error", "xf_launch_count", "xf_tmap_cache_stats", "xf_gemm", "xf_set_gemm_cta_cap",
     "xf_patchify", "xf_fold", "xf_lang_rows_fwd", "xf_lang_rows_bwd",
     "xf_layernorm_fwd", "xf_layernorm_bwd", "xf_colsum", "xf_cast_pad", "xf_cast_pad_multi", "xf_unpad_add", "xf_bf16_to_f32",
     "xf_attn_delta", "xf_attn_fwd", "xf_attn_bwd", "xf_attn_bwd_workspace_bytes", "xf_rows_gather",

@@ -2,6 +2,8 @@
 #include "ptx.cuh"
 
 #include <mutex>
+#include <string.h>
+#include <unordered_map>
 
 #include "../../include/xfusion.h"
 
@@ -24,6 +26,54 @@ EncodeTiledFn get_encode_tiled() {
   return fn;
 }
 
+// ---- descriptor cache ("lazily created TMA descriptors keyed by (ptr, shape) and guarded by a mutex").
+// A tensor map is a pure function of (address, extents, pitches, box, swizzle): a step re-encodes the same ~1300 maps, so
+// they are looked up by a 64-bit hash of those fields and verified field by field; the table is dropped when it grows past
+// 8192 entries (shapes changed) -- never stale: the same key always encodes the same descriptor.
+namespace {
+struct TmapKey {
+  const void* ptr;
+  uint32_t rank, swz;
+  uint64_t gdim[4], gstr[3];
+  uint32_t box[4];
+  bool operator==(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) == 0; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+    uint64_t h = 0x9E3779B97F4A7C15ull;
+    for (size_t i = 0; i < sizeof(TmapKey) / 8; ++i) { h ^= w[i]; h *= 0xff51afd7ed558ccdull; h ^= h >> 32; }
+    return static_cast<size_t>(h);
+  }
+};
+std::mutex g_tmap_mu;
+std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+std::atomic<int64_t> g_tmap_hits{0}, g_tmap_misses{0};
+}  // namespace
+
+static CUresult encode_cached(EncodeTiledFn enc, CUtensorMap* out, cuuint32_t rank, const void* ptr, const cuuint64_t* gdim,
+                              const cuuint64_t* gstr, const cuuint32_t* box, const cuuint32_t* estr, CUtensorMapSwizzle swz) {
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.ptr = ptr; key.rank = rank; key.swz = static_cast<uint32_t>(swz);
+  for (cuuint32_t i = 0; i < rank; ++i) { key.gdim[i] = gdim[i]; key.box[i] = box[i]; }
+  for (cuuint32_t i = 0; i + 1 < rank; ++i) key.gstr[i] = gstr[i];
+  {
+    std::lock_guard<std::mutex> lock(g_tmap_mu);
+    auto it = g_tmap_cache.find(key);
+    if (it != g_tmap_cache.end()) { *out = it->second; g_tmap_hits.fetch_add(1, std::memory_order_relaxed); return CUDA_SUCCESS; }
+  }
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == CUDA_SUCCESS) {
+    g_tmap_misses.fetch_add(1, std::memory_order_relaxed);
+    std::lock_guard<std::mutex> lock(g_tmap_mu);
+    if (g_tmap_cache.size() >= 8192) g_tmap_cache.clear();
+    g_tmap_cache.emplace(key, *out);
+  }
+  return r;
+}
+
 int make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint32_t box_cols, uint32_t box_rows, int swizzle_bytes) {
   EncodeTiledFn enc = get_encode_tiled();
@@ -38,9 +88,7 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t
   cuuint64_t gstr[1] = {ld * 2};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz2, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = encode_cached(enc, out, 2, ptr, gdim, gstr, box, estr, swz2);
   if (r != CUDA_SUCCESS) return fail(-14, "cuTensorMapEncodeTiled failed: %d (rows=%llu cols=%llu ld=%llu)", (int)r,
                                      (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld);
   return 0;
@@ -58,9 +106,7 @@ int make_tmap_3d_bf16(CUtensorMap* out, const void* ptr, uint64_t batch, uint64_
   cuuint64_t gstr[2] = {ld * 2, rows * ld * 2};
   cuuint32_t box[3] = {box_cols, box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = encode_cached(enc, out, 3, ptr, gdim, gstr, box, estr, swz);
   if (r != CUDA_SUCCESS) return fail(-14, "cuTensorMapEncodeTiled(3d) failed: %d", (int)r);
   return 0;
 }
@@ -85,8 +131,7 @@ int make_tmap_4d_bf16(CUtensorMap* out, const void* ptr, uint64_t nb1, uint64_t 
   cuuint64_t gstr[3] = {ld * 2, bs2 * 2, bs1 * 2};
   cuuint32_t box[4] = {box_cols, box_rows, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = encode_cached(enc, out, 4, ptr, gdim, gstr, box, estr, swz);
   if (r != CUDA_SUCCESS) return fail(-14, "cuTensorMapEncodeTiled(4d batched) failed: %d", (int)r);
   return 0;
 }
@@ -102,9 +147,7 @@ int make_tmap_chunks_bf16(CUtensorMap* out, const void* ptr, uint64_t batch, uin
   cuuint64_t gstr[3] = {ld * 2, 64, rows * ld * 2};
   cuuint32_t box[4] = {32, box_rows, box_chunks, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = encode_cached(enc, out, 4, ptr, gdim, gstr, box, estr, CU_TENSOR_MAP_SWIZZLE_64B);
   if (r != CUDA_SUCCESS) return fail(-14, "cuTensorMapEncodeTiled(4d chunks) failed: %d", (int)r);
   return 0;
 }
@@ -120,9 +163,7 @@ int make_tmap_rowblock_bf16(CUtensorMap* out, const void* ptr, uint64_t rows, ui
   cuuint64_t gstr[2] = {ld * 2, static_cast<cuuint64_t>(bc) * 2};
   cuuint32_t box[3] = {bc, box_rows, static_cast<cuuint32_t>(cols / bc)};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = encode_cached(enc, out, 3, ptr, gdim, gstr, box, estr, CU_TENSOR_MAP_SWIZZLE_NONE);
   if (r != CUDA_SUCCESS) return fail(-14, "cuTensorMapEncodeTiled(row block) failed: %d", (int)r);
   return 0;
 }
@@ -164,4 +205,5 @@ extern "C" {
 int xf_version(void) { return XF_ABI_VERSION; }
 const char* xf_last_error(void) { return xf::g_err; }
 int64_t xf_launch_count(void) { return xf::g_launches.load(); }
+int64_t xf_tmap_cache_stats(int which) { return which == 0 ? xf::g_tmap_hits.load() : which == 1 ? xf::g_tmap_misses.load() : 0; }
 }
