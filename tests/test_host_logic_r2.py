@@ -70,6 +70,15 @@ def test_mode_switch_drops_the_weight_cache():
                               narr_pooling_layer=ref_loader.PassThroughPooling(), precision="fp16")
 
 
+def test_constructor_signature_matches_reference_keywords():
+    import inspect
+    sig = inspect.signature(CrossFusionBoxWrapper.__init__)
+    assert list(sig.parameters)[:5] == ["self", "rcnn_model", "cross_layer_args", "narr_embed_args", "criterion"]   # cross_f_box_wrapper.py:42-44
+    assert sig.parameters["criterion"].default is None
+    with pytest.raises(ValueError):
+        CrossFusionBoxWrapper(ref_loader.FakeRCNN([(4, 4)], [8], 9, 6))   # the reference's defaults are unconstructible
+
+
 def test_fpn_from_laterals_equals_torchvision_fpn():
     from torchvision.ops import FeaturePyramidNetwork
     from torchvision.ops.feature_pyramid_network import LastLevelMaxPool

@@ -36,11 +36,17 @@ def _default_pooling_factory(narr_embed_args, cross_layer_args):
 
 
 class CrossFusionBoxWrapper(nn.Module):
-    def __init__(self, rcnn_model, cross_layer_args, narr_embed_args, criterion=None, narr_pooling_layer=None, precision=None):
+    def __init__(self, rcnn_model, cross_layer_args=None, narr_embed_args=None, criterion=None, narr_pooling_layer=None, precision=None):
         """precision: None / "bf16" = the tensor-core path (bf16 operands, fp32 accumulate; training and inference);
         "fp32" (or XF_PRECISION=fp32) = the forward-only fp32-tolerance mode of cross_fusion/level_fp32.py (3-way bf16 split
         GEMMs, ~1e-5 relative to the fp32 reference; the reference's Ego4Dv2 config runs precision 32)."""
         super().__init__()
+        if cross_layer_args is None or narr_embed_args is None:
+            # the reference's keyword defaults (cross_f_wrapper.py:16-54: type "asymmetric", narr_out_mode "embedding", no
+            # fpn_features) select a variant its own box wrapper cannot construct (SURVEY Appendix D; KeyError at :60 there);
+            # same positional / keyword signature here, but an explicit message instead
+            raise ValueError("CrossFusionBoxWrapper: pass cross_layer_args (the merged fusion YAML, run_experiment.py:75-77,100) and "
+                             "narr_embed_args; the reference's defaults describe the unconstructible asymmetric variant")
         self.precision = precision or _os.environ.get("XF_PRECISION", "bf16")
         if self.precision not in ("bf16", "fp32"):
             raise ValueError("precision must be 'bf16' or 'fp32'")
