@@ -230,7 +230,12 @@ class CrossFusionBoxWrapper(nn.Module):
         cache = self.__dict__.setdefault("_xf_streams", {})
         dev = ref.device.index
         if dev not in cache:
-            cache[dev] = [torch.cuda.Stream(device=ref.device) for _ in range(len(self.fpn_features_idx))]
+            # XF_STREAM_PRIO="a,b,c,d": CUDA stream priority per level (-1 = high: its thread blocks are placed first when
+            # SMs free up); default: all equal
+            prio = [int(x) for x in _os.environ.get("XF_STREAM_PRIO", "").split(",") if x.strip()]
+            n_lv = len(self.fpn_features_idx)
+            prio = (prio + [0] * n_lv)[:n_lv]
+            cache[dev] = [torch.cuda.Stream(device=ref.device, priority=prio[i]) for i in range(n_lv)]
             # parameter gradients are produced on the side streams and accumulated on the caller's stream: the
             # engine inserts the synchronisation; the mismatch it warns about is intended
             quiet = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
