@@ -684,6 +684,12 @@ def run_ours(args):
             part = partial_e2e()
             if e2e_value is not None and not stall.get("in_e2e"):
                 note = "the extra bf16-feature end-to-end pass stalled; the fp32 `e2e` above is complete"
+            elif stall.get("pre") and (part is None or part[0] < 6):
+                n_pre, ms_pre_ = stall["pre"]
+                e2e_value = world * B * n_pre / (ms_pre_ / 1e3)
+                ms_e2e = ms_pre_ * args.steps / n_pre
+                note = (f"the {args.steps}-step end-to-end pass stalled; value from the preceding fully synchronised {n_pre}-step pass "
+                        f"(max over ranks); the device-timed fields above are complete")
             elif part is not None:
                 n_done, ms_part = part
                 e2e_value = world * B * n_done / (ms_part / 1e3)
@@ -708,6 +714,11 @@ def run_ours(args):
     prefetch(0)
     for _ in range(2):
         step_e2e()
+    if world >= 8 and args.steps > 6:
+        # the stall has only been seen on 8 GPUs: bank a short, fully synchronised (max over ranks) measurement first, so a
+        # stall in the long pass still leaves a complete end-to-end number behind (the guard reports it with a note)
+        ms_pre = timed(step_e2e, 6)
+        stall["pre"] = (6, ms_pre)
     stall["in_e2e"] = True
     ms_e2e = timed(step_e2e, args.steps)
     stall["in_e2e"] = False
